@@ -1,0 +1,479 @@
+"""pockettts-b200: B200-native `native-cuda` synthesis backend for go-pocket-tts.
+
+This package is the host-side mirror of the reference's `tts.Runtime` interface
+(/root/reference internal/tts/runtime.go:42-45) on top of the C ABI declared in
+include/pockettts_cuda.h.  It exists so the parity tests and the benchmark can
+drive the CUDA library the way the Go backend would; the product is the shared
+library `libpockettts_cuda.so` (sm_100a kernels + engine + scheduler).
+
+There is no CPU fallback: if the CUDA library is missing or no sm_100 device is
+present, construction fails loudly.  (The directory name contains hyphens, so it
+is loaded through `__graft_entry__.package()` as module `pockettts_b200`.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "libpockettts_cuda.so")
+CSRC = ["gemm.cu", "attention.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "safetensors.cpp"]
+
+PTTS_OK, PTTS_EINVAL, PTTS_ECUDA, PTTS_ENOMEM, PTTS_ESTATE, PTTS_ECANCELED = 0, -1, -2, -3, -4, -5
+PTTS_REQ_NO_PCM_D2H = 1
+LATENT_DIM = 32
+SAMPLES_PER_FRAME = 1920
+SAMPLE_RATE = 24000
+
+
+class NativeCudaError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(msg)
+        self.status = status
+
+
+# ---------------------------------------------------------------------------
+# build
+# ---------------------------------------------------------------------------
+def nvcc_command(out: str = LIB_PATH) -> list[str]:
+    srcs = [os.path.join(PKG_DIR, "csrc", s) for s in CSRC]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", out, *srcs]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree shared library."""
+    srcs = [os.path.join(PKG_DIR, "csrc", s) for s in os.listdir(os.path.join(PKG_DIR, "csrc"))]
+    srcs.append(os.path.join(REPO_ROOT, "include", "pockettts_cuda.h"))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in srcs)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+# ---------------------------------------------------------------------------
+# ctypes mirror of include/pockettts_cuda.h
+# ---------------------------------------------------------------------------
+class PttsConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("device", "max_batch", "page_tokens", "max_seq_tokens", "kv_pages",
+                                         "max_frames", "mimi_group_frames", "max_prefill_tokens", "flags")]
+
+
+class PttsGenCfg(C.Structure):
+    _fields_ = [("temperature", C.c_double), ("eos_threshold", C.c_double), ("max_steps", C.c_int32),
+                ("estimated_max_steps", C.c_int32), ("lsd_decode_steps", C.c_int32),
+                ("frames_after_eos", C.c_int32), ("force_eos_step", C.c_int32), ("flags", C.c_int32)]
+
+
+class PttsVoiceLayer(C.Structure):
+    _fields_ = [("cache", C.POINTER(C.c_float)), ("cache_tokens", C.c_int32), ("offset", C.c_int32)]
+
+
+class PttsVoiceKV(C.Structure):
+    _fields_ = [("layers", C.POINTER(PttsVoiceLayer)), ("n_layers", C.c_int32)]
+
+
+class PttsModelInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "d_model", "n_heads", "head_dim", "n_layers", "ffn_dim", "flow_dim", "flow_depth", "latent_dim",
+        "n_bins", "mimi_dim", "mimi_heads", "mimi_layers", "mimi_ffn_dim", "mimi_context",
+        "samples_per_frame", "mimi_steps_per_latent")] + [(n, C.c_int64) for n in (
+            "params_ar", "params_mimi", "macs_ar_frame", "macs_mimi_frame", "macs_prefill_token")]
+
+
+class PttsStageTimes(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")] + \
+               [(n, C.c_int64) for n in ("prefill_tokens", "step_rows", "steps", "mimi_frames", "kernel_launches")]
+
+
+class PttsResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_frames", C.c_int32), ("n_samples", C.c_int64),
+                ("queue_ms", C.c_double), ("first_frame_ms", C.c_double), ("total_ms", C.c_double)]
+
+
+EXPORTS = [
+    "ptts_last_error", "ptts_version", "ptts_device_count", "ptts_create", "ptts_destroy", "ptts_load_tensor",
+    "ptts_load_safetensors", "ptts_finalize_weights", "ptts_model_info_get", "ptts_generate_audio",
+    "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
+    "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
+    "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeCudaError(PTTS_ESTATE, f"native-cuda runtime unavailable: {LIB_PATH} not built "
+                                           f"(run __graft_entry__.build())")
+    L = C.CDLL(LIB_PATH)
+    fp, ip, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    vp = C.c_void_p
+    L.ptts_last_error.restype = C.c_char_p
+    L.ptts_version.restype = C.c_char_p
+    L.ptts_device_count.restype = C.c_int
+    L.ptts_create.argtypes = [C.POINTER(PttsConfig), C.POINTER(vp)]
+    L.ptts_destroy.argtypes = [vp]
+    L.ptts_destroy.restype = None
+    L.ptts_load_tensor.argtypes = [vp, C.c_char_p, i64p, C.c_int32, C.c_int32, vp]
+    L.ptts_load_safetensors.argtypes = [vp, C.c_char_p]
+    L.ptts_finalize_weights.argtypes = [vp]
+    L.ptts_model_info_get.argtypes = [vp, C.POINTER(PttsModelInfo)]
+    gen_args = [vp, i64p, C.c_int32, fp, C.c_int32, C.POINTER(PttsVoiceKV), C.POINTER(PttsGenCfg), fp,
+                C.c_int32, fp, C.c_int64]
+    L.ptts_generate_audio.argtypes = gen_args + [C.POINTER(PttsResult)]
+    L.ptts_submit.argtypes = gen_args + [i64p]
+    L.ptts_wait.argtypes = [vp, C.c_int64, C.POINTER(PttsResult)]
+    L.ptts_cancel.argtypes = [vp, C.c_int64]
+    L.ptts_ticket_latents.argtypes = [vp, C.c_int64, fp, fp, C.c_int32]
+    L.ptts_ticket_release.argtypes = [vp, C.c_int64]
+    L.ptts_seq_open.argtypes = [vp, i64p, C.c_int32, fp, C.c_int32, C.POINTER(PttsVoiceKV), C.c_int32,
+                                C.POINTER(vp)]
+    L.ptts_step.argtypes = [vp, C.POINTER(vp), C.c_int32, fp, fp, C.c_int32, fp, fp]
+    L.ptts_decode.argtypes = [vp, vp, C.c_int32, C.c_int32, fp]
+    L.ptts_decode_latents.argtypes = [vp, fp, ip, C.c_int32, fp]
+    L.ptts_seq_frames.argtypes = [vp]
+    L.ptts_seq_kv_len.argtypes = [vp]
+    L.ptts_seq_read_kv.argtypes = [vp, vp, C.c_int32, C.c_int32, fp]
+    L.ptts_seq_close.argtypes = [vp, vp]
+    L.ptts_stage_times_get.argtypes = [vp, C.POINTER(PttsStageTimes), C.c_int32]
+    L.ptts_debug_fetch.argtypes = [vp, C.c_char_p, fp, C.c_int64]
+    L.ptts_debug_fetch.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _fptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise NativeCudaError(rc, lib().ptts_last_error().decode("utf-8", "replace"))
+
+
+# ---------------------------------------------------------------------------
+# reference-shaped configuration objects
+# ---------------------------------------------------------------------------
+@dataclass
+class VoiceEmbedding:
+    """tts.VoiceEmbedding (internal/tts/runtime.go:11-15): data [1,T,D] or [T,D]."""
+    data: np.ndarray
+
+    def rows(self) -> np.ndarray:
+        a = np.ascontiguousarray(self.data, dtype=np.float32)
+        if a.ndim == 3:
+            if a.shape[0] != 1:
+                raise ValueError("voice embedding batch must be 1")
+            a = a[0]
+        if a.ndim != 2:
+            raise ValueError(f"voice embedding has {a.ndim}D shape, expected 2D or 3D")
+        return np.ascontiguousarray(a)
+
+
+@dataclass
+class VoiceModelState:
+    """safetensors.VoiceModelState: per-layer `cache` [2,1,T,H,Dh] + `offset`
+    (internal/safetensors/reader.go:273-308, flow_transformer.go:451-480)."""
+    caches: list  # list of np.ndarray [2,1,T,H,Dh]
+    offsets: list  # list of int
+
+
+@dataclass
+class RuntimeGenerateConfig:
+    """tts.RuntimeGenerateConfig (internal/tts/runtime.go:17-31).  `noise` is the
+    host-drawn N(0, temperature) array [steps, 32] (flow_lm.go:386-408 draws it
+    from math/rand inside the step; here it is an explicit input)."""
+    temperature: float = 0.7
+    eos_threshold: float = -4.0
+    max_steps: int = 0
+    estimated_max_steps: int = 0
+    lsd_decode_steps: int = 1
+    frames_after_eos: int = 3
+    voice_embedding: Optional[VoiceEmbedding] = None
+    voice_model_state: Optional[VoiceModelState] = None
+    step_callback: Optional[Callable[[int, int], None]] = None
+    noise: Optional[np.ndarray] = None
+    seed: int = 0
+    force_eos_step: int = -1
+    no_pcm_d2h: bool = False
+
+
+def estimate_max_frames(n_tokens: int, frame_rate: float = 12.5) -> int:
+    """internal/text/prepare.go:38-48."""
+    n_tokens = max(n_tokens, 0)
+    if not (frame_rate > 0) or math.isinf(frame_rate):
+        frame_rate = 12.5
+    return int(math.ceil((n_tokens / 3.0 + 2.0) * frame_rate))
+
+
+def resolve_max_steps(cfg: RuntimeGenerateConfig, n_tokens: int) -> int:
+    """internal/tts/runtime_native_safetensors.go:61-67."""
+    ms = cfg.max_steps
+    if ms <= 0:
+        ms = cfg.estimated_max_steps
+    if ms <= 0:
+        ms = estimate_max_frames(n_tokens)
+    return ms
+
+
+def make_noise(steps: int, temperature: float, seed: int) -> np.ndarray:
+    """Host noise: N(0,1)*sqrt(max(temperature,0)) as float32 (flow_lm.go:386-408)."""
+    sigma = math.sqrt(max(float(temperature), 0.0))
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((steps, LATENT_DIM)) * sigma).astype(np.float32)
+
+
+@dataclass
+class GenerateResult:
+    pcm: np.ndarray
+    n_frames: int
+    queue_ms: float = 0.0
+    first_frame_ms: float = 0.0
+    total_ms: float = 0.0
+    latents: Optional[np.ndarray] = None
+    eos_logits: Optional[np.ndarray] = None
+
+
+class _Pending:
+    def __init__(self, ticket, keep, pcm, max_steps):
+        self.ticket, self.keep, self.pcm, self.max_steps = ticket, keep, pcm, max_steps
+
+
+class NativeCudaRuntime:
+    """`tts.Runtime` for --backend native-cuda.
+
+    Mirrors nativeSafetensorsRuntime (internal/tts/runtime_native_safetensors.go):
+    `generate_audio(tokens, cfg) -> float32 PCM`, `close()` (nil-safe, idempotent),
+    `mimi_timing()`.  `generate_audio` may be called from many threads; the engine
+    batches them continuously."""
+
+    def __init__(self, checkpoint: Optional[str] = None, *, device: int = 0, max_batch: int = 256,
+                 max_seq_tokens: int = 1024, max_frames: int = 512, mimi_group_frames: int = 0,
+                 kv_pages: int = 0, tensors: Optional[dict] = None):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        cfg = PttsConfig(device=device, max_batch=max_batch, max_seq_tokens=max_seq_tokens,
+                         max_frames=max_frames, mimi_group_frames=mimi_group_frames, kv_pages=kv_pages)
+        _check(self._lib.ptts_create(C.byref(cfg), C.byref(self._h)))
+        try:
+            if checkpoint is not None:
+                _check(self._lib.ptts_load_safetensors(self._h, checkpoint.encode()))
+            if tensors:
+                for k, a in tensors.items():
+                    self.load_tensor(k, a)
+            if checkpoint is not None or tensors:
+                self.finalize()
+        except Exception:
+            self.close()
+            raise
+
+    # -- weights ----------------------------------------------------------
+    def load_tensor(self, key: str, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        _check(self._lib.ptts_load_tensor(self._h, key.encode(), shape, a.ndim, 0, a.ctypes.data_as(C.c_void_p)))
+
+    def finalize(self):
+        _check(self._lib.ptts_finalize_weights(self._h))
+        info = PttsModelInfo()
+        _check(self._lib.ptts_model_info_get(self._h, C.byref(info)))
+        self.info = info
+
+    # -- tts.Runtime ------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.ptts_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mimi_timing(self):
+        """(frame_rate, encoder_frame_rate, steps_per_latent), service.go:280-298."""
+        return 12.5, 200.0, 16
+
+    def _voice_args(self, cfg: RuntimeGenerateConfig, keep: list):
+        if cfg.voice_embedding is not None and cfg.voice_model_state is not None:
+            raise NativeCudaError(PTTS_EINVAL,
+                                  "generate: voice embedding and voice model state are mutually exclusive")
+        vemb, vframes, vkv = None, 0, None
+        if cfg.voice_embedding is not None:
+            rows = cfg.voice_embedding.rows()
+            keep.append(rows)
+            vemb, vframes = _fptr(rows), rows.shape[0]
+        if cfg.voice_model_state is not None:
+            st = cfg.voice_model_state
+            n = len(st.caches)
+            arr = (PttsVoiceLayer * n)()
+            for i, (c, off) in enumerate(zip(st.caches, st.offsets)):
+                c = np.ascontiguousarray(c, dtype=np.float32)
+                if c.ndim != 5 or c.shape[0] != 2 or c.shape[1] != 1:
+                    raise NativeCudaError(PTTS_EINVAL,
+                                          f"native: voice model state cache shape {list(c.shape)}, want [2,B,T,H,D]")
+                keep.append(c)
+                arr[i].cache = _fptr(c)
+                arr[i].cache_tokens = c.shape[2]
+                arr[i].offset = int(off)
+            kv = PttsVoiceKV(layers=arr, n_layers=n)
+            keep.extend([arr, kv])
+            vkv = C.byref(kv)
+        return vemb, vframes, vkv
+
+    def submit(self, tokens: Sequence[int], cfg: RuntimeGenerateConfig) -> _Pending:
+        if self._h is None:
+            raise NativeCudaError(PTTS_ESTATE, "native-cuda runtime unavailable")
+        toks = np.ascontiguousarray(np.asarray(tokens, dtype=np.int64))
+        if toks.size == 0:
+            raise NativeCudaError(PTTS_EINVAL, "generate: token slice must not be empty")
+        ms = resolve_max_steps(cfg, toks.size)
+        noise = cfg.noise
+        if noise is None:
+            noise = make_noise(ms, cfg.temperature, cfg.seed)
+        noise = np.ascontiguousarray(noise, dtype=np.float32)
+        keep: list = [toks, noise]
+        vemb, vframes, vkv = self._voice_args(cfg, keep)
+        flags = PTTS_REQ_NO_PCM_D2H if cfg.no_pcm_d2h else 0
+        g = PttsGenCfg(temperature=cfg.temperature, eos_threshold=cfg.eos_threshold, max_steps=cfg.max_steps,
+                       estimated_max_steps=cfg.estimated_max_steps, lsd_decode_steps=cfg.lsd_decode_steps,
+                       frames_after_eos=cfg.frames_after_eos, force_eos_step=cfg.force_eos_step, flags=flags)
+        pcm = None if cfg.no_pcm_d2h else np.empty(ms * SAMPLES_PER_FRAME, dtype=np.float32)
+        ticket = C.c_int64()
+        _check(self._lib.ptts_submit(self._h, toks.ctypes.data_as(C.POINTER(C.c_int64)), toks.size, vemb, vframes,
+                                     vkv, C.byref(g), _fptr(noise), noise.shape[0], _fptr(pcm),
+                                     0 if pcm is None else pcm.size, C.byref(ticket)))
+        return _Pending(ticket.value, keep, pcm, ms)
+
+    def wait(self, p: _Pending, want_latents: bool = False) -> GenerateResult:
+        res = PttsResult()
+        rc = self._lib.ptts_wait(self._h, p.ticket, C.byref(res))
+        try:
+            _check(rc)
+            lat = eos = None
+            if want_latents:
+                lat = np.empty((res.n_frames, LATENT_DIM), dtype=np.float32)
+                eos = np.empty(res.n_frames, dtype=np.float32)
+                n = self._lib.ptts_ticket_latents(self._h, p.ticket, _fptr(lat), _fptr(eos), res.n_frames)
+                if n < 0:
+                    _check(n)
+            pcm = p.pcm[: res.n_samples].copy() if p.pcm is not None else np.empty(0, np.float32)
+            return GenerateResult(pcm, res.n_frames, res.queue_ms, res.first_frame_ms, res.total_ms, lat, eos)
+        finally:
+            self._lib.ptts_ticket_release(self._h, p.ticket)
+
+    def cancel(self, p: _Pending):
+        _check(self._lib.ptts_cancel(self._h, p.ticket))
+
+    def generate_audio(self, tokens: Sequence[int], cfg: Optional[RuntimeGenerateConfig] = None) -> np.ndarray:
+        """GenerateAudio(ctx, tokens, cfg) ([]float32, error)."""
+        return self.generate(tokens, cfg).pcm
+
+    def generate(self, tokens, cfg: Optional[RuntimeGenerateConfig] = None, want_latents=False) -> GenerateResult:
+        cfg = cfg or RuntimeGenerateConfig()
+        r = self.wait(self.submit(tokens, cfg), want_latents)
+        if cfg.step_callback is not None:  # reported after the fact: the loop runs on the device side
+            ms = resolve_max_steps(cfg, len(tokens))
+            for s in range(r.n_frames):
+                cfg.step_callback(s + 1, ms)
+        return r
+
+    # -- stage-level API (native.Model mirror) ------------------------------
+    def seq_open(self, tokens, voice_embedding: Optional[VoiceEmbedding] = None,
+                 voice_model_state: Optional[VoiceModelState] = None, reserve_frames: int = 0) -> "Sequence_":
+        toks = np.ascontiguousarray(np.asarray(tokens, dtype=np.int64))
+        keep: list = [toks]
+        cfg = RuntimeGenerateConfig(voice_embedding=voice_embedding, voice_model_state=voice_model_state)
+        vemb, vframes, vkv = self._voice_args(cfg, keep)
+        h = C.c_void_p()
+        _check(self._lib.ptts_seq_open(self._h, toks.ctypes.data_as(C.POINTER(C.c_int64)), toks.size, vemb,
+                                       vframes, vkv, reserve_frames, C.byref(h)))
+        return Sequence_(self, h)
+
+    def step(self, seqs, noise: np.ndarray, frames_in: Optional[np.ndarray] = None, lsd_steps: int = 1):
+        """SampleNextLatentStateful for a batch: returns (latents [B,32], eos [B])."""
+        B = len(seqs)
+        noise = np.ascontiguousarray(noise, dtype=np.float32).reshape(B, LATENT_DIM)
+        if frames_in is not None:
+            frames_in = np.ascontiguousarray(frames_in, dtype=np.float32).reshape(B, LATENT_DIM)
+        arr = (C.c_void_p * B)(*[s._h for s in seqs])
+        lat = np.empty((B, LATENT_DIM), dtype=np.float32)
+        eos = np.empty(B, dtype=np.float32)
+        _check(self._lib.ptts_step(self._h, arr, B, _fptr(frames_in), _fptr(noise), lsd_steps, _fptr(lat), _fptr(eos)))
+        return lat, eos
+
+    def decode_latents(self, latents: np.ndarray, frames_per_seq: Optional[Sequence[int]] = None) -> np.ndarray:
+        """LatentToMimi + MimiDecode of caller latents [N,32] (ragged batch)."""
+        lat = np.ascontiguousarray(latents, dtype=np.float32).reshape(-1, LATENT_DIM)
+        fps = np.asarray(frames_per_seq if frames_per_seq is not None else [lat.shape[0]], dtype=np.int32)
+        assert int(fps.sum()) == lat.shape[0]
+        pcm = np.empty(lat.shape[0] * SAMPLES_PER_FRAME, dtype=np.float32)
+        _check(self._lib.ptts_decode_latents(self._h, _fptr(lat), fps.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             fps.size, _fptr(pcm)))
+        return pcm
+
+    def stage_times(self, reset: bool = False) -> dict:
+        t = PttsStageTimes()
+        _check(self._lib.ptts_stage_times_get(self._h, C.byref(t), 1 if reset else 0))
+        return {n: getattr(t, n) for n, _ in PttsStageTimes._fields_}
+
+    def debug_fetch(self, name: str) -> np.ndarray:
+        n = self._lib.ptts_debug_fetch(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float32)
+        self._lib.ptts_debug_fetch(self._h, name.encode(), _fptr(out), n)
+        return out
+
+
+class Sequence_:
+    """FlowLMState mirror (internal/native/flow_lm.go:45-49)."""
+
+    def __init__(self, rt: NativeCudaRuntime, h):
+        self._rt, self._h = rt, h
+
+    @property
+    def frames(self) -> int:
+        return self._rt._lib.ptts_seq_frames(self._h)
+
+    @property
+    def kv_len(self) -> int:
+        return self._rt._lib.ptts_seq_kv_len(self._h)
+
+    def read_kv(self, layer: int, which: int) -> np.ndarray:
+        info = self._rt.info
+        out = np.empty((info.n_heads, self.kv_len, info.head_dim), dtype=np.float32)
+        _check(self._rt._lib.ptts_seq_read_kv(self._rt._h, self._h, layer, which, _fptr(out)))
+        return out
+
+    def decode(self, first_frame: int = 0, n_frames: Optional[int] = None) -> np.ndarray:
+        n = self.frames - first_frame if n_frames is None else n_frames
+        pcm = np.empty(n * SAMPLES_PER_FRAME, dtype=np.float32)
+        _check(self._rt._lib.ptts_decode(self._rt._h, self._h, first_frame, n, _fptr(pcm)))
+        return pcm
+
+    def close(self):
+        h, self._h = self._h, None
+        if h and self._rt._h:
+            self._rt._lib.ptts_seq_close(self._rt._h, h)

@@ -1,0 +1,330 @@
+// attention.cu — RoPE + paged KV append and the two masked-attention kernels.
+//
+// Reference semantics (internal/runtime/ops/attention.go:307-484): per (row,
+// head) scores s_k = (q.k_k)/sqrt(Dh) over the allowed keys only (masked keys
+// are SKIPPED, never multiplied: unused slots of upstream voice files may hold
+// NaN, scripts/export_onnx.py:114), max, exp, sum, out = sum_k (e_k/sum) v_k;
+// a row with no allowed key yields zeros.  The reference evaluates exp and the
+// sum in fp64; here they are fp32 (expf, <= 8192 positive terms), which is far
+// inside the 2e-4 attention tolerance of ops/tolerance.go:13-24.
+//
+// One CTA of 128 threads per (row, head), head_dim == 64:
+//   phase 1: 16 keys per pass (8 lanes x 2 float4 per key, 3 shuffles) -> smem
+//   phase 2: block max / exp / sum
+//   phase 3: P.V with 16 float4 columns x 8 key groups, smem cross-group reduce
+// A KV page (16 tokens x 64 floats for one head) is one contiguous 4 KB run, so
+// phase 1 and 3 read whole 128-byte lines.
+#include "kernels.cuh"
+#include <math.h>
+
+namespace ptts {
+
+constexpr int HD = 64;       // head_dim (FlowLM 1024/16, Mimi 512/8)
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ float block_reduce_max(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < ATT_THREADS / 32; i++)
+    r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ATT_THREADS / 32; i++)
+    r += red[i];
+  __syncthreads();
+  return r;
+}
+
+// KeyFn(j) -> pointer to the 64 floats of key j; ValFn(j) likewise for values.
+template <class KeyFn, class ValFn>
+__device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp,
+                                           ValFn valp, float *out, float *scores,
+                                           float *red, float4 *pv) {
+  const int tid = threadIdx.x;
+  const float scale = 0.125f; // 1/sqrt(64)
+  // phase 1
+  const int part = tid & 7, kslot = tid >> 3; // 16 keys per pass
+  const float4 q0 = *reinterpret_cast<const float4 *>(q + part * 4);
+  const float4 q1 = *reinterpret_cast<const float4 *>(q + 32 + part * 4);
+  float lmax = -INFINITY;
+  for (int j0 = 0; j0 < nkeys; j0 += 16) {
+    const int j = j0 + kslot;
+    float s = 0.0f;
+    if (j < nkeys) {
+      const float *kp = keyp(j);
+      float4 a = *reinterpret_cast<const float4 *>(kp + part * 4);
+      float4 b = *reinterpret_cast<const float4 *>(kp + 32 + part * 4);
+      s = q0.x * a.x;
+      s = fmaf(q0.y, a.y, s);
+      s = fmaf(q0.z, a.z, s);
+      s = fmaf(q0.w, a.w, s);
+      s = fmaf(q1.x, b.x, s);
+      s = fmaf(q1.y, b.y, s);
+      s = fmaf(q1.z, b.z, s);
+      s = fmaf(q1.w, b.w, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (j < nkeys) {
+      s *= scale;
+      if (part == 0)
+        scores[j] = s;
+      lmax = fmaxf(lmax, s);
+    }
+  }
+  const float gmax = block_reduce_max(lmax, red); // includes __syncthreads
+  // phase 2
+  float lsum = 0.0f;
+  for (int j = tid; j < nkeys; j += ATT_THREADS) {
+    float e = expf(scores[j] - gmax);
+    scores[j] = e;
+    lsum += e;
+  }
+  const float gsum = block_reduce_sum(lsum, red);
+  const float inv = 1.0f / gsum;
+  // phase 3
+  const int c4 = tid & 15, grp = tid >> 4; // 8 key groups
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = grp; j < nkeys; j += 8) {
+    const float w = scores[j] * inv;
+    const float4 v = *reinterpret_cast<const float4 *>(valp(j) + c4 * 4);
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
+  pv[grp * 16 + c4] = acc;
+  __syncthreads();
+  if (tid < 16) {
+    float4 r = pv[tid];
+#pragma unroll
+    for (int g2 = 1; g2 < 8; g2++) {
+      float4 t = pv[g2 * 16 + tid];
+      r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+    }
+    *reinterpret_cast<float4 *>(out + tid * 4) = r;
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_paged_kernel(const float *qkv, long ldq, float *out, long ldo,
+                           const int32_t *row_slot, const int32_t *row_pos,
+                           KvGeom kv, int layer) {
+  extern __shared__ float smem[];
+  __shared__ float red[ATT_THREADS / 32];
+  __shared__ float4 pv[8 * 16];
+  const int r = blockIdx.x, h = blockIdx.y;
+  const int slot = row_slot[r], pos = row_pos[r];
+  float *o = out + (long)r * ldo + h * HD;
+  if (pos < 0) {
+    if (threadIdx.x < 16)
+      *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int nkeys = pos + 1;
+  const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
+  const int PT = kv.page_tokens;
+  const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
+  const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * PT * HD;
+  const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * PT * HD;
+  const float *pool = kv.pool;
+  auto keyp = [&](int j) {
+    return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
+  };
+  auto valp = [&](int j) {
+    return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
+  };
+  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_window_kernel(const float *qkv, long ldq, float *out, long ldo,
+                            int D, const int32_t *row_pos, int ctx) {
+  extern __shared__ float smem[];
+  __shared__ float red[ATT_THREADS / 32];
+  __shared__ float4 pv[8 * 16];
+  const int r = blockIdx.x, h = blockIdx.y;
+  const int pos = row_pos[r];
+  float *o = out + (long)r * ldo + h * HD;
+  if (pos < 0) {
+    if (threadIdx.x < 16)
+      *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  // allowed keys: 0 <= pos - pk < ctx  ->  the last min(ctx, pos+1) rows
+  const int nkeys = (ctx > 0 && pos + 1 > ctx) ? ctx : pos + 1;
+  const int first = r - (nkeys - 1);
+  const float *kbase = qkv + D + h * HD;
+  const float *vbase = qkv + 2 * D + h * HD;
+  auto keyp = [&](int j) { return kbase + (long)(first + j) * ldq; };
+  auto valp = [&](int j) { return vbase + (long)(first + j) * ldq; };
+  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv);
+}
+
+int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
+                    const int32_t *row_slot, const int32_t *row_pos,
+                    const KvGeom &kv, int layer, int max_keys, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  dim3 grid(rows, kv.n_heads);
+  size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
+  attention_paged_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, row_slot,
+                                                        row_pos, kv, layer);
+  return 1;
+}
+
+int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
+                     int D, int n_heads, const int32_t *row_pos, int ctx,
+                     cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  dim3 grid(rows, n_heads);
+  int mk = ctx > 0 ? ctx : 8192;
+  size_t sm = sizeof(float) * (size_t)((mk + 15) / 16 * 16);
+  attention_window_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, D,
+                                                         row_pos, ctx);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// RoPE + KV append
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    rope_kv_append_kernel(float *qkv, const int32_t *row_slot,
+                          const int32_t *row_pos, const float *cosT,
+                          const float *sinT, KvGeom kv, int layer) {
+  const int r = blockIdx.x;
+  const int slot = row_slot[r], pos = row_pos[r];
+  if (pos < 0)
+    return;
+  const int H = kv.n_heads, D = H * HD, half = HD / 2;
+  float *row = qkv + (long)r * 3 * D;
+  const float *c = cosT + (long)pos * half, *s = sinT + (long)pos * half;
+  const int PT = kv.page_tokens;
+  const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
+  float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
+  const int tok = pos % PT;
+  // q and k pairs
+  for (int p = threadIdx.x; p < D; p += blockDim.x) { // D/2 pairs each for q,k
+    const int isk = p >= D / 2;
+    const int pp = isk ? p - D / 2 : p;
+    const int h = pp / half, j = pp % half;
+    float *src = row + (isk ? D : 0) + h * HD + 2 * j;
+    const float a = src[0], b = src[1];
+    const float o0 = a * c[j] - b * s[j];
+    const float o1 = a * s[j] + b * c[j];
+    if (!isk) {
+      src[0] = o0;
+      src[1] = o1;
+    } else {
+      float *dst = page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + 2 * j;
+      dst[0] = o0;
+      dst[1] = o1;
+    }
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    page[((long)(layer * 2 + 1) * H + h) * PT * HD + (long)tok * HD + d] = row[2 * D + i];
+  }
+}
+
+int rope_kv_append(float *qkv, int rows, const int32_t *row_slot,
+                   const int32_t *row_pos, const float *cosT, const float *sinT,
+                   const KvGeom &kv, int layer, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  rope_kv_append_kernel<<<rows, 256, 0, st>>>(qkv, row_slot, row_pos, cosT, sinT, kv, layer);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    kv_write_rows_kernel(const float *rk, const float *rv, int slot, int pos0,
+                         KvGeom kv, int layer) {
+  const int t = blockIdx.x, pos = pos0 + t;
+  const int H = kv.n_heads, D = H * HD, PT = kv.page_tokens;
+  const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
+  float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
+  const int tok = pos % PT;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    page[((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + d] = rk[(long)t * D + i];
+    page[((long)(layer * 2 + 1) * H + h) * PT * HD + (long)tok * HD + d] = rv[(long)t * D + i];
+  }
+}
+
+int kv_write_rows(const float *rows_k, const float *rows_v, int T, int slot,
+                  int pos0, const KvGeom &kv, int layer, cudaStream_t st) {
+  if (T <= 0)
+    return 0;
+  kv_write_rows_kernel<<<T, 256, 0, st>>>(rows_k, rows_v, slot, pos0, kv, layer);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    kv_read_rows_kernel(float *out, int T, int slot, KvGeom kv, int layer, int which) {
+  const int t = blockIdx.x;
+  const int H = kv.n_heads, D = H * HD, PT = kv.page_tokens;
+  const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
+  const float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + t / PT] * page_stride;
+  const int tok = t % PT;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    out[((long)h * T + t) * HD + d] =
+        page[((long)(layer * 2 + which) * H + h) * PT * HD + (long)tok * HD + d];
+  }
+}
+
+int kv_read_rows(float *out, int T, int slot, const KvGeom &kv, int layer,
+                 int which, cudaStream_t st) {
+  if (T <= 0)
+    return 0;
+  kv_read_rows_kernel<<<T, 256, 0, st>>>(out, T, slot, kv, layer, which);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    rope_inplace_kernel(float *qkv, int D, int n_heads, const int32_t *row_pos,
+                        const float *cosT, const float *sinT) {
+  const int r = blockIdx.x, pos = row_pos[r];
+  if (pos < 0)
+    return;
+  const int half = HD / 2;
+  float *row = qkv + (long)r * 3 * D;
+  const float *c = cosT + (long)pos * half, *s = sinT + (long)pos * half;
+  for (int p = threadIdx.x; p < D; p += blockDim.x) {
+    const int isk = p >= D / 2;
+    const int pp = isk ? p - D / 2 : p;
+    const int h = pp / half, j = pp % half;
+    float *src = row + (isk ? D : 0) + h * HD + 2 * j;
+    const float a = src[0], b = src[1];
+    src[0] = a * c[j] - b * s[j];
+    src[1] = a * s[j] + b * c[j];
+  }
+}
+
+int rope_inplace(float *qkv, int rows, int D, int n_heads, const int32_t *row_pos,
+                 const float *cosT, const float *sinT, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  rope_inplace_kernel<<<rows, 256, 0, st>>>(qkv, D, n_heads, row_pos, cosT, sinT);
+  return 1;
+}
+
+} // namespace ptts

@@ -1,0 +1,245 @@
+// elementwise.cu — row-wise and gather/scatter kernels of the hot path.
+#include "kernels.cuh"
+#include <math.h>
+
+namespace ptts {
+
+// LayerNorm (+ optional adaLN modulate).  One warp per row, two-pass fp32
+// statistics about the mean (reference: fp64 mean / biased variance,
+// internal/native/linear.go:265-329; fp32 two-pass differs by ~1e-7 relative).
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const float *x, long ldx, float *out, long ldo, int rows,
+                     int D, const float *w, const float *b, float eps,
+                     const float *scale, const float *shift, long ldmod) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows)
+    return;
+  const float *xr = x + (long)row * ldx;
+  float s = 0.0f;
+  for (int i = lane * 4; i < D; i += 128) {
+    float4 v = *reinterpret_cast<const float4 *>(xr + i);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.0f;
+  for (int i = lane * 4; i < D; i += 128) {
+    float4 v = *reinterpret_cast<const float4 *>(xr + i);
+    float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
+    q += (a * a + c * c) + (d * d + e * e);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float inv = 1.0f / sqrtf(q / (float)D + eps);
+  float *orow = out + (long)row * ldo;
+  for (int i = lane * 4; i < D; i += 128) {
+    float4 v = *reinterpret_cast<const float4 *>(xr + i);
+    float n[4] = {(v.x - mean) * inv, (v.y - mean) * inv, (v.z - mean) * inv,
+                  (v.w - mean) * inv};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float t = n[j];
+      if (w)
+        t *= __ldg(w + i + j);
+      if (b)
+        t += __ldg(b + i + j);
+      if (scale)
+        t = t * (scale[(long)row * ldmod + i + j] + 1.0f) + shift[(long)row * ldmod + i + j];
+      n[j] = t;
+    }
+    *reinterpret_cast<float4 *>(orow + i) = make_float4(n[0], n[1], n[2], n[3]);
+  }
+}
+
+int layernorm(const float *x, long ldx, float *out, long ldo, int rows, int D,
+              const float *w, const float *b, float eps, const float *scale,
+              const float *shift, long ldmod, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  int ctas = (rows + 7) / 8;
+  layernorm_kernel<<<ctas, 256, 0, st>>>(x, ldx, out, ldo, rows, D, w, b, eps, scale,
+                                         shift, ldmod);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    embed_gather_kernel(const int64_t *ids, const float *table, float *out, int D) {
+  const int r = blockIdx.x;
+  if (ids[r] < 0) // voice-prefix rows are copied in by the host (runtime :104-119)
+    return;
+  const float4 *src = reinterpret_cast<const float4 *>(table + (long)ids[r] * D);
+  float4 *dst = reinterpret_cast<float4 *>(out + (long)r * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x)
+    dst[i] = __ldg(src + i);
+}
+
+int embed_gather(const int64_t *ids, const float *table, float *out, int rows,
+                 int D, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  embed_gather_kernel<<<rows, 256, 0, st>>>(ids, table, out, D);
+  return 1;
+}
+
+__global__ void nan_to_bos_kernel(const float *frames, const float *bos, float *out,
+                                  int n, int ldim) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float v = frames[i];
+  out[i] = isnan(v) ? bos[i % ldim] : v;
+}
+int nan_to_bos(const float *frames, const float *bos, float *out, int rows,
+               int ldim, cudaStream_t st) {
+  int n = rows * ldim;
+  if (n <= 0)
+    return 0;
+  nan_to_bos_kernel<<<(n + 255) / 256, 256, 0, st>>>(frames, bos, out, n, ldim);
+  return 1;
+}
+
+__global__ void add_vec_silu_kernel(const float *a, const float *tvec, float *out,
+                                    int n, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float y = tvec[i % C] + a[i];
+  out[i] = y / (1.0f + expf(-y));
+}
+int add_vec_silu(const float *a, const float *tvec, float *out, int rows, int C,
+                 cudaStream_t st) {
+  int n = rows * C;
+  if (n <= 0)
+    return 0;
+  add_vec_silu_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, tvec, out, n, C);
+  return 1;
+}
+
+__global__ void gather_rows_kernel(const float *src, const int64_t *off, float *dst,
+                                   int rows, int width) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width)
+    return;
+  int r = i / width, c = i % width;
+  dst[i] = src[off[r] + c];
+}
+int gather_rows(const float *src, const int64_t *src_off, float *dst, int rows,
+                int width, cudaStream_t st) {
+  int n = rows * width;
+  if (n <= 0)
+    return 0;
+  gather_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, src_off, dst, rows, width);
+  return 1;
+}
+__global__ void scatter_rows_kernel(const float *src, float *dst, const int64_t *off,
+                                    int rows, int width) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width)
+    return;
+  int r = i / width, c = i % width;
+  dst[off[r] + c] = src[i];
+}
+int scatter_rows(const float *src, float *dst, const int64_t *dst_off, int rows,
+                 int width, cudaStream_t st) {
+  int n = rows * width;
+  if (n <= 0)
+    return 0;
+  scatter_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, dst_off, rows, width);
+  return 1;
+}
+
+// Depthwise transposed conv: out[p*s + r, c] = in[p, c] w[c, r] + in[p-1, c] w[c, r+s]
+// (+ further taps if k > 2s), right-trimmed to s outputs per input position.
+__global__ void __launch_bounds__(256)
+    upsample_depthwise_kernel(const float *lat, const float *w, float *out, int C,
+                              int stride, int k, const int32_t *row_pos,
+                              const int32_t *row_frame0) {
+  const int row = blockIdx.x;
+  const int pos = row_pos[row];
+  float *o = out + (long)row * C;
+  if (pos < 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      o[c] = 0.0f;
+    return;
+  }
+  const int f0 = row_frame0[row];
+  const int q = pos / stride, r = pos % stride;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.0f;
+    // taps in the reference's accumulation order: ascending input index
+    for (int kx = r + ((k - 1 - r) / stride) * stride; kx >= 0; kx -= stride) {
+      const int ix = q - kx / stride;
+      if (ix < 0)
+        continue;
+      const float iv = lat[(long)(f0 + ix) * C + c];
+      acc += iv * __ldg(w + (long)c * k + kx);
+    }
+    o[c] = acc;
+  }
+}
+
+int upsample_depthwise(const float *lat, const float *w, float *out, int rows,
+                       int C, int stride, int k, const int32_t *row_pos,
+                       const int32_t *row_frame0, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  upsample_depthwise_kernel<<<rows, 256, 0, st>>>(lat, w, out, C, stride, k, row_pos,
+                                                  row_frame0);
+  return 1;
+}
+
+// Final Conv1d (Cout = 1): one thread per output sample, weights in smem.
+__global__ void __launch_bounds__(256)
+    final_conv_kernel(const float *x, int rows, int Cin, int k, const float *w,
+                      float bias, const uint8_t *rowmask, int mask_div, float *pcm) {
+  extern __shared__ float ws[];
+  const int K = Cin * k;
+  for (int i = threadIdx.x; i < K; i += blockDim.x)
+    ws[i] = w[i];
+  __syncthreads();
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows)
+    return;
+  if (rowmask && !rowmask[r / mask_div]) {
+    pcm[r] = 0.0f;
+    return;
+  }
+  const float *a = x + (r - (k - 1)) * Cin;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int i = 0; i < K; i += 4) {
+    float4 v = *reinterpret_cast<const float4 *>(a + i);
+    s0 = fmaf(v.x, ws[i + 0], s0);
+    s1 = fmaf(v.y, ws[i + 1], s1);
+    s2 = fmaf(v.z, ws[i + 2], s2);
+    s3 = fmaf(v.w, ws[i + 3], s3);
+  }
+  pcm[r] = ((s0 + s1) + (s2 + s3)) + bias;
+}
+
+int final_conv(const float *x, int rows, int Cin, int k, const float *w, float bias,
+               const uint8_t *rowmask, int mask_div, float *pcm, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  final_conv_kernel<<<(rows + 255) / 256, 256, sizeof(float) * Cin * k, st>>>(
+      x, rows, Cin, k, w, bias, rowmask, mask_div, pcm);
+  return 1;
+}
+
+__global__ void fill_zero_kernel(float4 *p, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+int fill_zero(float *p, size_t n, cudaStream_t st) {
+  if (n == 0)
+    return 0;
+  cudaMemsetAsync(p, 0, n * sizeof(float), st);
+  return 0;
+}
+
+} // namespace ptts

@@ -1,0 +1,1210 @@
+// engine.cu — weight upload, KV pool and the three device passes (prefill, AR
+// step + flow head, Mimi decode) of the native-cuda backend.
+#include "engine.cuh"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace ptts {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+const char *last_error() { return g_err; }
+
+// ---------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------
+int Engine::create(const ptts_config *c) {
+  cfg = *c;
+  if (cfg.max_batch <= 0) cfg.max_batch = 256;
+  if (cfg.page_tokens <= 0) cfg.page_tokens = 16;
+  if (cfg.max_seq_tokens <= 0) cfg.max_seq_tokens = 1024;
+  if (cfg.max_seq_tokens > 8192)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: max_seq_tokens %d exceeds the RoPE table (8192)",
+              cfg.max_seq_tokens);
+  if (cfg.max_frames <= 0) cfg.max_frames = 512;
+  if (cfg.mimi_group_frames <= 0) cfg.mimi_group_frames = 1536;
+  if (cfg.max_prefill_tokens <= 0) cfg.max_prefill_tokens = 8192;
+  if (cfg.max_prefill_tokens < cfg.max_seq_tokens) cfg.max_prefill_tokens = cfg.max_seq_tokens;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda runtime unavailable: no CUDA device (%s)",
+              cudaGetErrorString(ce));
+  if (cfg.device < 0 || cfg.device >= ndev)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: device %d out of range [0,%d)", cfg.device, ndev);
+  device = cfg.device;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda runtime unavailable: device %d is sm_%d%d, need sm_100",
+              device, prop.major, prop.minor);
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto &e : ev)
+    CUDA_TRY(cudaEventCreate(&e));
+  return PTTS_OK;
+}
+
+Engine::~Engine() {
+  {
+    std::unique_lock<std::mutex> lk(q_mu);
+    sched_stop = true;
+  }
+  q_cv.notify_all();
+  if (sched.joinable())
+    sched.join();
+  if (st) {
+    cudaSetDevice(device);
+    cudaStreamSynchronize(st);
+  }
+  for (void *p : allocs)
+    cudaFree(p);
+  auto fh = [](void *p) {
+    if (p)
+      cudaFreeHost(p);
+  };
+  fh(h_row_slot); fh(h_row_pos); fh(h_ids); fh(h_off_a); fh(h_off_b); fh(h_off_c);
+  fh(h_eos); fh(h_lat); fh(h_stage); fh(h_mrow_pos); fh(h_mrow_frame0); fh(h_mmask); fh(h_moff);
+  for (auto &e : ev)
+    if (e)
+      cudaEventDestroy(e);
+  if (st)
+    cudaStreamDestroy(st);
+}
+
+int Engine::dmalloc(void **p, size_t bytes) {
+  if (bytes == 0)
+    bytes = 256;
+  CUDA_TRY(cudaMalloc(p, bytes));
+  allocs.push_back(*p);
+  return PTTS_OK;
+}
+
+int Engine::upload(const std::vector<float> &v, float **out) {
+  int rc = dmalloc((void **)out, v.size() * sizeof(float));
+  if (rc)
+    return rc;
+  CUDA_TRY(cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return PTTS_OK;
+}
+
+int Engine::upload_key(const std::string &key, float **out, std::vector<int64_t> *shape) {
+  auto it = host.find(key);
+  if (it == host.end())
+    PTTS_FAIL(PTTS_EINVAL, "native: tensor %s not found", key.c_str());
+  if (shape)
+    *shape = it->second.shape;
+  return upload(it->second.data, out);
+}
+
+// ---------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------
+static inline float half_to_float(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000) << 16;
+  uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ff;
+  uint32_t f;
+  if (exp == 0) {
+    if (man == 0) {
+      f = sign;
+    } else {
+      exp = 127 - 15 + 1;
+      while (!(man & 0x400)) {
+        man <<= 1;
+        exp--;
+      }
+      man &= 0x3ff;
+      f = sign | (exp << 23) | (man << 13);
+    }
+  } else if (exp == 31) {
+    f = sign | 0x7f800000u | (man << 13);
+  } else {
+    f = sign | ((exp + 127 - 15) << 23) | (man << 13);
+  }
+  float r;
+  memcpy(&r, &f, 4);
+  return r;
+}
+
+// internal/safetensors/store.go:339-395 (decodeTensorData): F32 copied, F16 and
+// BF16 widened to fp32.
+int Engine::load_tensor(const char *key, const int64_t *shape, int rank, int dtype,
+                        const void *p) {
+  if (finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda: weights already finalized");
+  if (!key || !p || rank < 0 || rank > 6)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: load_tensor: bad arguments");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < rank; i++) {
+    if (shape[i] < 0)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: load_tensor %s: negative dim", key);
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.resize(n);
+  if (dtype == PTTS_DTYPE_F32) {
+    memcpy(t.data.data(), p, n * 4);
+  } else if (dtype == PTTS_DTYPE_BF16) {
+    const uint16_t *s = (const uint16_t *)p;
+    for (size_t i = 0; i < n; i++) {
+      uint32_t u = (uint32_t)s[i] << 16;
+      memcpy(&t.data[i], &u, 4);
+    }
+  } else if (dtype == PTTS_DTYPE_F16) {
+    const uint16_t *s = (const uint16_t *)p;
+    for (size_t i = 0; i < n; i++)
+      t.data[i] = half_to_float(s[i]);
+  } else {
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: load_tensor %s: unsupported dtype %d", key, dtype);
+  }
+  host[key] = std::move(t);
+  return PTTS_OK;
+}
+
+namespace {
+struct Loader {
+  Engine *e;
+  const HostTensor *get(const std::string &k) {
+    auto it = e->host.find(k);
+    return it == e->host.end() ? nullptr : &it->second;
+  }
+  bool has(const std::string &k) { return get(k) != nullptr; }
+  // internal/native/linear.go:19-49 (loadLinear)
+  int linear(const std::string &name, bool with_bias, DLinear *l) {
+    const HostTensor *w = get(name + ".weight");
+    if (!w)
+      PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", name.c_str());
+    if (w->shape.size() != 2)
+      PTTS_FAIL(PTTS_EINVAL, "native: linear \"%s\" weight must be rank-2", name.c_str());
+    l->out = (int)w->shape[0];
+    l->in = (int)w->shape[1];
+    int rc = e->upload(w->data, &l->w);
+    if (rc)
+      return rc;
+    l->b = nullptr;
+    if (with_bias) {
+      const HostTensor *b = get(name + ".bias");
+      if (b) {
+        if (b->shape.size() != 1 || b->shape[0] != w->shape[0])
+          PTTS_FAIL(PTTS_EINVAL, "native: linear \"%s\" bias shape incompatible with weight",
+                    name.c_str());
+        rc = e->upload(b->data, &l->b);
+        if (rc)
+          return rc;
+      }
+    }
+    return PTTS_OK;
+  }
+  // internal/native/linear.go:191-208 (loadLayerNorm)
+  int lnorm(const std::string &name, float eps, DLayerNorm *ln) {
+    const HostTensor *w = get(name + ".weight"), *b = get(name + ".bias");
+    if (!w || !b)
+      PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight/bias not found", name.c_str());
+    if (w->shape.size() != 1 || b->shape.size() != 1 || w->shape[0] != b->shape[0])
+      PTTS_FAIL(PTTS_EINVAL, "native: layernorm \"%s\" invalid shapes", name.c_str());
+    ln->d = (int)w->shape[0];
+    ln->eps = eps;
+    int rc = e->upload(w->data, &ln->w);
+    if (rc)
+      return rc;
+    return e->upload(b->data, &ln->b);
+  }
+  int tlayer(const std::string &p, bool mimi, DTLayer *l) {
+    int rc;
+    if ((rc = lnorm(p + ".norm1", 1e-5f, &l->n1))) return rc;
+    if ((rc = lnorm(p + ".norm2", 1e-5f, &l->n2))) return rc;
+    if ((rc = linear(p + ".self_attn.in_proj", false, &l->in_proj))) return rc;
+    if ((rc = linear(p + ".self_attn.out_proj", false, &l->out_proj))) return rc;
+    if ((rc = linear(p + ".linear1", false, &l->l1))) return rc;
+    if ((rc = linear(p + ".linear2", false, &l->l2))) return rc;
+    if (mimi) {
+      if (const HostTensor *t = get(p + ".layer_scale_1.scale"))
+        if ((rc = e->upload(t->data, &l->ls1))) return rc;
+      if (const HostTensor *t = get(p + ".layer_scale_2.scale"))
+        if ((rc = e->upload(t->data, &l->ls2))) return rc;
+    }
+    return PTTS_OK;
+  }
+  // Conv1d [Cout,Cin,k] -> GEMM weight [Cout, k*Cin] (tap-major K so that the
+  // A row of output t is the contiguous channels-last span t-k+1..t).
+  int conv(const std::string &p, DConvG *c) {
+    const HostTensor *w = get(p + ".weight");
+    if (!w)
+      PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", p.c_str());
+    if (w->shape.size() != 3)
+      PTTS_FAIL(PTTS_EINVAL, "native: conv1d weight must be rank-3, got rank %zu",
+                w->shape.size());
+    int co = (int)w->shape[0], ci = (int)w->shape[1], k = (int)w->shape[2];
+    std::vector<float> wp((size_t)co * ci * k);
+    for (int oc = 0; oc < co; oc++)
+      for (int ic = 0; ic < ci; ic++)
+        for (int kx = 0; kx < k; kx++)
+          wp[((size_t)oc * k + kx) * ci + ic] = w->data[((size_t)oc * ci + ic) * k + kx];
+    c->cin = ci; c->cout = co; c->taps = k; c->stride = 1; c->N = co; c->K = k * ci;
+    int rc = e->upload(wp, &c->w);
+    if (rc)
+      return rc;
+    c->b = nullptr;
+    if (const HostTensor *b = get(p + ".bias"))
+      if ((rc = e->upload(b->data, &c->b)))
+        return rc;
+    return PTTS_OK;
+  }
+  // ConvTranspose1d [Cin,Cout,k], stride s, right trim k-s -> s phase GEMMs
+  // stacked along N: W[(r*Cout+oc), (j*Cin+ic)] = w[ic][oc][r + s*(J-1-j)].
+  int convtr(const std::string &p, int stride, DConvG *c) {
+    const HostTensor *w = get(p + ".weight");
+    if (!w)
+      PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", p.c_str());
+    if (w->shape.size() != 3)
+      PTTS_FAIL(PTTS_EINVAL, "native: convtranspose1d weight must be rank-3");
+    int ci = (int)w->shape[0], co = (int)w->shape[1], k = (int)w->shape[2];
+    if (k < stride)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: convtranspose1d kernel %d < stride %d", k, stride);
+    int J = (k + stride - 1) / stride;
+    std::vector<float> wp((size_t)stride * co * J * ci, 0.0f);
+    for (int r = 0; r < stride; r++)
+      for (int oc = 0; oc < co; oc++)
+        for (int j = 0; j < J; j++) {
+          int kx = r + stride * (J - 1 - j);
+          if (kx >= k)
+            continue;
+          for (int ic = 0; ic < ci; ic++)
+            wp[((size_t)(r * co + oc) * J + j) * ci + ic] = w->data[((size_t)ic * co + oc) * k + kx];
+        }
+    c->cin = ci; c->cout = co; c->taps = J; c->stride = stride; c->N = stride * co; c->K = J * ci;
+    int rc = e->upload(wp, &c->w);
+    if (rc)
+      return rc;
+    c->b = nullptr;
+    if (const HostTensor *b = get(p + ".bias")) {
+      std::vector<float> bp((size_t)stride * co);
+      for (int r = 0; r < stride; r++)
+        for (int oc = 0; oc < co; oc++)
+          bp[(size_t)r * co + oc] = b->data[oc];
+      if ((rc = e->upload(bp, &c->b)))
+        return rc;
+    }
+    return PTTS_OK;
+  }
+};
+
+// internal/native/flow_transformer.go:797-832 (buildRoPE)
+void build_rope(int max_seq, int hd, double max_period, std::vector<float> &c,
+                std::vector<float> &s) {
+  int half = hd / 2;
+  c.resize((size_t)max_seq * half);
+  s.resize((size_t)max_seq * half);
+  for (int pos = 0; pos < max_seq; pos++)
+    for (int i = 0; i < half; i++) {
+      double f = 1.0 / std::pow(max_period, (double)i / (double)half);
+      double a = (double)pos * f;
+      c[(size_t)pos * half + i] = (float)std::cos(a);
+      s[(size_t)pos * half + i] = (float)std::sin(a);
+    }
+}
+} // namespace
+
+int Engine::finalize() {
+  if (finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda: weights already finalized");
+  CUDA_TRY(cudaSetDevice(device));
+  Loader ld{this};
+  int rc;
+  // ---- FlowLM (flow_lm.go:51-119) ----
+  const HostTensor *emb = ld.get("flow_lm.conditioner.embed.weight");
+  if (!emb || emb->shape.size() != 2)
+    PTTS_FAIL(PTTS_EINVAL, "native: load conditioner: embed must be rank-2");
+  nbins = (int)emb->shape[0];
+  D = (int)emb->shape[1];
+  if ((rc = upload(emb->data, &embed))) return rc;
+  for (int i = 0;; i++) {
+    std::string p = "flow_lm.transformer.layers." + std::to_string(i);
+    if (!ld.has(p + ".norm1.weight"))
+      break;
+    DTLayer l;
+    if ((rc = ld.tlayer(p, false, &l))) return rc;
+    fl.push_back(l);
+  }
+  L = (int)fl.size();
+  if (L == 0)
+    PTTS_FAIL(PTTS_EINVAL, "native: no flow_lm transformer layers found");
+  if (fl[0].out_proj.out != D || D % H)
+    PTTS_FAIL(PTTS_EINVAL, "native: d_model %d not divisible by num_heads %d", D, H);
+  Dh = D / H;
+  if (Dh != 64)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: head_dim %d unsupported (kernels are specialised for 64)", Dh);
+  F = fl[0].l1.out;
+  for (auto &l : fl)
+    if (l.in_proj.out != 3 * D || l.in_proj.in != D || l.out_proj.in != D ||
+        l.l1.in != D || l.l2.in != l.l1.out || l.l2.out != D || l.n1.d != D || l.n2.d != D)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: flow_lm transformer layer shape mismatch");
+  {
+    const HostTensor *b = ld.get("flow_lm.bos_emb");
+    if (!b || b->shape.size() != 1 || b->shape[0] != ldim)
+      PTTS_FAIL(PTTS_EINVAL, "native: tensor flow_lm.bos_emb missing or not [%d]", ldim);
+    if ((rc = upload(b->data, &bos))) return rc;
+  }
+  if ((rc = ld.linear("flow_lm.input_linear", true, &input_linear))) return rc;
+  if ((rc = ld.lnorm("flow_lm.out_norm", 1e-5f, &out_norm))) return rc;
+  if ((rc = ld.linear("flow_lm.out_eos", true, &out_eos_lin))) return rc;
+  if (input_linear.in != ldim || input_linear.out != D || out_eos_lin.in != D || out_eos_lin.out != 1)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: flow_lm input_linear/out_eos shape mismatch");
+  if (const HostTensor *b = ld.get("flow_lm.out_eos.bias"))
+    out_eos_bias = b->data[0];
+  // ---- flow net (flow_net.go:250-305) ----
+  if ((rc = ld.linear("flow_lm.flow_net.cond_embed", true, &cond_embed))) return rc;
+  if ((rc = ld.linear("flow_lm.flow_net.input_proj", true, &input_proj))) return rc;
+  C = input_proj.out;
+  std::vector<float> ada_w, ada_b;
+  bool ada_has_bias = true;
+  auto append_ada = [&](const std::string &name, int want_out) -> int {
+    const HostTensor *w = ld.get(name + ".weight"), *b = ld.get(name + ".bias");
+    if (!w || w->shape.size() != 2 || w->shape[0] != want_out || w->shape[1] != C)
+      PTTS_FAIL(PTTS_EINVAL, "native: flow modulation %s shape invalid", name.c_str());
+    ada_w.insert(ada_w.end(), w->data.begin(), w->data.end());
+    if (b)
+      ada_b.insert(ada_b.end(), b->data.begin(), b->data.end());
+    else {
+      ada_b.insert(ada_b.end(), (size_t)want_out, 0.0f);
+      ada_has_bias = ada_has_bias && false;
+    }
+    return PTTS_OK;
+  };
+  for (int i = 0;; i++) {
+    std::string p = "flow_lm.flow_net.res_blocks." + std::to_string(i);
+    if (!ld.has(p + ".in_ln.weight"))
+      break;
+    DResBlk b;
+    if ((rc = ld.lnorm(p + ".in_ln", 1e-6f, &b.in_ln))) return rc;
+    if ((rc = ld.linear(p + ".mlp.0", true, &b.mlp0))) return rc;
+    if ((rc = ld.linear(p + ".mlp.2", true, &b.mlp2))) return rc;
+    if ((rc = append_ada(p + ".adaLN_modulation.1", 3 * C))) return rc;
+    if (b.mlp0.in != C || b.mlp2.out != C || b.mlp2.in != b.mlp0.out || b.in_ln.d != C)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: flow res block %d shape mismatch", i);
+    rb.push_back(b);
+  }
+  depth = (int)rb.size();
+  if (depth == 0)
+    PTTS_FAIL(PTTS_EINVAL, "native: no flow_net res blocks found");
+  if ((rc = append_ada("flow_lm.flow_net.final_layer.adaLN_modulation.1", 2 * C))) return rc;
+  ada_n = depth * 3 * C + 2 * C;
+  ada_all.in = C;
+  ada_all.out = ada_n;
+  if ((rc = upload(ada_w, &ada_all.w))) return rc;
+  if ((rc = upload(ada_b, &ada_all.b))) return rc;
+  if ((rc = ld.linear("flow_lm.flow_net.final_layer.linear", true, &final_linear))) return rc;
+  if (final_linear.in != C || final_linear.out != ldim || cond_embed.in != D ||
+      cond_embed.out != C || input_proj.in != ldim)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: flow_net shape mismatch");
+  for (int i = 0; i < 2; i++) {
+    std::string p = "flow_lm.flow_net.time_embed." + std::to_string(i);
+    const HostTensor *fq = ld.get(p + ".freqs"), *w1 = ld.get(p + ".mlp.0.weight"),
+                     *b1 = ld.get(p + ".mlp.0.bias"), *w2 = ld.get(p + ".mlp.2.weight"),
+                     *b2 = ld.get(p + ".mlp.2.bias"), *al = ld.get(p + ".mlp.3.alpha");
+    if (!fq || !w1 || !w2 || !al)
+      PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.* not found", p.c_str());
+    TEmb &t = te[i];
+    t.freqs = fq->data;
+    t.w1 = w1->data;
+    t.w2 = w2->data;
+    t.alpha = al->data;
+    t.hid = (int)w1->shape[0];
+    t.in = (int)w1->shape[1];
+    t.out = (int)w2->shape[0];
+    t.b1 = b1 ? b1->data : std::vector<float>((size_t)t.hid, 0.0f);
+    t.b2 = b2 ? b2->data : std::vector<float>((size_t)t.out, 0.0f);
+    if (t.in != 2 * (int)t.freqs.size() || t.out != C || (int)w2->shape[1] != t.hid ||
+        (int)t.alpha.size() != C)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: time_embed.%d shape mismatch", i);
+  }
+  nfreq = (int)te[0].freqs.size();
+  {
+    std::vector<float> c, s;
+    build_rope(8192, Dh, 10000.0, c, s);
+    if ((rc = upload(c, &rope_cos))) return rc;
+    if ((rc = upload(s, &rope_sin))) return rc;
+  }
+  // ---- Mimi (mimi.go:546-637) ----
+  {
+    const HostTensor *q = ld.get("mimi.quantizer.output_proj.weight");
+    const HostTensor *sd = ld.get("flow_lm.emb_std"), *mn = ld.get("flow_lm.emb_mean");
+    if (!q || q->shape.size() != 3)
+      PTTS_FAIL(PTTS_EINVAL, "native: quantizer projection weight rank must be 3");
+    if (!sd || !mn || (int)sd->data.size() < ldim || (int)mn->data.size() < ldim)
+      PTTS_FAIL(PTTS_EINVAL, "native: flow emb stats shape mismatch");
+    int oc_n = (int)q->shape[0], ic_n = (int)q->shape[1], k = (int)q->shape[2];
+    if (k != 1 || ic_n != ldim)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: quantizer.output_proj must be [Md,%d,1]", ldim);
+    // model.go:226-242: W*std, bias = sum W*mean
+    std::vector<float> pw((size_t)oc_n * ic_n), pb((size_t)oc_n);
+    for (int oc = 0; oc < oc_n; oc++) {
+      float bv = 0.0f;
+      for (int ic = 0; ic < ic_n; ic++) {
+        float w = q->data[(size_t)oc * ic_n + ic];
+        pw[(size_t)oc * ic_n + ic] = w * sd->data[ic];
+        bv += w * mn->data[ic];
+      }
+      pb[oc] = bv;
+    }
+    Md = oc_n;
+    proj.in = ic_n;
+    proj.out = oc_n;
+    if ((rc = upload(pw, &proj.w))) return rc;
+    if ((rc = upload(pb, &proj.b))) return rc;
+  }
+  {
+    const HostTensor *u = ld.get("mimi.upsample.convtr.convtr.weight");
+    if (!u || u->shape.size() != 3 || u->shape[0] != Md || u->shape[1] != 1)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: mimi.upsample.convtr must be depthwise [Md,1,k]");
+    up_k = (int)u->shape[2];
+    up_stride = 16; // mimi.go:25-34,665-686: encoder_frame_rate / frame_rate
+    if (up_k < up_stride)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: upsample kernel %d < stride %d", up_k, up_stride);
+    if ((rc = upload(u->data, &up_w))) return rc;
+  }
+  for (int i = 0;; i++) {
+    std::string p = "mimi.decoder_transformer.transformer.layers." + std::to_string(i);
+    if (!ld.has(p + ".norm1.weight"))
+      break;
+    DTLayer l;
+    if ((rc = ld.tlayer(p, true, &l))) return rc;
+    ml.push_back(l);
+  }
+  ML = (int)ml.size();
+  if (ML == 0)
+    PTTS_FAIL(PTTS_EINVAL, "native: no mimi decoder transformer layers found");
+  if (ml[0].out_proj.out != Md || Md % MH || Md / MH != 64)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: mimi d_model %d / heads %d must give head_dim 64", Md, MH);
+  MF = ml[0].l1.out;
+  {
+    std::vector<float> c, s;
+    build_rope(8192, Md / MH, 10000.0, c, s);
+    if ((rc = upload(c, &mrope_cos))) return rc;
+    if ((rc = upload(s, &mrope_sin))) return rc;
+  }
+  if ((rc = ld.conv("mimi.decoder.model.0.conv", &init_conv))) return rc;
+  const int strides[3] = {6, 5, 4};
+  const char *upk[3] = {"2", "5", "8"};
+  const char *rsk[3] = {"3", "6", "9"};
+  int ch = init_conv.cout;
+  if (init_conv.cin != Md)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: seanet init conv expects %d input channels", Md);
+  for (int s = 0; s < 3; s++) {
+    std::string base = "mimi.decoder.model.";
+    if ((rc = ld.convtr(base + upk[s] + ".convtr", strides[s], &up[s]))) return rc;
+    if (up[s].cin != ch)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: seanet stage %d channel mismatch", s);
+    ch = up[s].cout;
+    if ((rc = ld.conv(base + rsk[s] + ".block.1.conv", &res1[s]))) return rc;
+    if ((rc = ld.conv(base + rsk[s] + ".block.3.conv", &res2[s]))) return rc;
+    if (res1[s].cin != ch || res2[s].cout != ch || res2[s].cin != res1[s].cout)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: seanet res block %d channel mismatch", s);
+  }
+  {
+    const HostTensor *w = ld.get("mimi.decoder.model.11.conv.weight");
+    const HostTensor *b = ld.get("mimi.decoder.model.11.conv.bias");
+    if (!w || w->shape.size() != 3 || w->shape[0] != 1 || w->shape[1] != ch)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: final conv must be [1,%d,k]", ch);
+    final_cin = ch;
+    final_k = (int)w->shape[2];
+    std::vector<float> wp((size_t)final_cin * final_k);
+    for (int ic = 0; ic < final_cin; ic++)
+      for (int kx = 0; kx < final_k; kx++)
+        wp[(size_t)kx * final_cin + ic] = w->data[(size_t)ic * final_k + kx];
+    if ((rc = upload(wp, &final_w))) return rc;
+    final_b = b ? b->data[0] : 0.0f;
+  }
+  if (init_conv.taps - 1 > mimi_pad || res1[0].taps - 1 > mimi_pad)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: conv kernel wider than the %d-row segment pad", mimi_pad);
+
+  // ---- model info (SURVEY §8d formulas evaluated on the loaded shapes) ----
+  info.d_model = D; info.n_heads = H; info.head_dim = Dh; info.n_layers = L; info.ffn_dim = F;
+  info.flow_dim = C; info.flow_depth = depth; info.latent_dim = ldim; info.n_bins = nbins;
+  info.mimi_dim = Md; info.mimi_heads = MH; info.mimi_layers = ML; info.mimi_ffn_dim = MF;
+  info.mimi_context = Mctx; info.samples_per_frame = up_stride * 6 * 5 * 4;
+  info.mimi_steps_per_latent = up_stride;
+  {
+    int64_t tl = (int64_t)L * (4LL * D * D + 2LL * D * F + 4LL * D);
+    int64_t io = (int64_t)ldim * D + (input_linear.b ? D : 0) + 2LL * D + D + 1;
+    int64_t temb = 0;
+    for (int i = 0; i < 2; i++)
+      temb += (int64_t)te[i].freqs.size() + (int64_t)te[i].hid * te[i].in + te[i].hid +
+              (int64_t)te[i].out * te[i].hid + te[i].out + C;
+    int64_t flow = (int64_t)ldim * C + C + (int64_t)D * C + C + temb +
+                   (int64_t)depth * (2LL * C + 2LL * ((int64_t)C * C + C) + 3LL * C * C + 3LL * C) +
+                   ((int64_t)ldim * C + ldim) + (2LL * C * C + 2LL * C);
+    info.params_ar = tl + io + flow;
+    info.macs_ar_frame = (int64_t)L * (4LL * D * D + 2LL * D * F) + (int64_t)ldim * D + D +
+                         (int64_t)ldim * C + (int64_t)D * C + (int64_t)ada_n * C +
+                         (int64_t)depth * 2LL * C * C + (int64_t)ldim * C;
+    info.macs_prefill_token = (int64_t)L * (4LL * D * D + 2LL * D * F);
+    int64_t mt = (int64_t)ML * (4LL * Md * Md + 2LL * Md * MF);
+    int64_t per16 = mt + (int64_t)init_conv.N * init_conv.K + (int64_t)up[0].N * up[0].K;
+    int64_t r1 = (int64_t)res1[0].N * res1[0].K + (int64_t)res2[0].N * res2[0].K +
+                 (int64_t)up[1].N * up[1].K;
+    int64_t r2 = (int64_t)res1[1].N * res1[1].K + (int64_t)res2[1].N * res2[1].K +
+                 (int64_t)up[2].N * up[2].K;
+    int64_t r3 = (int64_t)res1[2].N * res1[2].K + (int64_t)res2[2].N * res2[2].K +
+                 (int64_t)final_cin * final_k;
+    info.macs_mimi_frame = (int64_t)ldim * Md + (int64_t)up_stride * (per16 + 6 * (r1 + 5 * (r2 + 4 * r3)));
+    int64_t pm = (int64_t)ldim * Md + (int64_t)Md * up_k + (int64_t)ML * (4LL * Md * Md + 2LL * Md * MF + 6LL * Md);
+    pm += (int64_t)init_conv.N * init_conv.K + init_conv.N;
+    for (int s = 0; s < 3; s++)
+      pm += (int64_t)up[s].N * up[s].K / 1 + (int64_t)res1[s].N * res1[s].K + (int64_t)res2[s].N * res2[s].K;
+    info.params_mimi = pm;
+  }
+
+  // ---- KV pool, slots ----
+  max_batch = cfg.max_batch;
+  max_frames = cfg.max_frames;
+  page_tokens = cfg.page_tokens;
+  max_pages = (cfg.max_seq_tokens + page_tokens - 1) / page_tokens;
+  n_pages = cfg.kv_pages > 0 ? cfg.kv_pages : max_batch * max_pages;
+  size_t page_floats = (size_t)L * 2 * H * page_tokens * Dh;
+  if ((rc = dmalloc((void **)&kv_pool, (size_t)n_pages * page_floats * sizeof(float)))) return rc;
+  for (int i = n_pages - 1; i >= 0; i--)
+    free_pages.push_back(i);
+  for (int i = max_batch - 1; i >= 0; i--)
+    free_slots.push_back(i);
+  h_pagetab.assign((size_t)max_batch * max_pages, 0);
+  if ((rc = dmalloc((void **)&d_pagetab, h_pagetab.size() * sizeof(int32_t)))) return rc;
+  CUDA_TRY(cudaMemset(d_pagetab, 0, h_pagetab.size() * sizeof(int32_t)));
+  kvg.pool = kv_pool; kvg.pagetab = d_pagetab; kvg.max_pages = max_pages;
+  kvg.page_tokens = page_tokens; kvg.n_layers = L; kvg.n_heads = H; kvg.head_dim = Dh;
+  if ((rc = dmalloc((void **)&d_hist, (size_t)max_batch * (max_frames + 1) * ldim * sizeof(float)))) return rc;
+  if ((rc = dmalloc((void **)&d_noise, (size_t)max_batch * max_frames * ldim * sizeof(float)))) return rc;
+  {
+    std::vector<float> nanrow((size_t)ldim, NAN);
+    for (int s = 0; s < max_batch; s++)
+      CUDA_TRY(cudaMemcpy(d_hist + (size_t)s * (max_frames + 1) * ldim, nanrow.data(),
+                          ldim * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // ---- FlowLM workspaces ----
+  max_rows = cfg.max_prefill_tokens > max_batch ? cfg.max_prefill_tokens : max_batch;
+  if ((rc = dmalloc((void **)&x, (size_t)max_rows * D * 4))) return rc;
+  if ((rc = dmalloc((void **)&nrm, (size_t)max_rows * D * 4))) return rc;
+  if ((rc = dmalloc((void **)&att, (size_t)max_rows * D * 4))) return rc;
+  if ((rc = dmalloc((void **)&qkv, (size_t)max_rows * 3 * D * 4))) return rc;
+  if ((rc = dmalloc((void **)&ff, (size_t)max_rows * F * 4))) return rc;
+  if ((rc = dmalloc((void **)&d_row_slot, (size_t)max_rows * 4))) return rc;
+  if ((rc = dmalloc((void **)&d_row_pos, (size_t)max_rows * 4))) return rc;
+  if ((rc = dmalloc((void **)&d_ids, (size_t)max_rows * 8))) return rc;
+  if ((rc = dmalloc((void **)&d_off_a, (size_t)max_rows * 8))) return rc;
+  if ((rc = dmalloc((void **)&d_off_b, (size_t)max_rows * 8))) return rc;
+  if ((rc = dmalloc((void **)&d_off_c, (size_t)max_rows * 8))) return rc;
+  CUDA_TRY(cudaMallocHost((void **)&h_row_slot, (size_t)max_rows * 4));
+  CUDA_TRY(cudaMallocHost((void **)&h_row_pos, (size_t)max_rows * 4));
+  CUDA_TRY(cudaMallocHost((void **)&h_ids, (size_t)max_rows * 8));
+  CUDA_TRY(cudaMallocHost((void **)&h_off_a, (size_t)max_rows * 8));
+  CUDA_TRY(cudaMallocHost((void **)&h_off_b, (size_t)max_rows * 8));
+  CUDA_TRY(cudaMallocHost((void **)&h_off_c, (size_t)max_rows * 8));
+  CUDA_TRY(cudaMallocHost((void **)&h_eos, (size_t)max_batch * 4));
+  CUDA_TRY(cudaMallocHost((void **)&h_lat, (size_t)max_batch * ldim * 4));
+  CUDA_TRY(cudaMallocHost((void **)&h_stage, (size_t)max_batch * ldim * 4 * 2));
+  const int B = max_batch;
+  if ((rc = dmalloc((void **)&fh_in, (size_t)B * ldim * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_frames, (size_t)B * ldim * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_noise, (size_t)B * ldim * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_cur, (size_t)B * ldim * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_last, (size_t)B * D * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_eos, (size_t)B * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_cproj, (size_t)B * C * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_sy, (size_t)B * C * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_ada, (size_t)B * ada_n * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_x, (size_t)B * C * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_h, (size_t)B * C * 4))) return rc;
+  if ((rc = dmalloc((void **)&fh_h2, (size_t)B * rb[0].mlp0.out * 4))) return rc;
+
+  // ---- Mimi workspaces (front slack rows stay zero: causal left context) ----
+  mimi_frames_cap = cfg.mimi_group_frames;
+  int max_segs = 2 * max_batch + 64;
+  if (max_segs > mimi_frames_cap) max_segs = mimi_frames_cap;
+  mimi_rows_cap = up_stride * mimi_frames_cap + mimi_pad * max_segs;
+  auto slack_alloc = [&](float **p, size_t rows, int chn) -> int {
+    float *base = nullptr;
+    size_t n = (rows + 8) * (size_t)chn;
+    int r = dmalloc((void **)&base, n * sizeof(float));
+    if (r)
+      return r;
+    CUDA_TRY(cudaMemset(base, 0, n * sizeof(float)));
+    *p = base + 8 * (size_t)chn;
+    return PTTS_OK;
+  };
+  const size_t Rb = (size_t)mimi_rows_cap;
+  if ((rc = dmalloc((void **)&m_latin, (size_t)mimi_frames_cap * ldim * 4))) return rc;
+  if ((rc = dmalloc((void **)&m_lat, (size_t)mimi_frames_cap * Md * 4))) return rc;
+  if ((rc = slack_alloc(&m_x, Rb, Md))) return rc;
+  if ((rc = slack_alloc(&m_nrm, Rb, Md))) return rc;
+  if ((rc = slack_alloc(&m_att, Rb, Md))) return rc;
+  if ((rc = slack_alloc(&m_qkv, Rb, 3 * Md))) return rc;
+  if ((rc = slack_alloc(&m_ff, Rb, MF))) return rc;
+  if ((rc = slack_alloc(&m_y0e, Rb, init_conv.cout))) return rc;
+  size_t rows = Rb;
+  for (int s = 0; s < 3; s++) {
+    rows *= (size_t)up[s].stride;
+    if ((rc = slack_alloc(&m_y[s], rows, up[s].cout))) return rc;
+    if ((rc = slack_alloc(&m_ye[s], rows, up[s].cout))) return rc;
+    if ((rc = slack_alloc(&m_he[s], rows, res1[s].cout))) return rc;
+  }
+  if ((rc = slack_alloc(&m_pcm, rows, 1))) return rc;
+  if ((rc = dmalloc((void **)&d_mrow_pos, Rb * 4))) return rc;
+  if ((rc = dmalloc((void **)&d_mrow_frame0, Rb * 4))) return rc;
+  if ((rc = dmalloc((void **)&d_mmask, Rb))) return rc;
+  if ((rc = dmalloc((void **)&d_moff, (size_t)mimi_frames_cap * 8))) return rc;
+  CUDA_TRY(cudaMallocHost((void **)&h_mrow_pos, Rb * 4));
+  CUDA_TRY(cudaMallocHost((void **)&h_mrow_frame0, Rb * 4));
+  CUDA_TRY(cudaMallocHost((void **)&h_mmask, Rb));
+  CUDA_TRY(cudaMallocHost((void **)&h_moff, (size_t)mimi_frames_cap * 8));
+
+  host.clear(); // device copies are authoritative from here on
+  finalized = true;
+  return PTTS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// (s,t) schedule: tvec[i] = (TE0(i/steps) + TE1((i+1)/steps)) / 2, computed once
+// per lsd_steps on the host exactly as flow_net.go:42-83 + tensor_util.go:273-326.
+// ---------------------------------------------------------------------------
+static void host_time_embed(const Engine::TEmb &t, float tv, std::vector<float> &out) {
+  int nf = (int)t.freqs.size();
+  std::vector<float> emb((size_t)2 * nf), h((size_t)t.hid);
+  for (int i = 0; i < nf; i++) {
+    float arg = tv * t.freqs[i];
+    emb[i] = (float)std::cos((double)arg);
+    emb[nf + i] = (float)std::sin((double)arg);
+  }
+  for (int o = 0; o < t.hid; o++) {
+    float s = 0.0f;
+    for (int i = 0; i < t.in; i++)
+      s += emb[i] * t.w1[(size_t)o * t.in + i];
+    s += t.b1[o];
+    h[o] = s / (1.0f + (float)std::exp((double)(-s)));
+  }
+  out.assign((size_t)t.out, 0.0f);
+  for (int o = 0; o < t.out; o++) {
+    float s = 0.0f;
+    for (int i = 0; i < t.hid; i++)
+      s += h[i] * t.w2[(size_t)o * t.hid + i];
+    out[o] = s + t.b2[o];
+  }
+  double mean = 0;
+  for (float v : out)
+    mean += (double)v;
+  mean /= (double)t.out;
+  double var = 0;
+  for (float v : out) {
+    double d = (double)v - mean;
+    var += d * d;
+  }
+  if (t.out > 1)
+    var /= (double)(t.out - 1);
+  float inv = (float)(1.0 / std::sqrt(var + (double)1e-5f));
+  for (int j = 0; j < t.out; j++)
+    out[j] = out[j] * inv * t.alpha[j];
+}
+
+int Engine::get_tvec(int lsd_steps, float **out) {
+  auto it = tvec_cache.find(lsd_steps);
+  if (it != tvec_cache.end()) {
+    *out = it->second;
+    return PTTS_OK;
+  }
+  std::vector<float> all((size_t)lsd_steps * C), t0, t1;
+  for (int i = 0; i < lsd_steps; i++) {
+    float sv = (float)i / (float)lsd_steps, tv = (float)(i + 1) / (float)lsd_steps;
+    host_time_embed(te[0], sv, t0);
+    host_time_embed(te[1], tv, t1);
+    for (int j = 0; j < C; j++)
+      all[(size_t)i * C + j] = (t0[j] + t1[j]) * 0.5f;
+  }
+  float *d = nullptr;
+  int rc = upload(all, &d);
+  if (rc)
+    return rc;
+  tvec_cache[lsd_steps] = d;
+  *out = d;
+  return PTTS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sequence resources
+// ---------------------------------------------------------------------------
+int Engine::seq_alloc(int tokens_needed, Seq **out) {
+  if (tokens_needed > cfg.max_seq_tokens)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: sequence needs %d KV tokens, max_seq_tokens is %d",
+              tokens_needed, cfg.max_seq_tokens);
+  int np = (tokens_needed + page_tokens - 1) / page_tokens;
+  if (free_slots.empty())
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: no free sequence slot (max_batch %d)", max_batch);
+  if ((int)free_pages.size() < np)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: KV pool exhausted (%d pages wanted, %zu free)", np,
+              free_pages.size());
+  ptts_seq *ps = new ptts_seq();
+  Seq *s = &ps->impl;
+  s->e = this;
+  s->slot = free_slots.back();
+  free_slots.pop_back();
+  for (int i = 0; i < np; i++) {
+    s->pages.push_back(free_pages.back());
+    free_pages.pop_back();
+  }
+  s->kv_cap = np * page_tokens;
+  for (int i = 0; i < np; i++)
+    h_pagetab[(size_t)s->slot * max_pages + i] = s->pages[i];
+  *out = s;
+  return sync_pagetab(s);
+}
+
+int Engine::sync_pagetab(Seq *s) {
+  CUDA_TRY(cudaMemcpyAsync(d_pagetab + (size_t)s->slot * max_pages,
+                           h_pagetab.data() + (size_t)s->slot * max_pages,
+                           s->pages.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  // h_pagetab is pageable: the copy is staged before return, safe to reuse.
+  return PTTS_OK;
+}
+
+void Engine::seq_free(Seq *s) {
+  if (!s || s->slot < 0)
+    return;
+  for (int p : s->pages)
+    free_pages.push_back(p);
+  free_slots.push_back(s->slot);
+  s->slot = -1;
+  s->pages.clear();
+}
+
+// ---------------------------------------------------------------------------
+// FlowLM transformer over R rows already in x; row_slot/row_pos uploaded.
+// (flow_transformer.go:326-389, one pass of forwardWithState per layer)
+// ---------------------------------------------------------------------------
+int Engine::flow_forward(int R, int max_keys, bool) {
+  int64_t &nl = times.kernel_launches;
+  for (int l = 0; l < L; l++) {
+    DTLayer &ly = fl[l];
+    nl += layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st);
+    GemmArgs g;
+    g.A = nrm; g.lda = D; g.W = ly.in_proj.w; g.ldw = D; g.M = R; g.N = 3 * D; g.K = D;
+    g.epi.C = qkv; g.epi.ldc = 3 * D;
+    nl += gemm(g, st);
+    nl += rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st);
+    nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st);
+    GemmArgs o;
+    o.A = att; o.lda = D; o.W = ly.out_proj.w; o.ldw = D; o.M = R; o.N = D; o.K = D;
+    o.epi.residual = x; o.epi.ldr = D; o.epi.C = x; o.epi.ldc = D;
+    nl += gemm(o, st);
+    nl += layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st);
+    GemmArgs f1;
+    f1.A = nrm; f1.lda = D; f1.W = ly.l1.w; f1.ldw = D; f1.M = R; f1.N = F; f1.K = D;
+    f1.epi.act = ACT_GELU; f1.epi.C = ff; f1.epi.ldc = F;
+    nl += gemm(f1, st);
+    GemmArgs f2;
+    f2.A = ff; f2.lda = F; f2.W = ly.l2.w; f2.ldw = F; f2.M = R; f2.N = D; f2.K = F;
+    f2.epi.residual = x; f2.epi.ldr = D; f2.epi.C = x; f2.epi.ldc = D;
+    nl += gemm(f2, st);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PTTS_OK;
+}
+
+// flow_transformer.go:451-480: import upstream voice KV at positions [0, offset)
+int Engine::import_voice_kv(Seq *s, const ptts_voice_kv *vk) {
+  if (vk->n_layers != L)
+    PTTS_FAIL(PTTS_EINVAL, "native: voice model state has %d layers, transformer has %d",
+              vk->n_layers, L);
+  int off0 = vk->layers[0].offset;
+  for (int l = 0; l < L; l++) {
+    const ptts_voice_layer &vl = vk->layers[l];
+    if (!vl.cache)
+      PTTS_FAIL(PTTS_EINVAL, "native: voice model state module \"transformer.layers.%d.self_attn\" missing cache", l);
+    if (vl.offset < 0)
+      PTTS_FAIL(PTTS_EINVAL, "native: voice model state module has negative offset %d", vl.offset);
+    if (vl.offset > vl.cache_tokens)
+      PTTS_FAIL(PTTS_EINVAL, "native: voice model state offset %d exceeds cache length %d",
+                vl.offset, vl.cache_tokens);
+    if (vl.offset != off0)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: voice model state offsets differ across layers");
+  }
+  if (off0 > s->kv_cap)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: voice state (%d tokens) exceeds reserved KV", off0);
+  if (off0 > max_rows)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: voice state (%d tokens) exceeds workspace rows", off0);
+  for (int l = 0; l < L; l++) {
+    const ptts_voice_layer &vl = vk->layers[l];
+    // [2,1,T,H,Dh]: K half rows then V half rows, each row = [H*Dh]
+    const float *kh = vl.cache, *vh = vl.cache + (size_t)vl.cache_tokens * D;
+    CUDA_TRY(cudaMemcpyAsync(nrm, kh, (size_t)off0 * D * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(att, vh, (size_t)off0 * D * 4, cudaMemcpyHostToDevice, st));
+    times.kernel_launches += kv_write_rows(nrm, att, off0, s->slot, 0, kvg, l, st);
+    CUDA_TRY(cudaStreamSynchronize(st)); // staging buffers are reused per layer
+  }
+  s->kv_len = off0;
+  return PTTS_OK;
+}
+
+// Batched ragged prefill (flow_lm.go:155-187 -> flow_transformer.go:749-771).
+int Engine::prefill(const std::vector<Seq *> &seqs, const std::vector<const int64_t *> &tok,
+                    const std::vector<int> &ntok, const std::vector<const float *> &voice,
+                    const std::vector<int> &nvoice) {
+  int R = 0, max_keys = 0;
+  for (size_t i = 0; i < seqs.size(); i++) {
+    int t = ntok[i] + nvoice[i];
+    if (seqs[i]->kv_len + t > seqs[i]->kv_cap)
+      PTTS_FAIL(PTTS_ENOMEM, "native-cuda: prompt (%d tokens) exceeds reserved KV", t);
+    R += t;
+  }
+  if (R == 0)
+    return PTTS_OK;
+  if (R > max_rows)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: prefill of %d tokens exceeds max_prefill_tokens %d", R, max_rows);
+  cudaEventRecord(ev[0], st);
+  int r = 0;
+  for (size_t i = 0; i < seqs.size(); i++) {
+    Seq *s = seqs[i];
+    for (int j = 0; j < nvoice[i]; j++, r++) {
+      h_ids[r] = -1;
+      h_row_slot[r] = s->slot;
+      h_row_pos[r] = s->kv_len + j;
+    }
+    for (int j = 0; j < ntok[i]; j++, r++) {
+      int64_t id = tok[i][j];
+      if (id < 0 || id >= nbins)
+        PTTS_FAIL(PTTS_EINVAL, "generate: text embeddings: native: token id %d (%lld) out of range [0,%d)",
+                  j, (long long)id, nbins);
+      h_ids[r] = id;
+      h_row_slot[r] = s->slot;
+      h_row_pos[r] = s->kv_len + nvoice[i] + j;
+    }
+    int end = s->kv_len + nvoice[i] + ntok[i];
+    if (end > max_keys)
+      max_keys = end;
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_ids, h_ids, (size_t)R * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_row_slot, h_row_slot, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_row_pos, h_row_pos, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+  times.kernel_launches += embed_gather(d_ids, embed, x, R, D, st);
+  r = 0;
+  for (size_t i = 0; i < seqs.size(); i++) {
+    if (nvoice[i] > 0)
+      CUDA_TRY(cudaMemcpyAsync(x + (size_t)r * D, voice[i], (size_t)nvoice[i] * D * 4,
+                               cudaMemcpyHostToDevice, st));
+    r += nvoice[i] + ntok[i];
+  }
+  int rc = flow_forward(R, max_keys, false);
+  if (rc)
+    return rc;
+  for (size_t i = 0; i < seqs.size(); i++)
+    seqs[i]->kv_len += nvoice[i] + ntok[i];
+  cudaEventRecord(ev[1], st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]);
+  times.prefill_ms += ms;
+  times.prefill_tokens += R;
+  return PTTS_OK;
+}
+
+// flow_lm.go:262-353: out_norm, EOS logit, LSD Euler decode with the flow net.
+// Input: x [B, D] (transformer output), fh_noise [B, ldim].  Output fh_cur.
+int Engine::flow_head(int B, int lsd_steps) {
+  int64_t &nl = times.kernel_launches;
+  float *tvec = nullptr;
+  int rc = get_tvec(lsd_steps, &tvec);
+  if (rc)
+    return rc;
+  nl += layernorm(x, D, fh_last, D, B, D, out_norm.w, out_norm.b, out_norm.eps, nullptr, nullptr, 0, st);
+  nl += rowdot(fh_last, D, out_eos_lin.w, out_eos_bias, B, D, fh_eos, st);
+  {
+    GemmArgs g;
+    g.A = fh_last; g.lda = D; g.W = cond_embed.w; g.ldw = D; g.M = B; g.N = C; g.K = D;
+    g.epi.bias = cond_embed.b; g.epi.C = fh_cproj; g.epi.ldc = C;
+    nl += gemm(g, st);
+  }
+  CUDA_TRY(cudaMemcpyAsync(fh_cur, fh_noise, (size_t)B * ldim * 4, cudaMemcpyDeviceToDevice, st));
+  const float inv = 1.0f / (float)lsd_steps;
+  const int hid = rb[0].mlp0.out;
+  for (int i = 0; i < lsd_steps; i++) {
+    nl += add_vec_silu(fh_cproj, tvec + (size_t)i * C, fh_sy, B, C, st);
+    {
+      GemmArgs g;
+      g.A = fh_sy; g.lda = C; g.W = ada_all.w; g.ldw = C; g.M = B; g.N = ada_n; g.K = C;
+      g.epi.bias = ada_all.b; g.epi.C = fh_ada; g.epi.ldc = ada_n;
+      nl += gemm(g, st);
+    }
+    {
+      GemmArgs g;
+      g.A = fh_cur; g.lda = ldim; g.W = input_proj.w; g.ldw = ldim; g.M = B; g.N = C; g.K = ldim;
+      g.epi.bias = input_proj.b; g.epi.C = fh_x; g.epi.ldc = C;
+      nl += gemm(g, st);
+    }
+    for (int b = 0; b < depth; b++) {
+      const float *shift = fh_ada + (size_t)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
+      nl += layernorm(fh_x, C, fh_h, C, B, C, rb[b].in_ln.w, rb[b].in_ln.b, rb[b].in_ln.eps,
+                      scale, shift, ada_n, st);
+      GemmArgs g0;
+      g0.A = fh_h; g0.lda = C; g0.W = rb[b].mlp0.w; g0.ldw = C; g0.M = B; g0.N = hid; g0.K = C;
+      g0.epi.bias = rb[b].mlp0.b; g0.epi.act = ACT_SILU; g0.epi.C = fh_h2; g0.epi.ldc = hid;
+      nl += gemm(g0, st);
+      GemmArgs g2;
+      g2.A = fh_h2; g2.lda = hid; g2.W = rb[b].mlp2.w; g2.ldw = hid; g2.M = B; g2.N = C; g2.K = hid;
+      g2.epi.bias = rb[b].mlp2.b; g2.epi.mul = gate; g2.epi.ldmul = ada_n;
+      g2.epi.residual = fh_x; g2.epi.ldr = C; g2.epi.C = fh_x; g2.epi.ldc = C;
+      nl += gemm(g2, st);
+    }
+    const float *fshift = fh_ada + (size_t)depth * 3 * C, *fscale = fshift + C;
+    nl += layernorm(fh_x, C, fh_h, C, B, C, nullptr, nullptr, 1e-6f, fscale, fshift, ada_n, st);
+    GemmArgs gf;
+    gf.A = fh_h; gf.lda = C; gf.W = final_linear.w; gf.ldw = C; gf.M = B; gf.N = ldim; gf.K = C;
+    gf.epi.bias = final_linear.b; gf.epi.alpha = inv;
+    gf.epi.residual = fh_cur; gf.epi.ldr = ldim; gf.epi.C = fh_cur; gf.epi.ldc = ldim;
+    nl += gemm(gf, st);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PTTS_OK;
+}
+
+// One AR frame for B sequences (flow_lm.go:238-299).
+//   frames_in_host: [B,ldim] or null (feed back hist[slot][frames]);
+//   noise_host:     [B,ldim] or null (use d_noise[slot][frames]).
+int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
+                 const float *noise_host, int lsd_steps, float *lat_out_host,
+                 float *eos_out_host) {
+  const int B = (int)seqs.size();
+  if (B == 0)
+    return PTTS_OK;
+  if (B > max_batch)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: step batch %d exceeds max_batch %d", B, max_batch);
+  if (lsd_steps <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native: lsd decode steps must be >0");
+  int max_keys = 0;
+  for (int i = 0; i < B; i++) {
+    Seq *s = seqs[i];
+    if (s->kv_len + 1 > s->kv_cap)
+      PTTS_FAIL(PTTS_ENOMEM, "native-cuda: KV reservation exhausted (%d tokens)", s->kv_cap);
+    if (s->frames >= max_frames)
+      PTTS_FAIL(PTTS_ENOMEM, "native-cuda: frame budget exhausted (%d)", max_frames);
+    h_row_slot[i] = s->slot;
+    h_row_pos[i] = s->kv_len;
+    h_off_a[i] = ((int64_t)s->slot * (max_frames + 1) + s->frames) * ldim;     // input frame
+    h_off_b[i] = ((int64_t)s->slot * (max_frames + 1) + s->frames + 1) * ldim; // output frame
+    h_off_c[i] = ((int64_t)s->slot * max_frames + s->frames) * ldim;           // noise row
+    if (s->kv_len + 1 > max_keys)
+      max_keys = s->kv_len + 1;
+  }
+  int64_t &nl = times.kernel_launches;
+  cudaEventRecord(ev[2], st);
+  CUDA_TRY(cudaMemcpyAsync(d_row_slot, h_row_slot, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_row_pos, h_row_pos, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_off_b, h_off_b, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  if (frames_in_host) {
+    CUDA_TRY(cudaMemcpyAsync(fh_frames, frames_in_host, (size_t)B * ldim * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(d_off_a, h_off_a, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    nl += gather_rows(d_hist, d_off_a, fh_frames, B, ldim, st);
+  }
+  if (noise_host) {
+    CUDA_TRY(cudaMemcpyAsync(fh_noise, noise_host, (size_t)B * ldim * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(d_off_c, h_off_c, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    nl += gather_rows(d_noise, d_off_c, fh_noise, B, ldim, st);
+  }
+  nl += nan_to_bos(fh_frames, bos, fh_in, B, ldim, st);
+  {
+    GemmArgs g;
+    g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = B; g.N = D; g.K = ldim;
+    g.epi.bias = input_linear.b; g.epi.C = x; g.epi.ldc = D;
+    nl += gemm(g, st);
+  }
+  int rc = flow_forward(B, max_keys, false);
+  if (rc)
+    return rc;
+  cudaEventRecord(ev[3], st);
+  rc = flow_head(B, lsd_steps);
+  if (rc)
+    return rc;
+  nl += scatter_rows(fh_cur, d_hist, d_off_b, B, ldim, st);
+  cudaEventRecord(ev[4], st);
+  CUDA_TRY(cudaMemcpyAsync(h_eos, fh_eos, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (lat_out_host)
+    CUDA_TRY(cudaMemcpyAsync(h_lat, fh_cur, (size_t)B * ldim * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (eos_out_host)
+    memcpy(eos_out_host, h_eos, (size_t)B * 4);
+  if (lat_out_host)
+    memcpy(lat_out_host, h_lat, (size_t)B * ldim * 4);
+  for (Seq *s : seqs) {
+    s->kv_len++;
+    s->frames++;
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev[2], ev[4]);
+  times.step_ms += ms;
+  cudaEventElapsedTime(&ms, ev[3], ev[4]);
+  times.flow_head_ms += ms;
+  times.step_rows += B;
+  times.steps += 1;
+  debug_bufs["last_hidden"] = {fh_last, (size_t)B * D};
+  debug_bufs["step_x"] = {x, (size_t)B * D};
+  return PTTS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Mimi decode of a ragged batch (model.go:141-167 + mimi.go:719-789).
+// m_latin holds the gathered latent frames [total_frames, ldim].
+// ---------------------------------------------------------------------------
+int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) {
+  int64_t &nl = times.kernel_launches;
+  const int P = mimi_pad;
+  int Rb = 0;
+  for (auto &sg : segs) {
+    sg.row0 = Rb;
+    for (int i = 0; i < P; i++) {
+      h_mrow_pos[Rb + i] = -1;
+      h_mrow_frame0[Rb + i] = sg.frame0;
+      h_mmask[Rb + i] = 0;
+    }
+    int n = sg.n_frames * up_stride;
+    for (int i = 0; i < n; i++) {
+      h_mrow_pos[Rb + P + i] = i;
+      h_mrow_frame0[Rb + P + i] = sg.frame0;
+      h_mmask[Rb + P + i] = 1;
+    }
+    Rb += P + n;
+  }
+  if (Rb > mimi_rows_cap || total_frames > mimi_frames_cap)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: mimi group (%d frames, %d rows) exceeds workspace", total_frames, Rb);
+  cudaEventRecord(ev[5], st);
+  CUDA_TRY(cudaMemcpyAsync(d_mrow_pos, h_mrow_pos, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_mrow_frame0, h_mrow_frame0, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_mmask, h_mmask, (size_t)Rb, cudaMemcpyHostToDevice, st));
+  // latent -> mimi projection (folded denorm + 1x1 conv)
+  {
+    GemmArgs g;
+    g.A = m_latin; g.lda = ldim; g.W = proj.w; g.ldw = ldim; g.M = total_frames; g.N = Md; g.K = ldim;
+    g.epi.bias = proj.b; g.epi.C = m_lat; g.epi.ldc = Md;
+    nl += gemm(g, st);
+  }
+  nl += upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st);
+  debug_bufs["mimi_upsample"] = {m_x, (size_t)Rb * Md};
+  // decoder transformer (mimi.go:245-441)
+  for (int l = 0; l < ML; l++) {
+    DTLayer &ly = ml[l];
+    nl += layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st);
+    GemmArgs g;
+    g.A = m_nrm; g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
+    g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
+    nl += gemm(g, st);
+    nl += rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st);
+    nl += attention_window(m_qkv, 3 * Md, m_att, Md, Rb, Md, MH, d_mrow_pos, Mctx, st);
+    GemmArgs o;
+    o.A = m_att; o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
+    o.epi.colscale = ly.ls1; o.epi.residual = m_x; o.epi.ldr = Md; o.epi.C = m_x; o.epi.ldc = Md;
+    nl += gemm(o, st);
+    nl += layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st);
+    GemmArgs f1;
+    f1.A = m_nrm; f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
+    f1.epi.act = ACT_GELU; f1.epi.C = m_ff; f1.epi.ldc = MF;
+    nl += gemm(f1, st);
+    GemmArgs f2;
+    f2.A = m_ff; f2.lda = MF; f2.W = ly.l2.w; f2.ldw = MF; f2.M = Rb; f2.N = Md; f2.K = MF;
+    f2.epi.colscale = ly.ls2; f2.epi.residual = m_x; f2.epi.ldr = Md; f2.epi.C = m_x; f2.epi.ldc = Md;
+    if (l == ML - 1) { // pad rows must be zero again: they are the conv left context
+      f2.epi.rowmask = d_mmask;
+      f2.epi.mask_div = 1;
+    }
+    nl += gemm(f2, st);
+  }
+  debug_bufs["mimi_transformer"] = {m_x, (size_t)Rb * Md};
+  // SEANet (mimi.go:745-787): convs as GEMMs over overlapping channels-last rows
+  auto conv_gemm = [&](const DConvG &c, const float *in, int rows, int div, float *raw,
+                       float *elu, const float *residual) {
+    GemmArgs g;
+    g.A = in - (size_t)(c.taps - 1) * c.cin; g.lda = c.cin; g.W = c.w; g.ldw = c.K;
+    g.M = rows; g.N = c.N; g.K = c.K;
+    g.epi.bias = c.b; g.epi.C = raw; g.epi.ldc = c.N; g.epi.C2 = elu; g.epi.ldc2 = c.N;
+    g.epi.residual = residual; g.epi.ldr = c.N;
+    g.epi.rowmask = d_mmask; g.epi.mask_div = div;
+    nl += gemm(g, st);
+  };
+  conv_gemm(init_conv, m_x, Rb, 1, nullptr, m_y0e, nullptr);
+  debug_bufs["mimi_init_elu"] = {m_y0e, (size_t)Rb * init_conv.cout};
+  const float *cur = m_y0e;
+  int rows = Rb, div = 1;
+  for (int s = 0; s < 3; s++) {
+    conv_gemm(up[s], cur, rows, div, m_y[s], m_ye[s], nullptr); // rows*stride outputs
+    rows *= up[s].stride;
+    div *= up[s].stride;
+    conv_gemm(res1[s], m_ye[s], rows, div, nullptr, m_he[s], nullptr);
+    conv_gemm(res2[s], m_he[s], rows, div, nullptr, m_ye[s], m_y[s]); // elu(x + conv2(..))
+    cur = m_ye[s];
+  }
+  nl += final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, m_pcm, st);
+  cudaEventRecord(ev[6], st);
+  const int spb = div; // samples per base row
+  if (d2h) {
+    for (auto &sg : segs)
+      if (sg.host_out)
+        CUDA_TRY(cudaMemcpyAsync(sg.host_out, m_pcm + (size_t)(sg.row0 + P) * spb,
+                                 (size_t)sg.n_frames * up_stride * spb * 4, cudaMemcpyDeviceToHost, st));
+  }
+  cudaEventRecord(ev[7], st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev[5], ev[6]);
+  times.mimi_ms += ms;
+  cudaEventElapsedTime(&ms, ev[6], ev[7]);
+  times.d2h_ms += ms;
+  times.mimi_frames += total_frames;
+  debug_bufs["mimi_pcm"] = {m_pcm, (size_t)rows};
+  return PTTS_OK;
+}
+
+// Decode frame spans of live sequences, grouped to fit the workspace.
+int Engine::decode_seqs(const std::vector<Seq *> &seqs, const std::vector<int> &first,
+                        const std::vector<int> &count, const std::vector<float *> &outs,
+                        bool d2h) {
+  size_t i = 0;
+  const int max_segs = (mimi_rows_cap - up_stride * mimi_frames_cap) / mimi_pad;
+  while (i < seqs.size()) {
+    std::vector<MimiSeg> segs;
+    int tf = 0;
+    while (i < seqs.size() && (int)segs.size() < max_segs) {
+      int n = count[i];
+      if (n <= 0 || first[i] < 0 || first[i] + n > seqs[i]->frames)
+        PTTS_FAIL(PTTS_EINVAL, "native-cuda: decode span [%d,%d) outside generated frames %d",
+                  first[i], first[i] + n, seqs[i]->frames);
+      if (n > mimi_frames_cap)
+        PTTS_FAIL(PTTS_ENOMEM, "native-cuda: %d frames exceed mimi_group_frames %d", n, mimi_frames_cap);
+      if (tf + n > mimi_frames_cap)
+        break;
+      MimiSeg sg;
+      sg.n_frames = n;
+      sg.frame0 = tf;
+      sg.row0 = 0;
+      sg.host_out = outs[i];
+      for (int f = 0; f < n; f++)
+        h_moff[tf + f] = ((int64_t)seqs[i]->slot * (max_frames + 1) + first[i] + f + 1) * ldim;
+      tf += n;
+      segs.push_back(sg);
+      i++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_moff, h_moff, (size_t)tf * 8, cudaMemcpyHostToDevice, st));
+    times.kernel_launches += gather_rows(d_hist, d_moff, m_latin, tf, ldim, st);
+    int rc = mimi_decode(segs, tf, d2h);
+    if (rc)
+      return rc;
+  }
+  return PTTS_OK;
+}
+
+} // namespace ptts

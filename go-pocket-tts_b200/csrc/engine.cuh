@@ -1,0 +1,248 @@
+// engine.cuh — device-resident model + per-sequence state of the native-cuda
+// backend (replaces internal/native.Model and FlowLMState of the reference).
+#pragma once
+#include "../../include/pockettts_cuda.h"
+#include "kernels.cuh"
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace ptts {
+
+void set_error(const char *fmt, ...);
+#define PTTS_FAIL(code, ...)                                                   \
+  do {                                                                         \
+    ::ptts::set_error(__VA_ARGS__);                                            \
+    return (code);                                                             \
+  } while (0)
+#define CUDA_TRY(expr)                                                         \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      ::ptts::set_error("cuda: %s failed: %s", #expr, cudaGetErrorString(_e)); \
+      return PTTS_ECUDA;                                                       \
+    }                                                                          \
+  } while (0)
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct DLinear {
+  float *w = nullptr, *b = nullptr;
+  int in = 0, out = 0;
+};
+struct DLayerNorm {
+  float *w = nullptr, *b = nullptr;
+  int d = 0;
+  float eps = 1e-5f;
+};
+struct DTLayer {
+  DLayerNorm n1, n2;
+  DLinear in_proj, out_proj, l1, l2;
+  float *ls1 = nullptr, *ls2 = nullptr;
+};
+// Conv / ConvTranspose in GEMM form: W [N, taps*cin], A rows overlap (lda=cin).
+struct DConvG {
+  float *w = nullptr, *b = nullptr;
+  int cin = 0, cout = 0, taps = 0, stride = 1, N = 0, K = 0;
+};
+struct DResBlk {
+  DLayerNorm in_ln;
+  DLinear mlp0, mlp2;
+};
+
+struct Seq; // ptts_seq
+struct Request;
+
+struct MimiSeg { // one chunk inside a batched Mimi decode
+  int n_frames;
+  int frame0;    // first row in the gathered latent matrix
+  int row0;      // first base row (pad rows included)
+  float *host_out; // destination for PCM (may be null)
+};
+
+struct Engine {
+  ptts_config cfg{};
+  int device = 0;
+  cudaStream_t st = nullptr;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host;
+
+  // ---- dims ----
+  int D = 0, H = 16, Dh = 0, L = 0, F = 0, ldim = 32, nbins = 0;
+  int C = 0, depth = 0, nfreq = 0, ada_n = 0;
+  int Md = 0, MH = 8, ML = 0, MF = 0, Mctx = 250, up_stride = 16, up_k = 0;
+  ptts_model_info info{};
+
+  // ---- device weights ----
+  std::vector<void *> allocs;
+  float *embed = nullptr, *bos = nullptr;
+  std::vector<DTLayer> fl, ml;
+  DLinear input_linear, out_eos_lin, cond_embed, input_proj, ada_all, final_linear;
+  float out_eos_bias = 0.f;
+  DLayerNorm out_norm;
+  std::vector<DResBlk> rb;
+  float *rope_cos = nullptr, *rope_sin = nullptr;   // [8192, Dh/2]
+  float *mrope_cos = nullptr, *mrope_sin = nullptr; // [8192, MDh/2]
+  DLinear proj;       // folded latent->mimi projector [Md, ldim] + bias
+  float *up_w = nullptr; // depthwise upsample [Md, up_k]
+  DConvG init_conv, up[3], res1[3], res2[3];
+  float *final_w = nullptr;
+  float final_b = 0.f;
+  int final_cin = 0, final_k = 0;
+  // host copies needed for the (s,t) schedule precompute (flow_net.go:42-83)
+  struct TEmb {
+    std::vector<float> freqs, w1, b1, w2, b2, alpha;
+    int in = 0, hid = 0, out = 0;
+  } te[2];
+  std::map<int, float *> tvec_cache; // lsd_steps -> device [steps, C]
+
+  // ---- KV pool ----
+  float *kv_pool = nullptr;
+  int n_pages = 0, page_tokens = 16, max_pages = 0;
+  std::vector<int> free_pages, free_slots;
+  int32_t *d_pagetab = nullptr;
+  std::vector<int32_t> h_pagetab;
+  KvGeom kvg{};
+
+  // ---- per-slot frame storage ----
+  int max_batch = 0, max_frames = 0;
+  float *d_hist = nullptr;  // [slot][max_frames+1][32], row 0 = NaN (BOS)
+  float *d_noise = nullptr; // [slot][max_frames][32]
+
+  // ---- FlowLM workspaces (rows <= max_rows) ----
+  int max_rows = 0;
+  float *x = nullptr, *nrm = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr;
+  int32_t *d_row_slot = nullptr, *d_row_pos = nullptr;
+  int64_t *d_ids = nullptr, *d_off_a = nullptr, *d_off_b = nullptr, *d_off_c = nullptr;
+  // pinned host staging
+  int32_t *h_row_slot = nullptr, *h_row_pos = nullptr;
+  int64_t *h_ids = nullptr, *h_off_a = nullptr, *h_off_b = nullptr, *h_off_c = nullptr;
+  float *h_eos = nullptr, *h_lat = nullptr, *h_stage = nullptr;
+  // flow head (rows <= max_batch)
+  float *fh_in = nullptr, *fh_frames = nullptr, *fh_last = nullptr, *fh_eos = nullptr;
+  float *fh_cproj = nullptr, *fh_sy = nullptr, *fh_ada = nullptr, *fh_x = nullptr;
+  float *fh_h = nullptr, *fh_h2 = nullptr, *fh_cur = nullptr, *fh_noise = nullptr;
+
+  // ---- Mimi workspaces ----
+  int mimi_frames_cap = 0, mimi_rows_cap = 0, mimi_pad = 8;
+  float *m_latin = nullptr, *m_lat = nullptr;
+  float *m_x = nullptr, *m_nrm = nullptr, *m_qkv = nullptr, *m_att = nullptr, *m_ff = nullptr;
+  float *m_y0e = nullptr;
+  float *m_y[3] = {nullptr, nullptr, nullptr}, *m_ye[3] = {nullptr, nullptr, nullptr},
+        *m_he[3] = {nullptr, nullptr, nullptr};
+  float *m_pcm = nullptr;
+  int32_t *d_mrow_pos = nullptr, *d_mrow_frame0 = nullptr;
+  uint8_t *d_mmask = nullptr;
+  int32_t *h_mrow_pos = nullptr, *h_mrow_frame0 = nullptr;
+  uint8_t *h_mmask = nullptr;
+  int64_t *d_moff = nullptr, *h_moff = nullptr;
+
+  // ---- timing / counters ----
+  ptts_stage_times times{};
+  cudaEvent_t ev[8]{};
+  std::map<std::string, std::pair<const float *, size_t>> debug_bufs;
+
+  // ---- scheduler ----
+  std::mutex gpu_mu;   // serialises GPU passes (scheduler thread vs stage API)
+  std::mutex q_mu;
+  std::condition_variable q_cv;
+  std::deque<std::shared_ptr<Request>> queue;
+  std::unordered_map<int64_t, std::shared_ptr<Request>> tickets;
+  int64_t next_ticket = 1;
+  std::thread sched;
+  bool sched_running = false, sched_stop = false;
+
+  ~Engine();
+  int create(const ptts_config *c);
+  int load_tensor(const char *key, const int64_t *shape, int rank, int dtype, const void *p);
+  int finalize();
+
+  // allocation helpers
+  int dmalloc(void **p, size_t bytes);
+  int upload(const std::vector<float> &v, float **out);
+  int upload_key(const std::string &key, float **out, std::vector<int64_t> *shape);
+
+  // sequence resources
+  int seq_alloc(int tokens_needed, Seq **out);
+  void seq_free(Seq *s);
+  int sync_pagetab(Seq *s);
+
+  // passes (caller holds gpu_mu)
+  int flow_forward(int R, int max_keys, bool mask_none);
+  int prefill(const std::vector<Seq *> &seqs, const std::vector<const int64_t *> &tok,
+              const std::vector<int> &ntok, const std::vector<const float *> &voice,
+              const std::vector<int> &nvoice);
+  int import_voice_kv(Seq *s, const ptts_voice_kv *vk);
+  int step(const std::vector<Seq *> &seqs, const float *frames_in_host,
+           const float *noise_host, int lsd_steps, float *lat_out_host,
+           float *eos_out_host);
+  int flow_head(int B, int lsd_steps);
+  int get_tvec(int lsd_steps, float **out);
+  int mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h);
+  int decode_seqs(const std::vector<Seq *> &seqs, const std::vector<int> &first,
+                  const std::vector<int> &count, const std::vector<float *> &outs,
+                  bool d2h);
+
+  // scheduler
+  void sched_loop();
+  void ensure_sched();
+};
+
+struct Seq {
+  Engine *e = nullptr;
+  int slot = -1;
+  std::vector<int> pages;
+  int kv_len = 0;   // tokens in cache
+  int kv_cap = 0;   // tokens reserved
+  int frames = 0;   // latent frames generated
+};
+
+struct Request {
+  int64_t ticket = 0;
+  std::vector<int64_t> tokens;
+  const float *voice_emb = nullptr;
+  int voice_frames = 0;
+  const ptts_voice_kv *voice_kv = nullptr;
+  ptts_gen_cfg cfg{};
+  const float *noise = nullptr;
+  int noise_rows = 0;
+  float *pcm_out = nullptr;
+  int64_t pcm_cap = 0;
+  int max_steps = 0, lsd_steps = 1;
+  // state
+  Seq *seq = nullptr;
+  bool have_cd = false;
+  int countdown = 0;
+  std::atomic<bool> cancel{false};
+  std::vector<float> latents, eos;
+  std::chrono::steady_clock::time_point t_submit;
+  int finished_at_iter = 0;
+  // completion
+  std::mutex mu;
+  std::condition_variable cv;
+  bool done = false;
+  ptts_result res{};
+  std::string err;
+};
+
+int load_safetensors_file(Engine *e, const char *path);
+
+} // namespace ptts
+
+struct ptts_engine {
+  ptts::Engine impl;
+};
+struct ptts_seq {
+  ptts::Seq impl;
+};

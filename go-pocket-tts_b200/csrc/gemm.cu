@@ -1,0 +1,364 @@
+// gemm.cu — fp32 "TN" GEMMs (C = A * W^T, both K-contiguous) with the fused
+// epilogue of kernels.cuh.  Replaces the reference's per-output DotProduct loop
+// (internal/native/linear.go:117-182 over tensor/dot_amd64.s:34-116) and, through
+// overlapping A rows, its im2col Conv1D / dot-scatter ConvTranspose1D
+// (ops/conv1d.go:20-83, ops/convtranspose1d.go:73-148).
+//
+// Two regimes:
+//  * M <= 8   : weight-streaming skinny kernel.  HBM-bound: every weight byte is
+//               read exactly once with 128-bit non-allocating loads, activations
+//               come from L1/L2, warp-shuffle reduction, epilogue on lane 0.
+//  * M  > 8   : register-tiled SGEMM (CUDA cores, fp32 FMA, fp32 accumulate),
+//               double-buffered shared-memory tiles.  (The tcgen05 split-bf16
+//               path replaces this for the batched regime; see DESIGN.md.)
+#include "kernels.cuh"
+#include <math.h>
+
+namespace ptts {
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+  case ACT_GELU:
+    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  case ACT_SILU:
+    return v / (1.0f + expf(-v));
+  case ACT_ELU:
+    return v > 0.0f ? v : expf(v) - 1.0f;
+  default:
+    return v;
+  }
+}
+
+__device__ __forceinline__ float epi_one(const GemmEpi &e, float acc, int m, int n) {
+  float v = acc;
+  if (e.bias)
+    v += __ldg(e.bias + n);
+  v = act_apply(v, e.act);
+  if (e.colscale)
+    v *= __ldg(e.colscale + n);
+  if (e.mul)
+    v *= e.mul[(long)m * e.ldmul + n];
+  v *= e.alpha;
+  if (e.residual)
+    v += e.residual[(long)m * e.ldr + n];
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// skinny kernel: MR rows (<= 8), NC output columns per warp pass
+// ---------------------------------------------------------------------------
+template <int MR, int NC>
+__global__ void __launch_bounds__(256) gemv_kernel(GemmArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int M = g.M, N = g.N, K = g.K;
+  for (int n0 = warp * NC; n0 < N; n0 += nwarps * NC) {
+    float acc[MR][NC];
+#pragma unroll
+    for (int r = 0; r < MR; r++)
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        acc[r][c] = 0.0f;
+#pragma unroll 2
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 w[NC];
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        int n = n0 + c < N ? n0 + c : N - 1;
+        w[c] = ldg_stream(g.W + (long)n * g.ldw + k);
+      }
+#pragma unroll
+      for (int r = 0; r < MR; r++) {
+        int rr = r < M ? r : M - 1;
+        float4 x = *reinterpret_cast<const float4 *>(g.A + (long)rr * g.lda + k);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          acc[r][c] = fmaf(x.x, w[c].x, acc[r][c]);
+          acc[r][c] = fmaf(x.y, w[c].y, acc[r][c]);
+          acc[r][c] = fmaf(x.z, w[c].z, acc[r][c]);
+          acc[r][c] = fmaf(x.w, w[c].w, acc[r][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < MR; r++)
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        float v = acc[r][c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[r][c] = v;
+      }
+    // lanes 0..MR*NC-1 each finish one output (spreads the epilogue loads)
+    if (lane < MR * NC) {
+      int r = lane / NC, c = lane % NC;
+      float v = 0.0f;
+#pragma unroll
+      for (int rr = 0; rr < MR; rr++)
+#pragma unroll
+        for (int cc = 0; cc < NC; cc++)
+          if (rr == r && cc == c)
+            v = acc[rr][cc];
+      int n = n0 + c;
+      if (r < M && n < N) {
+        const GemmEpi &e = g.epi;
+        v = epi_one(e, v, r, n);
+        if (e.rowmask && !e.rowmask[r / e.mask_div])
+          v = 0.0f;
+        if (e.C)
+          e.C[(long)r * e.ldc + n] = v;
+        if (e.C2)
+          e.C2[(long)r * e.ldc2 + n] = act_apply(v, ACT_ELU);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tiled SGEMM
+// ---------------------------------------------------------------------------
+template <int BM, int BN, int RM, int RN>
+__global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)))
+    sgemm_tn_kernel(GemmArgs g) {
+  constexpr int BK = 16;
+  constexpr int TX = BN / (4 * RN), TY = BM / (4 * RM), NT = TX * TY;
+  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+  constexpr int A_F4 = BM * BK / 4, B_F4 = BN * BK / 4;
+  constexpr int A_PER = (A_F4 + NT - 1) / NT, B_PER = (B_F4 + NT - 1) / NT;
+  __shared__ __align__(16) float As[2][BK][LDA_S];
+  __shared__ __align__(16) float Bs[2][BK][LDB_S];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int M = g.M, N = g.N, K = g.K;
+
+  float4 ra[A_PER], rb[B_PER];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_PER; i++) {
+      int idx = tid + i * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < A_F4) {
+        int row = idx >> 2, kq = idx & 3;
+        int gm = m0 + row, gk = k0 + kq * 4;
+        if (gm < M && gk < K)
+          v = *reinterpret_cast<const float4 *>(g.A + (long)gm * g.lda + gk);
+      }
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; i++) {
+      int idx = tid + i * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < B_F4) {
+        int row = idx >> 2, kq = idx & 3;
+        int gn = n0 + row, gk = k0 + kq * 4;
+        if (gn < N && gk < K)
+          v = __ldg(reinterpret_cast<const float4 *>(g.W + (long)gn * g.ldw + gk));
+      }
+      rb[i] = v;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER; i++) {
+      int idx = tid + i * NT;
+      if (idx < A_F4) {
+        int row = idx >> 2, kq = (idx & 3) * 4;
+        As[buf][kq + 0][row] = ra[i].x;
+        As[buf][kq + 1][row] = ra[i].y;
+        As[buf][kq + 2][row] = ra[i].z;
+        As[buf][kq + 3][row] = ra[i].w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; i++) {
+      int idx = tid + i * NT;
+      if (idx < B_F4) {
+        int row = idx >> 2, kq = (idx & 3) * 4;
+        Bs[buf][kq + 0][row] = rb[i].x;
+        Bs[buf][kq + 1][row] = rb[i].y;
+        Bs[buf][kq + 2][row] = rb[i].z;
+        Bs[buf][kq + 3][row] = rb[i].w;
+      }
+    }
+  };
+
+  float acc[4 * RM][4 * RN];
+#pragma unroll
+  for (int i = 0; i < 4 * RM; i++)
+#pragma unroll
+    for (int j = 0; j < 4 * RN; j++)
+      acc[i][j] = 0.0f;
+
+  const int nk = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk)
+      gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      float a[4 * RM], b[4 * RN];
+#pragma unroll
+      for (int rm = 0; rm < RM; rm++) {
+        float4 t = *reinterpret_cast<const float4 *>(&As[buf][k][rm * (BM / RM) + ty * 4]);
+        a[rm * 4 + 0] = t.x; a[rm * 4 + 1] = t.y; a[rm * 4 + 2] = t.z; a[rm * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int rn = 0; rn < RN; rn++) {
+        float4 t = *reinterpret_cast<const float4 *>(&Bs[buf][k][rn * (BN / RN) + tx * 4]);
+        b[rn * 4 + 0] = t.x; b[rn * 4 + 1] = t.y; b[rn * 4 + 2] = t.z; b[rn * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4 * RM; i++)
+#pragma unroll
+        for (int j = 0; j < 4 * RN; j++)
+          acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk)
+      sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  const GemmEpi &e = g.epi;
+#pragma unroll
+  for (int rm = 0; rm < RM; rm++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int m = m0 + rm * (BM / RM) + ty * 4 + i;
+      if (m >= M)
+        continue;
+      const bool live = !e.rowmask || e.rowmask[m / e.mask_div];
+#pragma unroll
+      for (int rn = 0; rn < RN; rn++) {
+        const int n = n0 + rn * (BN / RN) + tx * 4;
+        if (n >= N)
+          continue;
+        float4 v;
+        v.x = epi_one(e, acc[rm * 4 + i][rn * 4 + 0], m, n + 0);
+        v.y = epi_one(e, acc[rm * 4 + i][rn * 4 + 1], m, n + 1);
+        v.z = epi_one(e, acc[rm * 4 + i][rn * 4 + 2], m, n + 2);
+        v.w = epi_one(e, acc[rm * 4 + i][rn * 4 + 3], m, n + 3);
+        if (!live)
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.C)
+          *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = v;
+        if (e.C2) {
+          float4 u;
+          u.x = act_apply(v.x, ACT_ELU);
+          u.y = act_apply(v.y, ACT_ELU);
+          u.z = act_apply(v.z, ACT_ELU);
+          u.w = act_apply(v.w, ACT_ELU);
+          *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u;
+        }
+      }
+    }
+}
+
+template <int BM, int BN, int RM, int RN>
+static void launch_sgemm(const GemmArgs &g, cudaStream_t st) {
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
+  sgemm_tn_kernel<BM, BN, RM, RN><<<grid, NT, 0, st>>>(g);
+}
+
+template <int MR>
+static void launch_gemv(const GemmArgs &g, cudaStream_t st) {
+  // one column per warp pass keeps every SM streaming for N ~ 1e3
+  const int warps_per_cta = 8;
+  if (g.N >= 8192) {
+    int ctas = (g.N / 2 + warps_per_cta - 1) / warps_per_cta;
+    if (ctas > 148 * 8)
+      ctas = 148 * 8;
+    gemv_kernel<MR, 2><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+  } else {
+    int ctas = (g.N + warps_per_cta - 1) / warps_per_cta;
+    if (ctas > 148 * 8)
+      ctas = 148 * 8;
+    gemv_kernel<MR, 1><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+  }
+}
+
+int gemm(const GemmArgs &g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0)
+    return 0;
+  if (g.M <= 8) {
+    if (g.M == 1)
+      launch_gemv<1>(g, st);
+    else if (g.M == 2)
+      launch_gemv<2>(g, st);
+    else if (g.M <= 4)
+      launch_gemv<4>(g, st);
+    else
+      launch_gemv<8>(g, st);
+    return 1;
+  }
+  auto ctas = [&](int bm, int bn) {
+    return (long)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
+  };
+  const long want = 148; // at least one CTA per SM before growing the tile
+  if (g.N <= 32) {
+    if (ctas(128, 32) >= want)
+      launch_sgemm<128, 32, 2, 1>(g, st);
+    else
+      launch_sgemm<64, 32, 2, 1>(g, st);
+  } else if (ctas(128, 128) >= want && g.N >= 128) {
+    launch_sgemm<128, 128, 2, 2>(g, st);
+  } else if (ctas(64, 128) >= want && g.N >= 128) {
+    launch_sgemm<64, 128, 2, 2>(g, st);
+  } else if (ctas(64, 64) >= want || g.M > 32) {
+    launch_sgemm<64, 64, 2, 2>(g, st);
+  } else {
+    launch_sgemm<32, 64, 1, 2>(g, st);
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    rowdot_kernel(const float *A, long lda, const float *w, float bias0, int M,
+                  int K, float *out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M)
+    return;
+  const float *a = A + (long)row * lda;
+  float s = 0.0f;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 x = *reinterpret_cast<const float4 *>(a + k);
+    float4 y = __ldg(reinterpret_cast<const float4 *>(w + k));
+    s = fmaf(x.x, y.x, s);
+    s = fmaf(x.y, y.y, s);
+    s = fmaf(x.z, y.z, s);
+    s = fmaf(x.w, y.w, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0)
+    out[row] = s + bias0;
+}
+
+int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
+           float *out, cudaStream_t st) {
+  if (M <= 0)
+    return 0;
+  int ctas = (M + 7) / 8;
+  rowdot_kernel<<<ctas, 256, 0, st>>>(A, lda, w, bias0, M, K, out);
+  return 1;
+}
+
+} // namespace ptts

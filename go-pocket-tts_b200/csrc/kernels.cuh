@@ -1,0 +1,131 @@
+// kernels.cuh — launch wrappers of the sm_100a kernels behind the native-cuda
+// backend.  Layout conventions:
+//   * activations are row-major fp32 [rows, channels] ("channels-last" for the
+//     SEANet stack, so a causal Conv1d over k taps is a GEMM whose A rows
+//     overlap: row stride = Cin, K = k*Cin);
+//   * weights are [N, K] row-major (K contiguous), exactly the reference's
+//     Linear layout (internal/native/linear.go:12-17);
+//   * FlowLM K/V live in a paged pool
+//     kv[page][layer][k|v][head][tok_in_page][head_dim].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptts {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_ELU = 3 };
+
+// Fused GEMM epilogue, applied in this order (matches the reference op order:
+// Linear bias -> activation -> LayerScale -> adaLN gate -> residual add):
+//   v = acc + bias[n]; v = act(v); v *= colscale[n]; v *= mul[m,n];
+//   v *= alpha; v += residual[m,n]; if (!rowmask) v = 0;
+//   C[m,n] = v; C2[m,n] = elu(v)
+struct GemmEpi {
+  const float *bias = nullptr;
+  const float *colscale = nullptr;
+  const float *mul = nullptr;
+  long ldmul = 0;
+  const float *residual = nullptr;
+  long ldr = 0;
+  float alpha = 1.0f;
+  int act = ACT_NONE;
+  float *C = nullptr;
+  long ldc = 0;
+  float *C2 = nullptr;
+  long ldc2 = 0;
+  const uint8_t *rowmask = nullptr; // row m is live iff rowmask[m / mask_div]
+  int mask_div = 1;
+};
+
+struct GemmArgs {
+  const float *A = nullptr; // row m at A + m*lda, K contiguous floats
+  long lda = 0;
+  const float *W = nullptr; // [N, K]
+  long ldw = 0;
+  int M = 0, N = 0, K = 0;
+  GemmEpi epi;
+};
+
+// C = epi(A * W^T).  Chooses the weight-streaming skinny kernel for M <= 8 and
+// a tiled SGEMM otherwise.  Requires K % 4 == 0, N % 4 == 0 for the tiled path
+// (N == 1 goes through rowdot).  Returns the number of kernels launched.
+int gemm(const GemmArgs &g, cudaStream_t st);
+// out[m] = dot(A[m,:K], w) + bias0   (N == 1 linear: out_eos)
+int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
+           float *out, cudaStream_t st);
+
+// LayerNorm over the last dim with optional affine and optional adaLN
+// modulation: out = (LN(x)*w + b) * (1 + scale[m,:]) + shift[m,:].
+// (linear.go:265-329, tensor_util.go:175-193)
+int layernorm(const float *x, long ldx, float *out, long ldo, int rows, int D,
+              const float *w, const float *b, float eps, const float *scale,
+              const float *shift, long ldmod, cudaStream_t st);
+
+// out[r,:] = table[ids[r],:]   (conditioner.go:31-53)
+int embed_gather(const int64_t *ids, const float *table, float *out, int rows,
+                 int D, cudaStream_t st);
+
+struct KvGeom {
+  float *pool;          // paged KV pool
+  const int32_t *pagetab; // [slots, max_pages]
+  int max_pages, page_tokens, n_layers, n_heads, head_dim;
+};
+
+// RoPE (interleaved pairs, rope.go:81-105) on q and k of qkv [R, 3*D] in place
+// for q, and K/V append into the paged cache at (slot, pos)
+// (flow_transformer.go:32-67).
+int rope_kv_append(float *qkv, int rows, const int32_t *row_slot,
+                   const int32_t *row_pos, const float *cosT, const float *sinT,
+                   const KvGeom &kv, int layer, cudaStream_t st);
+// Raw K/V rows [T, H*Dh] into pages of one slot (voice model-state import,
+// flow_transformer.go:517-631).
+int kv_write_rows(const float *rows_k, const float *rows_v, int T, int slot,
+                  int pos0, const KvGeom &kv, int layer, cudaStream_t st);
+// Reads valid K or V rows of a slot back as [H, T, Dh] (parity tap).
+int kv_read_rows(float *out, int T, int slot, const KvGeom &kv, int layer,
+                 int which, cudaStream_t st);
+
+// Causal attention of each row against its sequence's paged cache: row r at
+// position p sees keys 0..p (attention.go:307-484 with posK[i] = i < len).
+// q is read from qkv[r, 0:D], output to out[r, 0:D].
+int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
+                    const int32_t *row_slot, const int32_t *row_pos,
+                    const KvGeom &kv, int layer, int max_keys, cudaStream_t st);
+
+// RoPE in place on q and k of qkv [R, 3*D] with per-row positions (<0 = skip).
+int rope_inplace(float *qkv, int rows, int D, int n_heads, const int32_t *row_pos,
+                 const float *cosT, const float *sinT, cudaStream_t st);
+// Sliding-window causal attention inside contiguous segments: row r at local
+// position p = row_pos[r] attends rows r-j, 0 <= j < min(ctx, p+1)
+// (mimi.go:386-441, attention.go:473-484).  Pad rows (p < 0) produce zeros.
+int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
+                     int D, int n_heads, const int32_t *row_pos, int ctx,
+                     cudaStream_t st);
+
+// x_in[r,:] = isnan(frames[r,i]) ? bos[i] : frames[r,i]  (tensor_util.go:242-271)
+int nan_to_bos(const float *frames, const float *bos, float *out, int rows,
+               int ldim, cudaStream_t st);
+// out = silu(a[m,:] + tvec[:])   (flow_net.go:334-343 + resblock SiLU(y))
+int add_vec_silu(const float *a, const float *tvec, float *out, int rows, int C,
+                 cudaStream_t st);
+// gathers/scatters of [*,32] latent rows by index
+int gather_rows(const float *src, const int64_t *src_off, float *dst, int rows,
+                int width, cudaStream_t st);
+int scatter_rows(const float *src, float *dst, const int64_t *dst_off, int rows,
+                 int width, cudaStream_t st);
+
+// Depthwise ConvTranspose1d (stride s, kernel k<=2s, right trim k-s) from
+// per-frame features lat [frames, C] into the padded channels-last layout:
+// out[row, c], row_frame[row] = source frame index of that row's segment start
+// (or -1 on pad rows), row_pos = local position.  (mimi.go:116-125,
+// convtranspose1d.go:154-202)
+int upsample_depthwise(const float *lat, const float *w, float *out, int rows,
+                       int C, int stride, int k, const int32_t *row_pos,
+                       const int32_t *row_frame0, cudaStream_t st);
+// Final Conv1d Cin->1 over channels-last rows: pcm[r] = dot(x[r-k+1..r, :], w) + b
+int final_conv(const float *x, int rows, int Cin, int k, const float *w,
+               float bias, const uint8_t *rowmask, int mask_div, float *pcm,
+               cudaStream_t st);
+int fill_zero(float *p, size_t n, cudaStream_t st);
+
+} // namespace ptts

@@ -1,0 +1,648 @@
+// scheduler.cu — continuous-batching scheduler + the extern "C" boundary.
+//
+// Replaces, behind the same blocking GenerateAudio contract, the reference's
+// per-request B=1 loop whose AR step is serialised by rngMu
+// (internal/tts/runtime_native_safetensors.go:155-198) and the server's
+// semaphore worker pool (internal/server/server.go:114,402-421): every
+// in-flight request owns a sequence slot; each scheduler iteration admits and
+// prefills new requests, runs ONE batched AR frame for all live sequences,
+// applies the reference's EOS-countdown rule per request on the host, and
+// batch-decodes finished chunks through Mimi.
+#include "engine.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace ptts {
+
+const char *last_error();
+
+static int resolve_max_steps(const ptts_gen_cfg &c, int ntok) {
+  // runtime_native_safetensors.go:61-67 + internal/text/prepare.go:38-48
+  int ms = c.max_steps;
+  if (ms <= 0)
+    ms = c.estimated_max_steps;
+  if (ms <= 0) {
+    int n = ntok < 0 ? 0 : ntok;
+    ms = (int)std::ceil(((double)n / 3.0 + 2.0) * 12.5);
+  }
+  return ms;
+}
+
+static void complete(const std::shared_ptr<Request> &r, int status, const char *msg) {
+  std::unique_lock<std::mutex> lk(r->mu);
+  r->res.status = status;
+  if (msg)
+    r->err = msg;
+  auto now = std::chrono::steady_clock::now();
+  r->res.total_ms = std::chrono::duration<double, std::milli>(now - r->t_submit).count();
+  r->done = true;
+  r->cv.notify_all();
+}
+
+void Engine::ensure_sched() {
+  std::unique_lock<std::mutex> lk(q_mu);
+  if (!sched_running) {
+    sched_running = true;
+    sched = std::thread([this] { sched_loop(); });
+  }
+}
+
+void Engine::sched_loop() {
+  cudaSetDevice(device);
+  std::vector<std::shared_ptr<Request>> active, pending;
+  int pending_frames = 0;
+  long iter = 0;
+  for (;;) {
+    std::vector<std::shared_ptr<Request>> candidates;
+    {
+      std::unique_lock<std::mutex> lk(q_mu);
+      if (active.empty() && pending.empty())
+        q_cv.wait(lk, [&] { return sched_stop || !queue.empty(); });
+      if (sched_stop) {
+        for (auto &r : queue)
+          complete(r, PTTS_ECANCELED, "native-cuda: engine destroyed");
+        queue.clear();
+        break;
+      }
+      // take as many queued requests as there could be room for; resources are
+      // claimed below under gpu_mu, leftovers are pushed back in order.
+      while (!queue.empty() && (int)(active.size() + pending.size() + candidates.size()) < max_batch) {
+        candidates.push_back(queue.front());
+        queue.pop_front();
+      }
+    }
+    std::unique_lock<std::mutex> gl(gpu_mu);
+    iter++;
+    // ---- cancellation (ctx.Err() check per step, :156-159) ----
+    for (size_t i = 0; i < active.size();) {
+      if (active[i]->cancel) {
+        seq_free(active[i]->seq);
+        delete reinterpret_cast<ptts_seq *>(active[i]->seq);
+        active[i]->seq = nullptr;
+        complete(active[i], PTTS_ECANCELED, "context canceled");
+        active.erase(active.begin() + i);
+      } else
+        i++;
+    }
+    // ---- admission + batched prefill ----
+    std::vector<std::shared_ptr<Request>> admitted, leftover;
+    int ptoks = 0;
+    for (auto &r : candidates) {
+      if (r->cancel) {
+        complete(r, PTTS_ECANCELED, "context canceled");
+        continue;
+      }
+      if (!leftover.empty()) { // keep FIFO order once one had to wait
+        leftover.push_back(r);
+        continue;
+      }
+      int voice_tokens = r->voice_kv ? r->voice_kv->layers[0].offset : r->voice_frames;
+      int prompt = (r->voice_kv ? 0 : r->voice_frames) + (int)r->tokens.size();
+      int need = voice_tokens + (int)r->tokens.size() + r->max_steps;
+      if (ptoks + prompt > max_rows) {
+        leftover.push_back(r);
+        continue;
+      }
+      Seq *s = nullptr;
+      int rc = seq_alloc(need, &s);
+      if (rc == PTTS_ENOMEM && (!active.empty() || !pending.empty() || !admitted.empty()) &&
+          need <= cfg.max_seq_tokens) {
+        leftover.push_back(r); // back-pressure: wait for pages / slots
+        continue;
+      }
+      if (rc) {
+        complete(r, rc, last_error());
+        continue;
+      }
+      r->seq = s;
+      ptoks += prompt;
+      admitted.push_back(r);
+    }
+    if (!leftover.empty()) {
+      std::unique_lock<std::mutex> lk(q_mu);
+      for (auto it = leftover.rbegin(); it != leftover.rend(); ++it)
+        queue.push_front(*it);
+    }
+    if (!admitted.empty()) {
+      std::vector<Seq *> seqs;
+      std::vector<const int64_t *> tok;
+      std::vector<int> ntok, nvoice;
+      std::vector<const float *> voice;
+      int rc = PTTS_OK;
+      for (auto &r : admitted) {
+        auto now = std::chrono::steady_clock::now();
+        r->res.queue_ms = std::chrono::duration<double, std::milli>(now - r->t_submit).count();
+        cudaMemcpyAsync(d_noise + (size_t)r->seq->slot * max_frames * ldim, r->noise,
+                        (size_t)r->max_steps * ldim * 4, cudaMemcpyHostToDevice, st);
+        if (r->voice_kv && rc == PTTS_OK)
+          rc = import_voice_kv(r->seq, r->voice_kv);
+        seqs.push_back(r->seq);
+        tok.push_back(r->tokens.data());
+        ntok.push_back((int)r->tokens.size());
+        voice.push_back(r->voice_kv ? nullptr : r->voice_emb);
+        nvoice.push_back(r->voice_kv ? 0 : r->voice_frames);
+      }
+      if (rc == PTTS_OK)
+        rc = prefill(seqs, tok, ntok, voice, nvoice);
+      if (rc) {
+        std::string msg = last_error();
+        for (auto &r : admitted) {
+          seq_free(r->seq);
+          delete reinterpret_cast<ptts_seq *>(r->seq);
+          r->seq = nullptr;
+          complete(r, rc, msg.c_str());
+        }
+      } else {
+        for (auto &r : admitted)
+          active.push_back(r);
+      }
+    }
+    // ---- one AR frame for every live sequence ----
+    if (!active.empty()) {
+      // group by lsd_steps (normally a single group)
+      std::map<int, std::vector<size_t>> groups;
+      for (size_t i = 0; i < active.size(); i++)
+        groups[active[i]->lsd_steps].push_back(i);
+      std::vector<char> finished(active.size(), 0), failed(active.size(), 0);
+      std::string fail_msg;
+      int fail_rc = 0;
+      for (auto &kv : groups) {
+        std::vector<Seq *> seqs;
+        for (size_t i : kv.second)
+          seqs.push_back(active[i]->seq);
+        std::vector<float> eos(seqs.size());
+        int rc = step(seqs, nullptr, nullptr, kv.first, nullptr, eos.data());
+        if (rc) {
+          fail_rc = rc;
+          fail_msg = last_error();
+          for (size_t i : kv.second)
+            failed[i] = 1;
+          continue;
+        }
+        auto now = std::chrono::steady_clock::now();
+        for (size_t j = 0; j < kv.second.size(); j++) {
+          Request &r = *active[kv.second[j]];
+          const int stepi = r.seq->frames - 1; // 0-based step just executed
+          r.eos.push_back(eos[j]);
+          if (stepi == 0)
+            r.res.first_frame_ms = std::chrono::duration<double, std::milli>(now - r.t_submit).count();
+          // runtime_native_safetensors.go:178-190
+          bool is_eos = eos[j] > (float)r.cfg.eos_threshold;
+          if (r.cfg.force_eos_step >= 0 && stepi >= r.cfg.force_eos_step)
+            is_eos = true;
+          bool stop = false;
+          if (is_eos && !r.have_cd) {
+            r.have_cd = true;
+            r.countdown = r.cfg.frames_after_eos;
+          }
+          if (r.have_cd) {
+            if (r.countdown == 0)
+              stop = true;
+            else
+              r.countdown--;
+          }
+          if (!stop && r.seq->frames >= r.max_steps)
+            stop = true;
+          if (stop)
+            finished[kv.second[j]] = 1;
+        }
+      }
+      std::vector<std::shared_ptr<Request>> keep;
+      for (size_t i = 0; i < active.size(); i++) {
+        auto &r = active[i];
+        if (failed[i]) {
+          seq_free(r->seq);
+          delete reinterpret_cast<ptts_seq *>(r->seq);
+          r->seq = nullptr;
+          complete(r, fail_rc, fail_msg.c_str());
+        } else if (finished[i]) {
+          r->finished_at_iter = (int)iter;
+          pending_frames += r->seq->frames;
+          pending.push_back(r);
+        } else
+          keep.push_back(r);
+      }
+      active.swap(keep);
+    }
+    // ---- batched Mimi decode of finished chunks ----
+    bool queue_empty;
+    {
+      std::unique_lock<std::mutex> lk(q_mu);
+      queue_empty = queue.empty();
+    }
+    bool trigger = !pending.empty() &&
+                   (pending_frames >= mimi_frames_cap / 2 || (active.empty() && queue_empty) ||
+                    iter - pending.front()->finished_at_iter >= 16 ||
+                    (int)(active.size() + pending.size()) >= max_batch);
+    if (trigger) {
+      std::vector<Seq *> seqs;
+      std::vector<int> first, count;
+      std::vector<float *> outs;
+      for (auto &r : pending) {
+        int n = r->seq->frames;
+        r->latents.resize((size_t)n * ldim);
+        cudaMemcpyAsync(r->latents.data(),
+                        d_hist + ((size_t)r->seq->slot * (max_frames + 1) + 1) * ldim,
+                        (size_t)n * ldim * 4, cudaMemcpyDeviceToHost, st);
+        seqs.push_back(r->seq);
+        first.push_back(0);
+        count.push_back(n);
+        outs.push_back((r->cfg.flags & PTTS_REQ_NO_PCM_D2H) ? nullptr : r->pcm_out);
+      }
+      int rc = decode_seqs(seqs, first, count, outs, true);
+      cudaStreamSynchronize(st);
+      std::string msg = rc ? last_error() : "";
+      for (auto &r : pending) {
+        r->res.n_frames = r->seq->frames;
+        r->res.n_samples = (int64_t)r->seq->frames * info.samples_per_frame;
+        seq_free(r->seq);
+        delete reinterpret_cast<ptts_seq *>(r->seq);
+        r->seq = nullptr;
+        complete(r, rc, rc ? msg.c_str() : nullptr);
+      }
+      pending.clear();
+      pending_frames = 0;
+    }
+  }
+}
+
+} // namespace ptts
+
+// ===========================================================================
+// extern "C"
+// ===========================================================================
+using namespace ptts;
+
+extern "C" {
+
+const char *ptts_last_error(void) { return ptts::last_error(); }
+const char *ptts_version(void) { return "pockettts-b200 native-cuda 0.1 (sm_100a)"; }
+
+int ptts_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+int ptts_create(const ptts_config *cfg, ptts_engine **out) {
+  if (!out)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: ptts_create: out is NULL");
+  *out = nullptr;
+  ptts_config c{};
+  if (cfg)
+    c = *cfg;
+  ptts_engine *e = new ptts_engine();
+  int rc = e->impl.create(&c);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return PTTS_OK;
+}
+
+void ptts_destroy(ptts_engine *e) {
+  if (e)
+    delete e;
+}
+
+int ptts_load_tensor(ptts_engine *e, const char *key, const int64_t *shape, int32_t rank,
+                     int32_t dtype, const void *host_ptr) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  return e->impl.load_tensor(key, shape, rank, dtype, host_ptr);
+}
+
+int ptts_load_safetensors(ptts_engine *e, const char *path) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  return load_safetensors_file(&e->impl, path);
+}
+
+int ptts_finalize_weights(ptts_engine *e) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  int rc = e->impl.finalize();
+  if (rc == PTTS_OK && cudaDeviceSynchronize() != cudaSuccess)
+    PTTS_FAIL(PTTS_ECUDA, "cuda: device synchronize after weight upload failed");
+  return rc;
+}
+
+int ptts_model_info_get(ptts_engine *e, ptts_model_info *out) {
+  if (!e || !e->impl.finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable");
+  *out = e->impl.info;
+  return PTTS_OK;
+}
+
+static int validate_request(Engine &E, int32_t n_tokens, const float *voice_emb, int32_t voice_frames,
+                            const ptts_voice_kv *voice_kv, const ptts_gen_cfg *cfg,
+                            const float *noise, int32_t noise_rows, float *pcm_out, int64_t pcm_cap,
+                            int *max_steps_out) {
+  if (!E.finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable");
+  if (n_tokens <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "generate: token slice must not be empty");
+  if (!cfg)
+    PTTS_FAIL(PTTS_EINVAL, "generate: config is NULL");
+  if (voice_emb && voice_kv)
+    PTTS_FAIL(PTTS_EINVAL, "generate: voice embedding and voice model state are mutually exclusive");
+  if (voice_emb && voice_frames <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "generate: build voice tensor: voice_frames must be > 0");
+  if (voice_kv && (voice_kv->n_layers <= 0 || !voice_kv->layers))
+    PTTS_FAIL(PTTS_EINVAL, "generate: load voice model state: no layers");
+  int ms = resolve_max_steps(*cfg, n_tokens);
+  if (ms > E.max_frames)
+    PTTS_FAIL(PTTS_ENOMEM, "generate: max steps %d exceeds engine max_frames %d", ms, E.max_frames);
+  if (!noise || noise_rows < ms)
+    PTTS_FAIL(PTTS_EINVAL, "generate: need %d noise rows, got %d", ms, noise_rows);
+  bool no_pcm = (cfg->flags & PTTS_REQ_NO_PCM_D2H) != 0;
+  if (!no_pcm && (!pcm_out || pcm_cap < (int64_t)ms * E.info.samples_per_frame))
+    PTTS_FAIL(PTTS_EINVAL, "generate: pcm buffer too small (%lld < %lld)", (long long)pcm_cap,
+              (long long)ms * E.info.samples_per_frame);
+  *max_steps_out = ms;
+  return PTTS_OK;
+}
+
+int ptts_submit(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const float *voice_emb,
+                int32_t voice_frames, const ptts_voice_kv *voice_kv, const ptts_gen_cfg *cfg,
+                const float *noise, int32_t noise_rows, float *pcm_out, int64_t pcm_cap,
+                int64_t *ticket) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  Engine &E = e->impl;
+  int ms = 0;
+  int rc = validate_request(E, n_tokens, voice_emb, voice_frames, voice_kv, cfg, noise, noise_rows,
+                            pcm_out, pcm_cap, &ms);
+  if (rc)
+    return rc;
+  if (!tokens || !ticket)
+    PTTS_FAIL(PTTS_EINVAL, "generate: NULL argument");
+  auto r = std::make_shared<Request>();
+  r->tokens.assign(tokens, tokens + n_tokens);
+  r->voice_emb = voice_emb;
+  r->voice_frames = voice_emb ? voice_frames : 0;
+  r->voice_kv = voice_kv;
+  r->cfg = *cfg;
+  r->noise = noise;
+  r->noise_rows = noise_rows;
+  r->pcm_out = pcm_out;
+  r->pcm_cap = pcm_cap;
+  r->max_steps = ms;
+  r->lsd_steps = cfg->lsd_decode_steps > 0 ? cfg->lsd_decode_steps : 1;
+  r->t_submit = std::chrono::steady_clock::now();
+  E.ensure_sched();
+  {
+    std::unique_lock<std::mutex> lk(E.q_mu);
+    r->ticket = E.next_ticket++;
+    E.tickets[r->ticket] = r;
+    E.queue.push_back(r);
+    *ticket = r->ticket;
+  }
+  E.q_cv.notify_all();
+  return PTTS_OK;
+}
+
+static std::shared_ptr<Request> find_ticket(Engine &E, int64_t t) {
+  std::unique_lock<std::mutex> lk(E.q_mu);
+  auto it = E.tickets.find(t);
+  return it == E.tickets.end() ? nullptr : it->second;
+}
+
+int ptts_wait(ptts_engine *e, int64_t ticket, ptts_result *result) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  auto r = find_ticket(e->impl, ticket);
+  if (!r)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: unknown ticket %lld", (long long)ticket);
+  std::unique_lock<std::mutex> lk(r->mu);
+  r->cv.wait(lk, [&] { return r->done; });
+  if (result)
+    *result = r->res;
+  if (r->res.status != PTTS_OK)
+    set_error("%s", r->err.c_str());
+  return r->res.status;
+}
+
+int ptts_cancel(ptts_engine *e, int64_t ticket) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  auto r = find_ticket(e->impl, ticket);
+  if (!r)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: unknown ticket %lld", (long long)ticket);
+  r->cancel = true;
+  e->impl.q_cv.notify_all();
+  return PTTS_OK;
+}
+
+int ptts_ticket_latents(ptts_engine *e, int64_t ticket, float *latents, float *eos_logits,
+                        int32_t cap_frames) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  auto r = find_ticket(e->impl, ticket);
+  if (!r || !r->done)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda: ticket not complete");
+  int n = r->res.n_frames;
+  if (cap_frames < n)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: latents buffer too small (%d < %d)", cap_frames, n);
+  if (latents)
+    memcpy(latents, r->latents.data(), (size_t)n * PTTS_LATENT_DIM * 4);
+  if (eos_logits)
+    memcpy(eos_logits, r->eos.data(), (size_t)n * 4);
+  return n;
+}
+
+int ptts_ticket_release(ptts_engine *e, int64_t ticket) {
+  if (!e)
+    return PTTS_OK;
+  std::unique_lock<std::mutex> lk(e->impl.q_mu);
+  e->impl.tickets.erase(ticket);
+  return PTTS_OK;
+}
+
+int ptts_generate_audio(ptts_engine *e, const int64_t *tokens, int32_t n_tokens,
+                        const float *voice_emb, int32_t voice_frames, const ptts_voice_kv *voice_kv,
+                        const ptts_gen_cfg *cfg, const float *noise, int32_t noise_rows,
+                        float *pcm_out, int64_t pcm_cap, ptts_result *result) {
+  int64_t t = 0;
+  int rc = ptts_submit(e, tokens, n_tokens, voice_emb, voice_frames, voice_kv, cfg, noise, noise_rows,
+                       pcm_out, pcm_cap, &t);
+  if (rc)
+    return rc;
+  rc = ptts_wait(e, t, result);
+  ptts_ticket_release(e, t);
+  return rc;
+}
+
+// ---- stage-level API ------------------------------------------------------
+int ptts_seq_open(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const float *voice_emb,
+                  int32_t voice_frames, const ptts_voice_kv *voice_kv, int32_t reserve_frames,
+                  ptts_seq **out) {
+  if (!e || !e->impl.finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable");
+  if (!out)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: seq_open: out is NULL");
+  if (voice_emb && voice_kv)
+    PTTS_FAIL(PTTS_EINVAL, "generate: voice embedding and voice model state are mutually exclusive");
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  if (reserve_frames <= 0)
+    reserve_frames = E.max_frames;
+  int vt = voice_kv ? voice_kv->layers[0].offset : (voice_emb ? voice_frames : 0);
+  Seq *s = nullptr;
+  int rc = E.seq_alloc(vt + n_tokens + reserve_frames, &s);
+  if (rc)
+    return rc;
+  if (voice_kv)
+    rc = E.import_voice_kv(s, voice_kv);
+  if (rc == PTTS_OK && (n_tokens > 0 || (voice_emb && voice_frames > 0)))
+    rc = E.prefill({s}, {tokens}, {n_tokens}, {voice_kv ? nullptr : voice_emb},
+                   {voice_kv || !voice_emb ? 0 : voice_frames});
+  if (rc) {
+    E.seq_free(s);
+    delete reinterpret_cast<ptts_seq *>(s);
+    return rc;
+  }
+  *out = reinterpret_cast<ptts_seq *>(s);
+  return PTTS_OK;
+}
+
+int ptts_step(ptts_engine *e, ptts_seq *const *seqs, int32_t batch, const float *frames_in,
+              const float *noise, int32_t lsd_steps, float *latents_out, float *eos_logits_out) {
+  if (!e || !e->impl.finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable");
+  if (!noise)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: step: noise is NULL");
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  std::vector<Seq *> v;
+  for (int i = 0; i < batch; i++) {
+    if (!seqs[i])
+      PTTS_FAIL(PTTS_EINVAL, "native: flow_lm state unavailable");
+    v.push_back(&seqs[i]->impl);
+  }
+  return E.step(v, frames_in, noise, lsd_steps > 0 ? lsd_steps : 1, latents_out, eos_logits_out);
+}
+
+int ptts_decode(ptts_engine *e, ptts_seq *seq, int32_t first_frame, int32_t n_frames, float *pcm_out) {
+  if (!e || !e->impl.finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable");
+  if (!seq || !pcm_out || first_frame < 0 || n_frames <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: decode: bad arguments");
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  const int spf = E.info.samples_per_frame;
+  if (first_frame == 0)
+    return E.decode_seqs({&seq->impl}, {0}, {n_frames}, {pcm_out}, true);
+  // causal stack: decode the prefix and hand back the requested tail
+  std::vector<float> tmp((size_t)(first_frame + n_frames) * spf);
+  int rc = E.decode_seqs({&seq->impl}, {0}, {first_frame + n_frames}, {tmp.data()}, true);
+  if (rc)
+    return rc;
+  memcpy(pcm_out, tmp.data() + (size_t)first_frame * spf, (size_t)n_frames * spf * 4);
+  return PTTS_OK;
+}
+
+int ptts_decode_latents(ptts_engine *e, const float *latents, const int32_t *frames_per_seq,
+                        int32_t n_seqs, float *pcm_out) {
+  if (!e || !e->impl.finalized)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable");
+  if (!latents || !frames_per_seq || n_seqs <= 0 || !pcm_out)
+    PTTS_FAIL(PTTS_EINVAL, "native: latent tensor is nil");
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  const int spf = E.info.samples_per_frame;
+  const int max_segs = (E.mimi_rows_cap - E.up_stride * E.mimi_frames_cap) / E.mimi_pad;
+  int i = 0;
+  size_t foff = 0;
+  while (i < n_seqs) {
+    std::vector<MimiSeg> segs;
+    int tf = 0;
+    size_t f0 = foff;
+    while (i < n_seqs && (int)segs.size() < max_segs) {
+      int n = frames_per_seq[i];
+      if (n <= 0)
+        PTTS_FAIL(PTTS_EINVAL, "native: latent shape must be positive");
+      if (n > E.mimi_frames_cap)
+        PTTS_FAIL(PTTS_ENOMEM, "native-cuda: %d frames exceed mimi_group_frames %d", n, E.mimi_frames_cap);
+      if (tf + n > E.mimi_frames_cap)
+        break;
+      MimiSeg sg;
+      sg.n_frames = n;
+      sg.frame0 = tf;
+      sg.row0 = 0;
+      sg.host_out = pcm_out + foff * spf;
+      segs.push_back(sg);
+      tf += n;
+      foff += n;
+      i++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(E.m_latin, latents + f0 * E.ldim, (size_t)tf * E.ldim * 4,
+                             cudaMemcpyHostToDevice, E.st));
+    int rc = E.mimi_decode(segs, tf, true);
+    if (rc)
+      return rc;
+  }
+  return PTTS_OK;
+}
+
+int ptts_seq_frames(ptts_seq *s) { return s ? s->impl.frames : 0; }
+int ptts_seq_kv_len(ptts_seq *s) { return s ? s->impl.kv_len : 0; }
+
+int ptts_seq_read_kv(ptts_engine *e, ptts_seq *s, int32_t layer, int32_t which, float *out) {
+  if (!e || !s || !out)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: read_kv: bad arguments");
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  int T = s->impl.kv_len;
+  if (T == 0)
+    return PTTS_OK;
+  if (layer < 0 || layer >= E.L || (size_t)T * E.D > (size_t)E.max_rows * E.D)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: read_kv: layer/size out of range");
+  E.times.kernel_launches += kv_read_rows(E.nrm, T, s->impl.slot, E.kvg, layer, which ? 1 : 0, E.st);
+  CUDA_TRY(cudaMemcpyAsync(out, E.nrm, (size_t)T * E.D * 4, cudaMemcpyDeviceToHost, E.st));
+  CUDA_TRY(cudaStreamSynchronize(E.st));
+  return PTTS_OK;
+}
+
+int ptts_seq_close(ptts_engine *e, ptts_seq *s) {
+  if (!e || !s)
+    return PTTS_OK;
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  E.seq_free(&s->impl);
+  delete s;
+  return PTTS_OK;
+}
+
+int ptts_stage_times_get(ptts_engine *e, ptts_stage_times *out, int32_t reset) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  if (out)
+    *out = e->impl.times;
+  if (reset)
+    e->impl.times = ptts_stage_times{};
+  return PTTS_OK;
+}
+
+int64_t ptts_debug_fetch(ptts_engine *e, const char *name, float *out, int64_t cap) {
+  if (!e || !name)
+    return -1;
+  Engine &E = e->impl;
+  std::unique_lock<std::mutex> gl(E.gpu_mu);
+  auto it = E.debug_bufs.find(name);
+  if (it == E.debug_bufs.end())
+    return -1;
+  int64_t n = (int64_t)it->second.second;
+  if (out) {
+    int64_t c = n < cap ? n : cap;
+    cudaMemcpyAsync(out, it->second.first, (size_t)c * 4, cudaMemcpyDeviceToHost, E.st);
+    cudaStreamSynchronize(E.st);
+  }
+  return n;
+}
+
+} // extern "C"
