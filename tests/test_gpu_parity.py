@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA path, driven through the C ABI, against the CPU
+restatement (oracle/) on the same seeded inputs.
+
+Tolerances (north star): latents within |a-b| <= 2e-4 + 1e-3*|b| (fp32
+accumulate; the abs term is the reference's own pairing, internal/tts/parity.go
+and python_parity_test.go:86), waveform SNR >= 40 dB.  The model is the
+`small` architecture variant (real head_dim / channel plan, fewer layers) so the
+CPU oracle finishes in seconds; full-size properties live in test_gpu_fullsize.py.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import allclose_ref, snr_db
+
+pytestmark = pytest.mark.gpu
+
+ABS, REL = 2e-4, 1e-3
+
+
+def _tokens(n, seed):
+    return np.random.default_rng(seed).integers(0, 4000, size=n).astype(np.int64)
+
+
+def test_library_reports_device(pkg):
+    assert pkg.lib().ptts_device_count() >= 1
+    assert b"sm_100a" in pkg.lib().ptts_version()
+
+
+def test_model_info_matches_checkpoint(small_rt, small_tensors):
+    info = small_rt.info
+    assert (info.d_model, info.n_heads, info.head_dim) == (1024, 16, 64)
+    assert info.n_layers == 2 and info.flow_depth == 2 and info.mimi_layers == 1
+    assert info.samples_per_frame == 1920 and info.mimi_steps_per_latent == 16
+    # params_ar counts exactly the tensors an AR frame streams
+    want = 0
+    for k, a in small_tensors.items():
+        if k.startswith("flow_lm.") and "conditioner" not in k and k not in (
+                "flow_lm.emb_std", "flow_lm.emb_mean", "flow_lm.bos_emb"):
+            want += a.size
+    assert info.params_ar == want
+
+
+def test_prefill_kv_matches_oracle(small_rt, small_oracle):
+    toks = _tokens(23, 1)
+    s = small_rt.seq_open(toks, reserve_frames=8)
+    st = small_oracle.new_state()
+    st.prompt(small_oracle.text_embeddings(toks))
+    try:
+        assert s.kv_len == st.offset(0) == 23
+        for layer in range(small_oracle.L):
+            for which in (0, 1):
+                got, want = s.read_kv(layer, which), st.read_kv(layer, which)
+                assert allclose_ref(got, want, ABS, REL), (layer, which, np.abs(got - want).max())
+    finally:
+        s.close()
+
+
+def test_step_teacher_forced_matches_oracle(small_rt, small_oracle, pkg):
+    toks = _tokens(9, 2)
+    noise = pkg.make_noise(6, 0.7, 5)
+    s = small_rt.seq_open(toks, reserve_frames=8)
+    st = small_oracle.new_state()
+    st.prompt(small_oracle.text_embeddings(toks))
+    frame = np.full(32, np.nan, np.float32)  # BOS sentinel
+    try:
+        for i in range(6):
+            want_lat, want_eos, want_last = st.step(frame, noise[i])
+            lat, eos = small_rt.step([s], noise[i], frames_in=frame)
+            last = small_rt.debug_fetch("last_hidden")
+            assert allclose_ref(last, want_last, ABS, REL), (i, np.abs(last - want_last).max())
+            assert abs(eos[0] - want_eos) <= ABS + REL * abs(want_eos), (i, eos[0], want_eos)
+            assert allclose_ref(lat[0], want_lat, ABS, REL), (i, np.abs(lat[0] - want_lat).max())
+            frame = want_lat  # teacher forcing
+        assert s.frames == 6 and s.kv_len == 15
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("lsd", [1, 2, 4])
+def test_lsd_steps(small_rt, small_oracle, pkg, lsd):
+    toks = _tokens(5, 3)
+    noise = pkg.make_noise(1, 0.7, 6)
+    s = small_rt.seq_open(toks, reserve_frames=4)
+    st = small_oracle.new_state()
+    st.prompt(small_oracle.text_embeddings(toks))
+    try:
+        frame = np.full(32, np.nan, np.float32)
+        want, _, _ = st.step(frame, noise[0], lsd_steps=lsd)
+        got, _ = small_rt.step([s], noise[0], frames_in=frame, lsd_steps=lsd)
+        assert allclose_ref(got[0], want, ABS, REL), np.abs(got[0] - want).max()
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("batch", [2, 5, 12])
+def test_batched_step_matches_oracle_per_sequence(small_rt, small_oracle, pkg, batch):
+    """Ragged prompts, one batched AR step (skinny kernel for B<=8, tiled for 12)."""
+    seqs, states = [], []
+    try:
+        for b in range(batch):
+            toks = _tokens(3 + 4 * b, 100 + b)
+            seqs.append(small_rt.seq_open(toks, reserve_frames=4))
+            st = small_oracle.new_state()
+            st.prompt(small_oracle.text_embeddings(toks))
+            states.append(st)
+        frames = np.full((batch, 32), np.nan, np.float32)
+        for step in range(2):
+            noise = pkg.make_noise(batch, 0.7, 40 + step)
+            lat, eos = small_rt.step(seqs, noise, frames_in=frames)
+            for b in range(batch):
+                wl, we, _ = states[b].step(frames[b], noise[b])
+                assert allclose_ref(lat[b], wl, ABS, REL), (step, b, np.abs(lat[b] - wl).max())
+                assert abs(eos[b] - we) <= ABS + REL * abs(we)
+                frames[b] = wl
+    finally:
+        for s in seqs:
+            s.close()
+
+
+@pytest.mark.parametrize("frames", [1, 2, 4, 7])
+def test_mimi_decode_matches_oracle(small_rt, small_oracle, frames):
+    rng = np.random.default_rng(frames)
+    lat = rng.standard_normal((frames, 32)).astype(np.float32)
+    want, (s0, s1, s2) = small_oracle.mimi_decode(small_oracle.latent_to_mimi(lat), stages=True)
+    got = small_rt.decode_latents(lat)
+    pad = 8
+    tr = small_rt.debug_fetch("mimi_transformer").reshape(-1, 512)[pad:]
+    assert allclose_ref(tr, s1.T, ABS, REL), np.abs(tr - s1.T).max()
+    assert got.shape == want.shape == (1920 * frames,)
+    assert snr_db(want, got) >= 40.0
+    # mimi_decode tolerance of the reference's python parity test (abs 2e-4 / rel 5e-2)
+    assert allclose_ref(got, want, 2e-4, 5e-2), np.abs(got - want).max()
+
+
+def test_mimi_decode_ragged_batch_equals_individual(small_rt, small_oracle):
+    rng = np.random.default_rng(9)
+    sizes = [3, 1, 6, 2]
+    lat = rng.standard_normal((sum(sizes), 32)).astype(np.float32)
+    got = small_rt.decode_latents(lat, sizes)
+    off = 0
+    for n in sizes:
+        want = small_oracle.decode_latents(lat[off:off + n])
+        g = got[off * 1920:(off + n) * 1920]
+        assert snr_db(want, g) >= 40.0
+        assert allclose_ref(g, want, 2e-4, 5e-2)
+        off += n
+
+
+def test_mimi_prefix_decode_is_causal(small_rt):
+    """Streaming property: decoding a prefix gives the same samples as the same
+    span of the whole-chunk decode (causal convs + causal windowed attention)."""
+    rng = np.random.default_rng(10)
+    lat = rng.standard_normal((20, 32)).astype(np.float32)
+    whole = small_rt.decode_latents(lat)
+    for n in (1, 5, 19):
+        part = small_rt.decode_latents(lat[:n])
+        np.testing.assert_allclose(part, whole[: n * 1920], atol=1e-5, rtol=1e-5)
+
+
+def _gen_both(rt, om, pkg, toks, max_steps, force, fae, seed, **kw):
+    noise = pkg.make_noise(max_steps, 0.7, seed)
+    cfg = pkg.RuntimeGenerateConfig(max_steps=max_steps, eos_threshold=1e30, force_eos_step=force,
+                                    frames_after_eos=fae, noise=noise, **kw)
+    got = rt.generate(toks, cfg, want_latents=True)
+    okw = {}
+    if kw.get("voice_embedding") is not None:
+        okw["voice_embedding"] = kw["voice_embedding"].rows()
+    pcm, lat, eos = om.generate_audio(toks, noise=noise, max_steps=max_steps, eos_threshold=1e30,
+                                      force_eos_step=force, frames_after_eos=fae, **okw)
+    return got, pcm, lat, eos
+
+
+def test_generate_audio_end_to_end(small_rt, small_oracle, pkg):
+    toks = _tokens(11, 4)
+    got, pcm, lat, eos = _gen_both(small_rt, small_oracle, pkg, toks, 14, 8, 3, 21)
+    assert got.n_frames == lat.shape[0] == 12  # EOS at step 8, +3 frames, break on the 4th
+    assert got.pcm.shape == pcm.shape == (12 * 1920,)
+    assert allclose_ref(got.latents, lat, ABS, REL), np.abs(got.latents - lat).max()
+    assert allclose_ref(got.eos_logits, eos, ABS, REL)
+    assert snr_db(pcm, got.pcm) >= 40.0
+
+
+def test_generate_audio_natural_eos_threshold(small_rt, small_oracle, pkg):
+    """EOS judged on the raw logit > threshold (flow_lm.go:281): pick a threshold
+    from the oracle's own logits so the countdown path is the natural one."""
+    toks = _tokens(7, 5)
+    noise = pkg.make_noise(12, 0.7, 22)
+    _, _, eos = small_oracle.generate_audio(toks, noise=noise, max_steps=12, eos_threshold=1e30, want_pcm=False)
+    srt = np.sort(eos[:8])
+    thr = float((srt[-1] + srt[-2]) / 2)  # exactly one of the first 8 steps exceeds it
+    pcm, lat, _ = small_oracle.generate_audio(toks, noise=noise, max_steps=12, eos_threshold=thr, frames_after_eos=2)
+    cfg = pkg.RuntimeGenerateConfig(max_steps=12, eos_threshold=thr, frames_after_eos=2, noise=noise)
+    got = small_rt.generate(toks, cfg, want_latents=True)
+    assert got.n_frames == lat.shape[0] < 12
+    assert allclose_ref(got.latents, lat, ABS, REL)
+    assert snr_db(pcm, got.pcm) >= 40.0
+
+
+def test_generate_audio_max_steps_cap(small_rt, small_oracle, pkg):
+    toks = _tokens(4, 6)
+    got, pcm, lat, _ = _gen_both(small_rt, small_oracle, pkg, toks, 5, -1, 3, 23)
+    assert got.n_frames == lat.shape[0] == 5
+    assert snr_db(pcm, got.pcm) >= 40.0
+
+
+def test_voice_embedding_prefix(small_rt, small_oracle, pkg):
+    # sin-wave voice as in native_safetensors_integration_test.go:81-84
+    tv = 13
+    voice = np.sin(0.01 * np.arange(tv * 1024, dtype=np.float64)).astype(np.float32).reshape(1, tv, 1024)
+    toks = _tokens(6, 7)
+    ve = pkg.VoiceEmbedding(voice)
+    got, pcm, lat, _ = _gen_both(small_rt, small_oracle, pkg, toks, 6, 3, 1, 24, voice_embedding=ve)
+    assert got.n_frames == lat.shape[0]
+    assert allclose_ref(got.latents, lat, ABS, REL), np.abs(got.latents - lat).max()
+    assert snr_db(pcm, got.pcm) >= 40.0
+    # and conditioning matters (integration test asserts the hash changes)
+    plain, _, _, _ = _gen_both(small_rt, small_oracle, pkg, toks, 6, 3, 1, 24)
+    assert np.abs(plain.latents - got.latents).max() > 1e-3
+
+
+def test_voice_model_state_import(small_rt, small_oracle, pkg):
+    """Upstream voice file = serialized prompted KV [2,1,T,H,D] + offset; slots past
+    offset may hold NaN and must be ignored (flow_transformer.go:451-631)."""
+    rng = np.random.default_rng(8)
+    T, off = 24, 17
+    caches = []
+    for _ in range(small_oracle.L):
+        c = rng.standard_normal((2, 1, T, 16, 64)).astype(np.float32) * 0.5
+        c[:, :, off:] = np.nan
+        caches.append(c)
+    toks = _tokens(5, 9)
+    noise = pkg.make_noise(4, 0.7, 25)
+    st = small_oracle.new_state()
+    for i, c in enumerate(caches):
+        st.set_voice_layer(i, c, off)
+    pcm, lat, _ = small_oracle.generate_audio(toks, noise=noise, max_steps=4, eos_threshold=1e30, state=st)
+    cfg = pkg.RuntimeGenerateConfig(max_steps=4, eos_threshold=1e30, noise=noise,
+                                    voice_model_state=pkg.VoiceModelState(caches, [off] * len(caches)))
+    got = small_rt.generate(toks, cfg, want_latents=True)
+    assert got.n_frames == 4
+    assert np.isfinite(got.latents).all()
+    assert allclose_ref(got.latents, lat, ABS, REL), np.abs(got.latents - lat).max()
+    assert snr_db(pcm, got.pcm) >= 40.0
+
+
+def test_guards_and_error_strings(small_rt, pkg):
+    # runtime_native_safetensors_test.go:29-69
+    with pytest.raises(pkg.NativeCudaError, match="must not be empty"):
+        small_rt.generate_audio([], pkg.RuntimeGenerateConfig(max_steps=2))
+    ve = pkg.VoiceEmbedding(np.zeros((1, 2, 1024), np.float32))
+    vs = pkg.VoiceModelState([np.zeros((2, 1, 2, 16, 64), np.float32)] * 2, [1, 1])
+    with pytest.raises(pkg.NativeCudaError, match="mutually exclusive"):
+        small_rt.generate_audio([1], pkg.RuntimeGenerateConfig(max_steps=2, voice_embedding=ve, voice_model_state=vs))
+    with pytest.raises(pkg.NativeCudaError, match="out of range"):
+        small_rt.generate_audio([1, 999999], pkg.RuntimeGenerateConfig(max_steps=2))
+    with pytest.raises(pkg.NativeCudaError, match="exceeds engine max_frames"):
+        small_rt.generate_audio([1], pkg.RuntimeGenerateConfig(max_steps=100000))
+    # the engine survives errors
+    out = small_rt.generate_audio([1, 2, 3], pkg.RuntimeGenerateConfig(max_steps=2, eos_threshold=1e30))
+    assert out.shape == (2 * 1920,) and np.isfinite(out).all()
+
+
+def test_close_is_idempotent_and_guards_after_close(pkg, small_tensors):
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=128, max_frames=8,
+                               mimi_group_frames=16)
+    rt.close()
+    rt.close()
+    with pytest.raises(pkg.NativeCudaError, match="runtime unavailable"):
+        rt.generate_audio([1, 2], pkg.RuntimeGenerateConfig(max_steps=2))
+
+
+def test_concurrent_requests_are_batched_and_match_oracle(small_rt, small_oracle, pkg):
+    """16 goroutine-style callers on one shared runtime (server.go:206-220)."""
+    n = 16
+    reqs = []
+    for i in range(n):
+        toks = _tokens(3 + (i * 5) % 17, 200 + i)
+        ms = 4 + i % 5
+        noise = pkg.make_noise(ms, 0.7, 300 + i)
+        reqs.append((toks, ms, noise))
+    results = [None] * n
+
+    def worker(i):
+        toks, ms, noise = reqs[i]
+        cfg = pkg.RuntimeGenerateConfig(max_steps=ms, eos_threshold=1e30, force_eos_step=ms - 3,
+                                        frames_after_eos=1, noise=noise)
+        results[i] = small_rt.generate(toks, cfg, want_latents=True)
+
+    small_rt.stage_times(reset=True)
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(n)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    st = small_rt.stage_times()
+    assert st["steps"] > 0 and st["step_rows"] / st["steps"] > 1.5  # really batched
+    for i in range(n):
+        toks, ms, noise = reqs[i]
+        pcm, lat, _ = small_oracle.generate_audio(toks, noise=noise, max_steps=ms, eos_threshold=1e30,
+                                                  force_eos_step=ms - 3, frames_after_eos=1)
+        got = results[i]
+        assert got.n_frames == lat.shape[0]
+        assert allclose_ref(got.latents, lat, ABS, REL), (i, np.abs(got.latents - lat).max())
+        assert snr_db(pcm, got.pcm) >= 40.0, i
+
+
+def test_more_requests_than_slots_queue_and_complete(pkg, small_tensors):
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=3, max_seq_tokens=128, max_frames=8,
+                               mimi_group_frames=32)
+    try:
+        pend = []
+        for i in range(10):
+            cfg = pkg.RuntimeGenerateConfig(max_steps=3 + i % 3, eos_threshold=1e30, seed=i)
+            pend.append((3 + i % 3, rt.submit(_tokens(4 + i, 400 + i), cfg)))
+        for ms, p in pend:
+            r = rt.wait(p)
+            assert r.n_frames == ms and r.pcm.shape == (ms * 1920,) and np.isfinite(r.pcm).all()
+    finally:
+        rt.close()
+
+
+def test_cancel_evicts_sequence(pkg, small_tensors):
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=256, max_frames=96,
+                               mimi_group_frames=96)
+    try:
+        cfg = pkg.RuntimeGenerateConfig(max_steps=90, eos_threshold=1e30)
+        p = rt.submit(_tokens(5, 1), cfg)
+        rt.cancel(p)
+        with pytest.raises(pkg.NativeCudaError) as ei:
+            rt.wait(p)
+        assert ei.value.status == pkg.PTTS_ECANCELED
+        ok = rt.generate_audio(_tokens(5, 2), pkg.RuntimeGenerateConfig(max_steps=2, eos_threshold=1e30))
+        assert ok.shape == (2 * 1920,)
+    finally:
+        rt.close()
+
+
+def test_seq_decode_span_equals_whole(small_rt, pkg):
+    toks = _tokens(6, 11)
+    s = small_rt.seq_open(toks, reserve_frames=8)
+    try:
+        for i in range(5):
+            small_rt.step([s], pkg.make_noise(1, 0.7, 50 + i))
+        whole = s.decode()
+        tail = s.decode(first_frame=3, n_frames=2)
+        np.testing.assert_array_equal(tail, whole[3 * 1920:])
+        first = s.decode(first_frame=0, n_frames=1)
+        np.testing.assert_allclose(first, whole[:1920], atol=1e-5, rtol=1e-5)
+    finally:
+        s.close()
+
+
+def test_safetensors_file_loader_roundtrip(pkg, ck, small_tensors, small_rt, tmp_path):
+    """ptts_load_safetensors (C++ parser) == per-key ptts_load_tensor, incl. BF16 widening."""
+    path = str(tmp_path / "small.safetensors")
+    bf = ck.to_bf16_exact(small_tensors)
+    ck.write_safetensors(path, bf, bf16=True)
+    rt_file = pkg.NativeCudaRuntime(checkpoint=path, max_batch=2, max_seq_tokens=128, max_frames=8,
+                                    mimi_group_frames=16)
+    rt_keys = pkg.NativeCudaRuntime(tensors=bf, max_batch=2, max_seq_tokens=128, max_frames=8,
+                                    mimi_group_frames=16)
+    try:
+        cfg = pkg.RuntimeGenerateConfig(max_steps=3, eos_threshold=1e30, seed=5)
+        a = rt_file.generate(_tokens(5, 3), cfg, want_latents=True)
+        b = rt_keys.generate(_tokens(5, 3), cfg, want_latents=True)
+        np.testing.assert_array_equal(a.latents, b.latents)
+        np.testing.assert_array_equal(a.pcm, b.pcm)
+    finally:
+        rt_file.close()
+        rt_keys.close()
