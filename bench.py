@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the native-cuda PocketTTS backend.
+
+Metric (BASELINE.json): batched audio-seconds per wall-second.  One "step" is
+one pass of the whole hot path (prefill -> AR frames + flow head -> Mimi
+decode -> PCM) over this rank's shard of the C5 workload ("4096 queued
+synthetic utterances sharded across 1/2/4/8 B200"): 4096/8 = 512 utterances of
+U{5..60} words per GPU, all submitted at t=0 and continuously batched.  Per-GPU
+work is fixed as N grows (weak scaling); at N=8 the job is exactly C5.
+
+  value : throughput with PCM left on the device (inputs are ~24 KB of tokens +
+          noise per request, staged at admission)
+  e2e   : the same pass through the public C-ABI call with HOST buffers:
+          tokens/noise H2D and float PCM D2H inside the timed region
+  --impl reference : the reference's CPU path.  No Go toolchain exists in this
+          image, so it is the C restatement (oracle/, "port") timed on all
+          host cores over a bounded sample of the same workload.
+
+Usage: python bench.py --gpus N --steps K --warmup W [--impl reference]
+(for N>1 launch under torch.distributed.run; see the driver contract).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "audio-s/wall-s (batched)"
+UNIT = "audio-s/s"
+TOTAL_UTTERANCES = 4096
+MAX_GPUS = 8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native-cuda", choices=["native-cuda", "reference"])
+    ap.add_argument("--utterances", type=int, default=TOTAL_UTTERANCES // MAX_GPUS, help="per GPU")
+    ap.add_argument("--max-batch", type=int, default=256)
+    ap.add_argument("--arch", default="full", choices=["full", "small"])
+    ap.add_argument("--cpu-sample-frames", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smmax, reasons = [], None, set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smmax = float(c[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smmax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_run(om, chunks, frames_cap, threads):
+    """Oracle port on `threads` host threads, one chunk per thread (the reference runs
+    N goroutines each on a B=1 loop).  Returns (audio_seconds, wall_seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    frames = [0] * len(chunks)
+
+    def one(i):
+        c = chunks[i]
+        ms = min(c.max_steps, frames_cap)
+        force = min(c.force_eos_step, ms - 1 - c.frames_after_eos) if ms > c.frames_after_eos + 1 else 0
+        pcm, lat, _ = om.generate_audio(c.tokens, noise=c.noise()[:ms], max_steps=ms, eos_threshold=1e30,
+                                        force_eos_step=max(force, 0), frames_after_eos=c.frames_after_eos)
+        frames[i] = lat.shape[0]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(len(chunks))))
+    dt = time.perf_counter() - t0
+    return sum(frames) * 1920 / 24000.0, dt, sum(frames)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun (the driver does this itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+
+    pkg = ge.package()
+    import importlib
+    ck = importlib.import_module("pockettts_b200.checkpoint")
+    wl = importlib.import_module("pockettts_b200.workload")
+    arch = ck.ArchConfig.full() if args.arch == "full" else ck.ArchConfig.small()
+    workload_name = (f"C5 shard: {args.utterances} utterances/GPU x U{{5..60}} words, <=50-token chunks, "
+                     f"forced-EOS schedule, lsd_steps=1, random-init PocketTTS ({args.arch}), seed 20260118")
+    config = {"workload": workload_name, "utterances_per_gpu": args.utterances, "max_batch": args.max_batch,
+              "l2": "working set (weights 341 MB + KV + Mimi workspace, several GB) >> 126 MB L2; no flush needed",
+              "weights": "fp32 as stored by the reference"}
+
+    # ---------------- reference arm: CPU port on host cores -----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        o = ge.oracle()
+        cores = os.cpu_count() or 1
+        tensors = ck.make_checkpoint(arch)
+        om = o.OracleModel(tensors)
+        chunks = wl.make_workload(cores, 5, 60, seed=7)[:cores]
+        for _ in range(max(args.warmup, 0) and 1):
+            cpu_run(om, chunks[: max(1, cores // 2)], 4, cores)
+        tot_a = tot_t = 0.0
+        for _ in range(args.steps):
+            a, t, _ = cpu_run(om, chunks, args.cpu_sample_frames, cores)
+            tot_a += a
+            tot_t += t
+        v = tot_a / tot_t
+        sample = (f"{cores} chunks (first of the workload) capped at {args.cpu_sample_frames} frames each, "
+                  f"one chunk per host thread")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference (Go toolchain unavailable); AVX2+FMA dot"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- native-cuda arm ---------------------------------------
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pkg.build_library()
+    tensors = ck.make_checkpoint(arch)
+    rt = pkg.NativeCudaRuntime(tensors=tensors, device=local_rank, max_batch=args.max_batch, max_seq_tokens=512,
+                               max_frames=256, mimi_group_frames=2048)
+    chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=rank * args.utterances)
+    noises = [c.noise() for c in chunks]
+    h2d = sum(c.tokens.nbytes + n.nbytes for c, n in zip(chunks, noises))
+
+    def run_pass(no_d2h: bool):
+        pend = []
+        for c, n in zip(chunks, noises):
+            cfg = pkg.RuntimeGenerateConfig(max_steps=c.max_steps, eos_threshold=1e30, force_eos_step=c.force_eos_step,
+                                            frames_after_eos=c.frames_after_eos, noise=n, no_pcm_d2h=no_d2h)
+            pend.append(rt.submit(c.tokens, cfg))
+        frames, samples = 0, 0
+        for p in pend:
+            r = rt.wait(p)
+            frames += r.n_frames
+            samples += r.pcm.size
+        return frames, samples
+
+    def timed(no_d2h: bool, steps: int):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        frames = samples = 0
+        for _ in range(steps):
+            f, s = run_pass(no_d2h)
+            frames += f
+            samples += s
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        t = torch.tensor([dev_ms, float(frames), float(samples), wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return tmax[0].item(), tsum[1].item(), tsum[2].item(), tmax[3].item()
+        return t[0].item(), t[1].item(), t[2].item(), t[3].item()
+
+    for _ in range(args.warmup):
+        run_pass(True)
+    rt.stage_times(reset=True)
+    rt.profile(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, frames, _, wall_ms = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    st = rt.stage_times()
+    prof = rt.profile_report()
+    rt.profile(False)
+    value = (frames * 1920 / 24000.0) / (ms / 1e3)
+    ms2, frames2, samples2, _ = timed(False, args.steps)
+    e2e = (frames2 * 1920 / 24000.0) / (ms2 / 1e3)
+
+    out = None
+    if rank == 0:
+        peaks = load_peaks()
+        info = rt.info
+        classes = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+        tot_ms = sum(v["ms"] for _, v in classes) or 1.0
+        kc = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share_of_profiled": round(v["ms"] / tot_ms, 4),
+                  "tflops": round(v["flops"] / (v["ms"] * 1e9), 3) if v["ms"] else 0.0,
+                  "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] else 0.0} for k, v in classes}
+        top, tv = classes[0]
+        if top.startswith("attention") or top.startswith("gemv"):
+            ach = tv["bytes"] / (tv["ms"] * 1e6)
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                        "per_launch_us": 1e3 * tv["ms"] / tv["launches"]}
+        else:
+            ach = tv["flops"] / (tv["ms"] * 1e9)
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"],
+                        "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + " (sustained bf16; kernel timed inside a long step)",
+                        "per_launch_us": 1e3 * tv["ms"] / tv["launches"],
+                        "note": "fp32 CUDA-core SGEMM this round; tensor-core (tcgen05) path is the next step"}
+        alg_flops = 2.0 * (info.macs_ar_frame + info.macs_mimi_frame) * frames
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
+                    "d2h_bytes_per_step": int(samples2 * 4 / max(args.steps, 1))},
+            "gpu_launches": int(st["kernel_launches"]),
+            "roofline": roofline,
+            "kernel_classes": kc,
+            "stage_ms_rank0": {k: round(st[k], 2) for k in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")},
+            "mean_batch_occupancy": st["step_rows"] / max(st["steps"], 1),
+            "steps_per_s_rank0": st["steps"] / (ms / 1e3),
+            "realtime_factor_per_gpu": value / world,
+            "achieved_tflops_job": alg_flops / (ms * 1e9),
+            "frac_of_tensor_roofline_job": alg_flops / (ms * 1e9) / (peaks["tf_sustained"] * world),
+            "wall_ms_per_step": wall_ms / max(args.steps, 1),
+            "frames_per_step": frames / max(args.steps, 1),
+        }
+
+    # ---------------- latency leg: C2 first chunk, B=1, streaming-style -------
+    if rank == 0 and not args.no_latency:
+        c2 = wl.paragraph_200_words()[0]
+        n2 = c2.noise()
+        ttfa = []
+        for i in range(12):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s = rt.seq_open(c2.tokens, reserve_frames=8)
+            rt.step([s], n2[0])
+            pcm = s.decode(0, 1)
+            ttfa.append((time.perf_counter() - t0) * 1e3)
+            s.close()
+        ttfa = sorted(ttfa[2:])
+        s = rt.seq_open(c2.tokens, reserve_frames=128)
+        for i in range(8):
+            rt.step([s], n2[i])
+        rt.stage_times(reset=True)
+        rt.profile(True)
+        t0 = time.perf_counter()
+        nb1 = 64
+        for i in range(nb1):
+            rt.step([s], n2[8 + i])
+        b1_wall = (time.perf_counter() - t0) / nb1
+        st1 = rt.stage_times()
+        p1 = rt.profile_report()
+        rt.profile(False)
+        s.close()
+        gv = p1.get("gemv_f32", {"ms": 0, "bytes": 0, "launches": 1})
+        peaks = load_peaks()
+        bytes_frame = 4.0 * info.params_ar
+        out["latency"] = {
+            "workload": "C2 first chunk (%d tokens), batch 1" % c2.tokens.size,
+            "ttfa_ms_p50": ttfa[len(ttfa) // 2], "ttfa_ms_min": ttfa[0],
+            "ttfa_definition": "seq_open (prefill) + 1 AR frame + Mimi decode of frame 0 + PCM D2H, host clock",
+            "b1_frame_us_device": 1e3 * st1["step_ms"] / nb1, "b1_frame_us_wall": 1e6 * b1_wall,
+            "b1_realtime_factor": 0.08 / b1_wall,
+            "b1_weight_stream_gbs": bytes_frame / (st1["step_ms"] / nb1 * 1e6),
+            "b1_frac_of_hbm_roofline": bytes_frame / (st1["step_ms"] / nb1 * 1e6) / peaks["hbm_gbs"],
+            "gemv_kernel_gbs": gv["bytes"] / (gv["ms"] * 1e6) if gv["ms"] else None,
+            "launches_per_frame": st1["kernel_launches"] / nb1,
+        }
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only) ---------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        o = ge.oracle()
+        cores = os.cpu_count() or 1
+        om = o.OracleModel(tensors)
+        sample_chunks = wl.make_workload(cores, 5, 60, seed=7)[:cores]
+        a, t, nfr = cpu_run(om, sample_chunks, args.cpu_sample_frames, cores)
+        out["cpu_baseline"] = {
+            "value": a / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(sample_chunks)} chunks (first of the workload) capped at {args.cpu_sample_frames} "
+                      f"frames each ({nfr} frames), one chunk per host thread, {t:.1f} s of wall time",
+            "note": "C restatement of the reference path (oracle/); the Go reference cannot be built here"}
+    if rank == 0:
+        print(json.dumps(out))
+    rt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

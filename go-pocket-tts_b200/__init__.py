@@ -108,7 +108,7 @@ EXPORTS = [
     "ptts_load_safetensors", "ptts_finalize_weights", "ptts_model_info_get", "ptts_generate_audio",
     "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
-    "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch",
+    "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
 ]
 
 _lib = None
@@ -155,6 +155,8 @@ def lib() -> C.CDLL:
     L.ptts_stage_times_get.argtypes = [vp, C.POINTER(PttsStageTimes), C.c_int32]
     L.ptts_debug_fetch.argtypes = [vp, C.c_char_p, fp, C.c_int64]
     L.ptts_debug_fetch.restype = C.c_int64
+    L.ptts_profile_enable.argtypes = [vp, C.c_int32]
+    L.ptts_profile_report.argtypes = [vp, C.c_char_p, C.c_int32]
     _lib = L
     return L
 
@@ -437,6 +439,17 @@ class NativeCudaRuntime:
         t = PttsStageTimes()
         _check(self._lib.ptts_stage_times_get(self._h, C.byref(t), 1 if reset else 0))
         return {n: getattr(t, n) for n, _ in PttsStageTimes._fields_}
+
+    def profile(self, on: bool):
+        _check(self._lib.ptts_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        n = self._lib.ptts_profile_report(self._h, buf, len(buf))
+        if n < 0:
+            _check(n)
+        return json.loads(buf.value.decode())
 
     def debug_fetch(self, name: str) -> np.ndarray:
         n = self._lib.ptts_debug_fetch(self._h, name.encode(), None, 0)

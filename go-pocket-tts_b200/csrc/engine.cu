@@ -105,6 +105,57 @@ int Engine::upload_key(const std::string &key, float **out, std::vector<int64_t>
 }
 
 // ---------------------------------------------------------------------------
+// profiling: one CUDA-event pair per profiled launch, resolved after the next
+// stream sync.  Algorithmic FLOPs/bytes are recorded with the launch so the
+// bench can quote achieved TFLOP/s / GB/s per kernel class.
+// ---------------------------------------------------------------------------
+void Engine::prof_begin(cudaEvent_t *a, cudaEvent_t *b) {
+  if (prof_pool.empty()) {
+    cudaEventCreate(a);
+    cudaEventCreate(b);
+  } else {
+    *a = prof_pool.back().first;
+    *b = prof_pool.back().second;
+    prof_pool.pop_back();
+  }
+  cudaEventRecord(*a, st);
+}
+void Engine::prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes) {
+  cudaEventRecord(b, st);
+  prof_pending.push_back(ProfRec{a, b, cls, flops, bytes});
+}
+void Engine::prof_collect() {
+  for (auto &r : prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ProfAcc &acc = prof_acc[r.cls];
+      acc.launches++;
+      acc.ms += ms;
+      acc.flops += r.flops;
+      acc.bytes += r.bytes;
+    }
+    prof_pool.push_back({r.a, r.b});
+  }
+  prof_pending.clear();
+}
+int Engine::pgemm(const GemmArgs &g0) {
+  GemmArgs g = g0;
+  g.ws = gemm_ws;
+  g.ws_floats = gemm_ws_floats;
+  g.counters = gemm_counters;
+  g.n_counters = gemm_n_counters;
+  if (!prof_on)
+    return gemm(g, st);
+  cudaEvent_t a, b;
+  prof_begin(&a, &b);
+  int n = gemm(g, st);
+  double kk = g.K < g.lda ? g.K : g.lda; // overlapping conv rows: unique A bytes
+  prof_end(a, b, gemm_last_variant(), 2.0 * g.M * g.N * g.K,
+           4.0 * ((double)g.N * g.K + (double)g.M * kk + (double)g.M * g.N));
+  return n;
+}
+
+// ---------------------------------------------------------------------------
 // weights
 // ---------------------------------------------------------------------------
 static inline float half_to_float(uint16_t h) {
@@ -588,6 +639,10 @@ int Engine::finalize() {
       CUDA_TRY(cudaMemcpy(d_hist + (size_t)s * (max_frames + 1) * ldim, nanrow.data(),
                           ldim * sizeof(float), cudaMemcpyHostToDevice));
   }
+  gemm_ws_floats = 16L << 20;
+  if ((rc = dmalloc((void **)&gemm_ws, (size_t)gemm_ws_floats * 4))) return rc;
+  if ((rc = dmalloc((void **)&gemm_counters, (size_t)gemm_n_counters * 4))) return rc;
+  CUDA_TRY(cudaMemset(gemm_counters, 0, (size_t)gemm_n_counters * 4));
   // ---- FlowLM workspaces ----
   max_rows = cfg.max_prefill_tokens > max_batch ? cfg.max_prefill_tokens : max_batch;
   if ((rc = dmalloc((void **)&x, (size_t)max_rows * D * 4))) return rc;
@@ -788,28 +843,38 @@ void Engine::seq_free(Seq *s) {
 // ---------------------------------------------------------------------------
 int Engine::flow_forward(int R, int max_keys, bool) {
   int64_t &nl = times.kernel_launches;
+  double prof_keys = 0; // sum over rows of keys attended (K and V rows read)
+  if (prof_on)
+    for (int r = 0; r < R; r++)
+      prof_keys += h_row_pos[r] + 1;
   for (int l = 0; l < L; l++) {
     DTLayer &ly = fl[l];
     nl += layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st);
     GemmArgs g;
     g.A = nrm; g.lda = D; g.W = ly.in_proj.w; g.ldw = D; g.M = R; g.N = 3 * D; g.K = D;
     g.epi.C = qkv; g.epi.ldc = 3 * D;
-    nl += gemm(g, st);
+    nl += pgemm(g);
     nl += rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st);
-    nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st);
+    if (prof_on) {
+      cudaEvent_t a, b;
+      prof_begin(&a, &b);
+      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st);
+      prof_end(a, b, "attention_paged", 4.0 * prof_keys * D, 8.0 * prof_keys * D);
+    } else
+      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st);
     GemmArgs o;
     o.A = att; o.lda = D; o.W = ly.out_proj.w; o.ldw = D; o.M = R; o.N = D; o.K = D;
     o.epi.residual = x; o.epi.ldr = D; o.epi.C = x; o.epi.ldc = D;
-    nl += gemm(o, st);
+    nl += pgemm(o);
     nl += layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st);
     GemmArgs f1;
     f1.A = nrm; f1.lda = D; f1.W = ly.l1.w; f1.ldw = D; f1.M = R; f1.N = F; f1.K = D;
     f1.epi.act = ACT_GELU; f1.epi.C = ff; f1.epi.ldc = F;
-    nl += gemm(f1, st);
+    nl += pgemm(f1);
     GemmArgs f2;
     f2.A = ff; f2.lda = F; f2.W = ly.l2.w; f2.ldw = F; f2.M = R; f2.N = D; f2.K = F;
     f2.epi.residual = x; f2.epi.ldr = D; f2.epi.C = x; f2.epi.ldc = D;
-    nl += gemm(f2, st);
+    nl += pgemm(f2);
   }
   CUDA_TRY(cudaGetLastError());
   return PTTS_OK;
@@ -905,6 +970,7 @@ int Engine::prefill(const std::vector<Seq *> &seqs, const std::vector<const int6
     seqs[i]->kv_len += nvoice[i] + ntok[i];
   cudaEventRecord(ev[1], st);
   CUDA_TRY(cudaStreamSynchronize(st));
+  prof_collect();
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[0], ev[1]);
   times.prefill_ms += ms;
@@ -926,7 +992,7 @@ int Engine::flow_head(int B, int lsd_steps) {
     GemmArgs g;
     g.A = fh_last; g.lda = D; g.W = cond_embed.w; g.ldw = D; g.M = B; g.N = C; g.K = D;
     g.epi.bias = cond_embed.b; g.epi.C = fh_cproj; g.epi.ldc = C;
-    nl += gemm(g, st);
+    nl += pgemm(g);
   }
   CUDA_TRY(cudaMemcpyAsync(fh_cur, fh_noise, (size_t)B * ldim * 4, cudaMemcpyDeviceToDevice, st));
   const float inv = 1.0f / (float)lsd_steps;
@@ -937,13 +1003,13 @@ int Engine::flow_head(int B, int lsd_steps) {
       GemmArgs g;
       g.A = fh_sy; g.lda = C; g.W = ada_all.w; g.ldw = C; g.M = B; g.N = ada_n; g.K = C;
       g.epi.bias = ada_all.b; g.epi.C = fh_ada; g.epi.ldc = ada_n;
-      nl += gemm(g, st);
+      nl += pgemm(g);
     }
     {
       GemmArgs g;
       g.A = fh_cur; g.lda = ldim; g.W = input_proj.w; g.ldw = ldim; g.M = B; g.N = C; g.K = ldim;
       g.epi.bias = input_proj.b; g.epi.C = fh_x; g.epi.ldc = C;
-      nl += gemm(g, st);
+      nl += pgemm(g);
     }
     for (int b = 0; b < depth; b++) {
       const float *shift = fh_ada + (size_t)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
@@ -952,12 +1018,12 @@ int Engine::flow_head(int B, int lsd_steps) {
       GemmArgs g0;
       g0.A = fh_h; g0.lda = C; g0.W = rb[b].mlp0.w; g0.ldw = C; g0.M = B; g0.N = hid; g0.K = C;
       g0.epi.bias = rb[b].mlp0.b; g0.epi.act = ACT_SILU; g0.epi.C = fh_h2; g0.epi.ldc = hid;
-      nl += gemm(g0, st);
+      nl += pgemm(g0);
       GemmArgs g2;
       g2.A = fh_h2; g2.lda = hid; g2.W = rb[b].mlp2.w; g2.ldw = hid; g2.M = B; g2.N = C; g2.K = hid;
       g2.epi.bias = rb[b].mlp2.b; g2.epi.mul = gate; g2.epi.ldmul = ada_n;
       g2.epi.residual = fh_x; g2.epi.ldr = C; g2.epi.C = fh_x; g2.epi.ldc = C;
-      nl += gemm(g2, st);
+      nl += pgemm(g2);
     }
     const float *fshift = fh_ada + (size_t)depth * 3 * C, *fscale = fshift + C;
     nl += layernorm(fh_x, C, fh_h, C, B, C, nullptr, nullptr, 1e-6f, fscale, fshift, ada_n, st);
@@ -965,7 +1031,7 @@ int Engine::flow_head(int B, int lsd_steps) {
     gf.A = fh_h; gf.lda = C; gf.W = final_linear.w; gf.ldw = C; gf.M = B; gf.N = ldim; gf.K = C;
     gf.epi.bias = final_linear.b; gf.epi.alpha = inv;
     gf.epi.residual = fh_cur; gf.epi.ldr = ldim; gf.epi.C = fh_cur; gf.epi.ldc = ldim;
-    nl += gemm(gf, st);
+    nl += pgemm(gf);
   }
   CUDA_TRY(cudaGetLastError());
   return PTTS_OK;
@@ -1021,7 +1087,7 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     GemmArgs g;
     g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = B; g.N = D; g.K = ldim;
     g.epi.bias = input_linear.b; g.epi.C = x; g.epi.ldc = D;
-    nl += gemm(g, st);
+    nl += pgemm(g);
   }
   int rc = flow_forward(B, max_keys, false);
   if (rc)
@@ -1045,6 +1111,7 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     s->kv_len++;
     s->frames++;
   }
+  prof_collect();
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[2], ev[4]);
   times.step_ms += ms;
@@ -1091,10 +1158,9 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     GemmArgs g;
     g.A = m_latin; g.lda = ldim; g.W = proj.w; g.ldw = ldim; g.M = total_frames; g.N = Md; g.K = ldim;
     g.epi.bias = proj.b; g.epi.C = m_lat; g.epi.ldc = Md;
-    nl += gemm(g, st);
+    nl += pgemm(g);
   }
   nl += upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st);
-  debug_bufs["mimi_upsample"] = {m_x, (size_t)Rb * Md};
   // decoder transformer (mimi.go:245-441)
   for (int l = 0; l < ML; l++) {
     DTLayer &ly = ml[l];
@@ -1102,18 +1168,28 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     GemmArgs g;
     g.A = m_nrm; g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
     g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
-    nl += gemm(g, st);
+    nl += pgemm(g);
     nl += rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st);
-    nl += attention_window(m_qkv, 3 * Md, m_att, Md, Rb, Md, MH, d_mrow_pos, Mctx, st);
+    if (prof_on) {
+      double keys = 0;
+      for (int r = 0; r < Rb; r++)
+        if (h_mrow_pos[r] >= 0)
+          keys += h_mrow_pos[r] + 1 < Mctx ? h_mrow_pos[r] + 1 : Mctx;
+      cudaEvent_t a, b;
+      prof_begin(&a, &b);
+      nl += attention_window(m_qkv, 3 * Md, m_att, Md, Rb, Md, MH, d_mrow_pos, Mctx, st);
+      prof_end(a, b, "attention_window", 4.0 * keys * Md, 8.0 * keys * Md);
+    } else
+      nl += attention_window(m_qkv, 3 * Md, m_att, Md, Rb, Md, MH, d_mrow_pos, Mctx, st);
     GemmArgs o;
     o.A = m_att; o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
     o.epi.colscale = ly.ls1; o.epi.residual = m_x; o.epi.ldr = Md; o.epi.C = m_x; o.epi.ldc = Md;
-    nl += gemm(o, st);
+    nl += pgemm(o);
     nl += layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st);
     GemmArgs f1;
     f1.A = m_nrm; f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
     f1.epi.act = ACT_GELU; f1.epi.C = m_ff; f1.epi.ldc = MF;
-    nl += gemm(f1, st);
+    nl += pgemm(f1);
     GemmArgs f2;
     f2.A = m_ff; f2.lda = MF; f2.W = ly.l2.w; f2.ldw = MF; f2.M = Rb; f2.N = Md; f2.K = MF;
     f2.epi.colscale = ly.ls2; f2.epi.residual = m_x; f2.epi.ldr = Md; f2.epi.C = m_x; f2.epi.ldc = Md;
@@ -1121,7 +1197,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
       f2.epi.rowmask = d_mmask;
       f2.epi.mask_div = 1;
     }
-    nl += gemm(f2, st);
+    nl += pgemm(f2);
   }
   debug_bufs["mimi_transformer"] = {m_x, (size_t)Rb * Md};
   // SEANet (mimi.go:745-787): convs as GEMMs over overlapping channels-last rows
@@ -1133,7 +1209,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     g.epi.bias = c.b; g.epi.C = raw; g.epi.ldc = c.N; g.epi.C2 = elu; g.epi.ldc2 = c.N;
     g.epi.residual = residual; g.epi.ldr = c.N;
     g.epi.rowmask = d_mmask; g.epi.mask_div = div;
-    nl += gemm(g, st);
+    nl += pgemm(g);
   };
   conv_gemm(init_conv, m_x, Rb, 1, nullptr, m_y0e, nullptr);
   debug_bufs["mimi_init_elu"] = {m_y0e, (size_t)Rb * init_conv.cout};
@@ -1159,6 +1235,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
   cudaEventRecord(ev[7], st);
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
+  prof_collect();
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[5], ev[6]);
   times.mimi_ms += ms;

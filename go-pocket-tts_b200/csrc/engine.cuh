@@ -107,6 +107,12 @@ struct Engine {
   } te[2];
   std::map<int, float *> tvec_cache; // lsd_steps -> device [steps, C]
 
+  // ---- split-K scratch for skinny GEMMs ----
+  float *gemm_ws = nullptr;
+  long gemm_ws_floats = 0;
+  int *gemm_counters = nullptr;
+  int gemm_n_counters = 4096;
+
   // ---- KV pool ----
   float *kv_pool = nullptr;
   int n_pages = 0, page_tokens = 16, max_pages = 0;
@@ -152,6 +158,25 @@ struct Engine {
   ptts_stage_times times{};
   cudaEvent_t ev[8]{};
   std::map<std::string, std::pair<const float *, size_t>> debug_bufs;
+
+  // ---- per-kernel-class profiling (CUDA events on the launch stream) ----
+  struct ProfAcc {
+    int64_t launches = 0;
+    double ms = 0, flops = 0, bytes = 0;
+  };
+  struct ProfRec {
+    cudaEvent_t a, b;
+    std::string cls;
+    double flops, bytes;
+  };
+  bool prof_on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+  std::vector<ProfRec> prof_pending;
+  std::map<std::string, ProfAcc> prof_acc;
+  int pgemm(const GemmArgs &g);
+  void prof_begin(cudaEvent_t *a, cudaEvent_t *b);
+  void prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes);
+  void prof_collect(); // after a stream sync
 
   // ---- scheduler ----
   std::mutex gpu_mu;   // serialises GPU passes (scheduler thread vs stage API)

@@ -127,8 +127,12 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemmArgs g) {
 // ---------------------------------------------------------------------------
 // tiled SGEMM
 // ---------------------------------------------------------------------------
+// Split-K (gridDim.z > 1): every CTA writes its partial tile to the workspace,
+// the last CTA to arrive on the tile's counter sums the partials in split order
+// (deterministic) and runs the epilogue; the counter resets itself.
 template <int BM, int BN, int RM, int RN>
-__global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)))
+__global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)),
+                                  ((BM / (4 * RM)) * (BN / (4 * RN)) >= 256 ? 2 : 3))
     sgemm_tn_kernel(GemmArgs g) {
   constexpr int BK = 16;
   constexpr int TX = BN / (4 * RN), TY = BM / (4 * RM), NT = TX * TY;
@@ -202,14 +206,20 @@ __global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)))
     for (int j = 0; j < 4 * RN; j++)
       acc[i][j] = 0.0f;
 
-  const int nk = (K + BK - 1) / BK;
-  gload(0);
-  sstore(0);
+  const int nk_all = (K + BK - 1) / BK;
+  const int S = gridDim.z;
+  const int kt_per = (nk_all + S - 1) / S;
+  const int kt0 = blockIdx.z * kt_per;
+  const int nk = min(nk_all - kt0, kt_per) > 0 ? min(nk_all - kt0, kt_per) : 0;
+  if (nk > 0) {
+    gload(kt0 * BK);
+    sstore(0);
+  }
   __syncthreads();
   for (int kt = 0; kt < nk; kt++) {
     const int buf = kt & 1;
     if (kt + 1 < nk)
-      gload((kt + 1) * BK);
+      gload((kt0 + kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; k++) {
       float a[4 * RM], b[4 * RN];
@@ -232,6 +242,44 @@ __global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)))
     if (kt + 1 < nk)
       sstore(buf ^ 1);
     __syncthreads();
+  }
+
+  if (S > 1) {
+    __shared__ int s_last;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    constexpr int FR = 4 * RM * RN; // float4 fragments per thread
+    float4 *wsp = reinterpret_cast<float4 *>(g.ws) + ((long)tile * S) * FR * NT;
+    float4 *mine = wsp + (long)blockIdx.z * FR * NT;
+#pragma unroll
+    for (int i = 0; i < 4 * RM; i++)
+#pragma unroll
+      for (int rn = 0; rn < RN; rn++)
+        mine[(i * RN + rn) * NT + tid] = make_float4(acc[i][rn * 4 + 0], acc[i][rn * 4 + 1],
+                                                     acc[i][rn * 4 + 2], acc[i][rn * 4 + 3]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int prev = atomicAdd(g.counters + tile, 1);
+      s_last = (prev == S - 1);
+      if (s_last)
+        g.counters[tile] = 0;
+    }
+    __syncthreads();
+    if (!s_last)
+      return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 4 * RM; i++)
+#pragma unroll
+      for (int rn = 0; rn < RN; rn++) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < S; sp++) {
+          float4 u = __ldcg(wsp + ((long)sp * FR + (i * RN + rn)) * NT + tid);
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        acc[i][rn * 4 + 0] = t.x; acc[i][rn * 4 + 1] = t.y;
+        acc[i][rn * 4 + 2] = t.z; acc[i][rn * 4 + 3] = t.w;
+      }
   }
 
   const GemmEpi &e = g.epi;
@@ -271,8 +319,20 @@ __global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)))
 
 template <int BM, int BN, int RM, int RN>
 static void launch_sgemm(const GemmArgs &g, cudaStream_t st) {
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, 1);
   constexpr int NT = (BM / (4 * RM)) * (BN / (4 * RN));
+  // split-K until ~2 CTAs per SM, bounded by the K loop and the workspace
+  const long tiles = (long)grid.x * grid.y;
+  const int nk = (g.K + 15) / 16;
+  int S = 1;
+  if (g.ws && g.counters && tiles < 148 && tiles <= g.n_counters) {
+    S = (int)((2 * 148 + tiles - 1) / tiles);
+    if (S > nk / 4) S = nk / 4;
+    if (S > 32) S = 32;
+    while (S > 1 && tiles * S * (long)BM * BN > g.ws_floats) S--;
+    if (S < 1) S = 1;
+  }
+  grid.z = S;
   sgemm_tn_kernel<BM, BN, RM, RN><<<grid, NT, 0, st>>>(g);
 }
 
@@ -293,10 +353,14 @@ static void launch_gemv(const GemmArgs &g, cudaStream_t st) {
   }
 }
 
+static thread_local const char *g_variant = "";
+const char *gemm_last_variant() { return g_variant; }
+
 int gemm(const GemmArgs &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0)
     return 0;
   if (g.M <= 8) {
+    g_variant = "gemv_f32";
     if (g.M == 1)
       launch_gemv<1>(g, st);
     else if (g.M == 2)
@@ -311,18 +375,38 @@ int gemm(const GemmArgs &g, cudaStream_t st) {
     return (long)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
   };
   const long want = 148; // at least one CTA per SM before growing the tile
+  const bool can_split = g.ws && g.counters && g.K >= 256;
+  if (can_split && g.N >= 128 && g.M <= 512) {
+    // skinny-M regime of the batched AR step: big tiles + split-K keep all SMs
+    // streaming weights
+    if (g.M > 64) {
+      g_variant = "sgemm_128x128";
+      launch_sgemm<128, 128, 2, 2>(g, st);
+    } else {
+      g_variant = "sgemm_64x128";
+      launch_sgemm<64, 128, 2, 2>(g, st);
+    }
+    return 1;
+  }
   if (g.N <= 32) {
-    if (ctas(128, 32) >= want)
+    if (ctas(128, 32) >= want) {
+      g_variant = "sgemm_128x32";
       launch_sgemm<128, 32, 2, 1>(g, st);
-    else
+    } else {
+      g_variant = "sgemm_64x32";
       launch_sgemm<64, 32, 2, 1>(g, st);
+    }
   } else if (ctas(128, 128) >= want && g.N >= 128) {
+    g_variant = "sgemm_128x128";
     launch_sgemm<128, 128, 2, 2>(g, st);
   } else if (ctas(64, 128) >= want && g.N >= 128) {
+    g_variant = "sgemm_64x128";
     launch_sgemm<64, 128, 2, 2>(g, st);
   } else if (ctas(64, 64) >= want || g.M > 32) {
+    g_variant = "sgemm_64x64";
     launch_sgemm<64, 64, 2, 2>(g, st);
   } else {
+    g_variant = "sgemm_32x64";
     launch_sgemm<32, 64, 1, 2>(g, st);
   }
   return 1;

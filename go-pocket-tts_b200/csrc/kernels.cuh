@@ -44,12 +44,19 @@ struct GemmArgs {
   long ldw = 0;
   int M = 0, N = 0, K = 0;
   GemmEpi epi;
+  // split-K scratch (optional): partial tiles + self-resetting tile counters
+  float *ws = nullptr;
+  long ws_floats = 0;
+  int *counters = nullptr;
+  int n_counters = 0;
 };
 
 // C = epi(A * W^T).  Chooses the weight-streaming skinny kernel for M <= 8 and
 // a tiled SGEMM otherwise.  Requires K % 4 == 0, N % 4 == 0 for the tiled path
 // (N == 1 goes through rowdot).  Returns the number of kernels launched.
 int gemm(const GemmArgs &g, cudaStream_t st);
+// Name of the kernel variant the last gemm() call on this thread selected.
+const char *gemm_last_variant();
 // out[m] = dot(A[m,:K], w) + bias0   (N == 1 linear: out_eos)
 int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
            float *out, cudaStream_t st);

@@ -628,6 +628,37 @@ int ptts_stage_times_get(ptts_engine *e, ptts_stage_times *out, int32_t reset) {
   return PTTS_OK;
 }
 
+int ptts_profile_enable(ptts_engine *e, int32_t on) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  e->impl.prof_on = on != 0;
+  if (on)
+    e->impl.prof_acc.clear();
+  return PTTS_OK;
+}
+
+int ptts_profile_report(ptts_engine *e, char *buf, int32_t cap) {
+  if (!e || !buf || cap <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: profile_report: bad arguments");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  std::string s = "{";
+  bool first = true;
+  for (auto &kv : e->impl.prof_acc) {
+    char tmp[512];
+    snprintf(tmp, sizeof tmp, "%s\"%s\":{\"launches\":%lld,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
+             first ? "" : ",", kv.first.c_str(), (long long)kv.second.launches, kv.second.ms,
+             kv.second.flops, kv.second.bytes);
+    s += tmp;
+    first = false;
+  }
+  s += "}";
+  if ((int)s.size() + 1 > cap)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: profile_report: buffer too small");
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
 int64_t ptts_debug_fetch(ptts_engine *e, const char *name, float *out, int64_t cap) {
   if (!e || !name)
     return -1;

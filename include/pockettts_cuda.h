@@ -218,6 +218,12 @@ int ptts_seq_close(ptts_engine *e, ptts_seq *s);
 
 /* ---- instrumentation (bench/stageprof "device-timed stages") -------------- */
 int ptts_stage_times_get(ptts_engine *e, ptts_stage_times *out, int32_t reset);
+/* Per-kernel-class CUDA-event profiling: while enabled every GEMM / attention
+ * launch is bracketed by an event pair on the launch stream; the report is a
+ * JSON object {class: {launches, ms, flops, bytes}} with ALGORITHMIC flops and
+ * bytes. */
+int ptts_profile_enable(ptts_engine *e, int32_t on);
+int ptts_profile_report(ptts_engine *e, char *buf, int32_t cap);
 /* Copies a named internal buffer of the last pass (debug / stage parity). */
 int64_t ptts_debug_fetch(ptts_engine *e, const char *name, float *out,
                          int64_t cap);
