@@ -148,6 +148,7 @@ def main():
     import importlib
     ck = importlib.import_module("pockettts_b200.checkpoint")
     wl = importlib.import_module("pockettts_b200.workload")
+    sh = importlib.import_module("pockettts_b200.sharding")
     arch = ck.ArchConfig.full() if args.arch == "full" else ck.ArchConfig.small()
     workload_name = (f"C5 shard: {args.utterances} utterances/GPU x U{{5..60}} words, <=50-token chunks, "
                      f"forced-EOS schedule, lsd_steps=1, random-init PocketTTS ({args.arch}), seed 20260118")
@@ -201,7 +202,7 @@ def main():
     tensors = ck.make_checkpoint(arch)
     rt = pkg.NativeCudaRuntime(tensors=tensors, device=local_rank, max_batch=args.max_batch, max_seq_tokens=512,
                                max_frames=256, mimi_group_frames=2048)
-    chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=rank * args.utterances)
+    chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=sh.shard_range(rank, world, args.utterances)[0])
     noises = [c.noise() for c in chunks]
     h2d = sum(c.tokens.nbytes + n.nbytes for c, n in zip(chunks, noises))
 
@@ -232,14 +233,8 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
         dev_ms = e0.elapsed_time(e1)
-        t = torch.tensor([dev_ms, float(frames), float(samples), wall * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone()
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            return tmax[0].item(), tsum[1].item(), tsum[2].item(), tmax[3].item()
-        return t[0].item(), t[1].item(), t[2].item(), t[3].item()
+        return sh.reduce_timing(dist if world > 1 else None, torch, "cuda", dev_ms, float(frames), float(samples),
+                                wall * 1e3)
 
     for _ in range(args.warmup):
         run_pass(True)
@@ -253,9 +248,9 @@ def main():
     st = rt.stage_times()
     prof = rt.profile_report()
     rt.profile(False)
-    value = (frames * 1920 / 24000.0) / (ms / 1e3)
+    value = sh.job_throughput(frames, ms)
     ms2, frames2, samples2, _ = timed(False, args.steps)
-    e2e = (frames2 * 1920 / 24000.0) / (ms2 / 1e3)
+    e2e = sh.job_throughput(frames2, ms2)
 
     out = None
     if rank == 0:

@@ -1,0 +1,212 @@
+//go:build cgo && linux
+
+// Package cuda binds the B200-native PocketTTS engine (libpockettts_cuda.so)
+// for the `native-cuda` backend.  It replaces internal/native.Model for the
+// synthesis hot path: weights are uploaded once from the safetensors store,
+// GenerateAudio becomes one blocking C call that the engine batches
+// continuously with every other in-flight request.
+package cuda
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../third_party/pockettts_b200/include
+#cgo LDFLAGS: -L${SRCDIR}/../../../third_party/pockettts_b200/lib -lpockettts_cuda -Wl,-rpath,$ORIGIN/../lib
+#include <stdlib.h>
+#include "pockettts_cuda.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"runtime"
+	"unsafe"
+
+	"github.com/cwbudde/go-pocket-tts/internal/safetensors"
+)
+
+// ErrCanceled is returned when the request's context was cancelled.
+var ErrCanceled = errors.New("native-cuda: request canceled")
+
+// Config mirrors ptts_config.
+type Config struct {
+	Device           int
+	MaxBatch         int
+	MaxSeqTokens     int
+	MaxFrames        int
+	KVPages          int
+	MimiGroupFrames  int
+	MaxPrefillTokens int
+}
+
+// GenConfig mirrors ptts_gen_cfg (tts.RuntimeGenerateConfig minus the voices).
+type GenConfig struct {
+	Temperature       float64
+	EOSThreshold      float64
+	MaxSteps          int
+	EstimatedMaxSteps int
+	LSDDecodeSteps    int
+	FramesAfterEOS    int
+}
+
+// VoiceLayer is one `transformer.layers.{i}.self_attn` module of an upstream
+// voice model-state file: cache [2,1,T,H,D] and offset.
+type VoiceLayer struct {
+	Cache       []float32
+	CacheTokens int
+	Offset      int
+}
+
+// Engine owns the device-resident model of one GPU.
+type Engine struct {
+	h *C.ptts_engine
+}
+
+func lastError(rc C.int) error {
+	if rc == C.PTTS_ECANCELED {
+		return ErrCanceled
+	}
+	return errors.New(C.GoString(C.ptts_last_error()))
+}
+
+// Open creates the engine and uploads every tensor of the store, exactly the
+// keys internal/native loads (LoadModelFromStore, model.go:42-66).
+func Open(store *safetensors.Store, cfg Config) (*Engine, error) {
+	var cc C.ptts_config
+	cc.device = C.int32_t(cfg.Device)
+	cc.max_batch = C.int32_t(cfg.MaxBatch)
+	cc.max_seq_tokens = C.int32_t(cfg.MaxSeqTokens)
+	cc.max_frames = C.int32_t(cfg.MaxFrames)
+	cc.kv_pages = C.int32_t(cfg.KVPages)
+	cc.mimi_group_frames = C.int32_t(cfg.MimiGroupFrames)
+	cc.max_prefill_tokens = C.int32_t(cfg.MaxPrefillTokens)
+
+	e := &Engine{}
+	if rc := C.ptts_create(&cc, &e.h); rc != 0 {
+		return nil, fmt.Errorf("native-cuda: create engine: %w", lastError(rc))
+	}
+
+	for _, name := range store.Names() {
+		t, err := store.Tensor(name) // decoded to []float32 (store.go:195-211)
+		if err != nil {
+			e.Close()
+			return nil, err
+		}
+		if len(t.Data) == 0 {
+			continue
+		}
+		cname := C.CString(name)
+		shape := make([]C.int64_t, len(t.Shape))
+		for i, d := range t.Shape {
+			shape[i] = C.int64_t(d)
+		}
+		var sp *C.int64_t
+		if len(shape) > 0 {
+			sp = &shape[0]
+		}
+		rc := C.ptts_load_tensor(e.h, cname, sp, C.int32_t(len(shape)), C.PTTS_DTYPE_F32,
+			unsafe.Pointer(&t.Data[0]))
+		C.free(unsafe.Pointer(cname))
+		runtime.KeepAlive(t)
+		if rc != 0 {
+			e.Close()
+			return nil, fmt.Errorf("native-cuda: upload %q: %w", name, lastError(rc))
+		}
+	}
+
+	if rc := C.ptts_finalize_weights(e.h); rc != 0 {
+		e.Close()
+		return nil, fmt.Errorf("native-cuda: finalize weights: %w", lastError(rc))
+	}
+	return e, nil
+}
+
+// Close releases the engine. Nil-safe and idempotent.
+func (e *Engine) Close() {
+	if e == nil || e.h == nil {
+		return
+	}
+	C.ptts_destroy(e.h)
+	e.h = nil
+}
+
+// Ticket identifies an in-flight request.
+type Ticket struct {
+	id   C.int64_t
+	pcm  []float32
+	pins runtime.Pinner
+}
+
+// Submit queues one chunk.  noise is [maxSteps*32], drawn by the caller
+// (flow_lm.go:386-408); voiceEmb is [Tv*1024] or nil; voice is the upstream
+// model state or nil.  All slices stay pinned until Wait returns.
+func (e *Engine) Submit(tokens []int64, voiceEmb []float32, voiceFrames int, voice []VoiceLayer,
+	cfg GenConfig, noise []float32, maxSteps int) (*Ticket, error) {
+	if e == nil || e.h == nil {
+		return nil, errors.New("native-cuda runtime unavailable")
+	}
+	if len(tokens) == 0 {
+		return nil, errors.New("generate: token slice must not be empty")
+	}
+
+	t := &Ticket{pcm: make([]float32, maxSteps*C.PTTS_SAMPLES_PER_FRAME)}
+	var g C.ptts_gen_cfg
+	g.temperature = C.double(cfg.Temperature)
+	g.eos_threshold = C.double(cfg.EOSThreshold)
+	g.max_steps = C.int32_t(maxSteps)
+	g.estimated_max_steps = C.int32_t(cfg.EstimatedMaxSteps)
+	g.lsd_decode_steps = C.int32_t(cfg.LSDDecodeSteps)
+	g.frames_after_eos = C.int32_t(cfg.FramesAfterEOS)
+	g.force_eos_step = -1
+
+	t.pins.Pin(&tokens[0])
+	t.pins.Pin(&noise[0])
+	t.pins.Pin(&t.pcm[0])
+
+	var vemb *C.float
+	if len(voiceEmb) > 0 {
+		t.pins.Pin(&voiceEmb[0])
+		vemb = (*C.float)(unsafe.Pointer(&voiceEmb[0]))
+	}
+
+	var vkv *C.ptts_voice_kv
+	if len(voice) > 0 {
+		// C-allocated so the engine may keep the descriptor until Wait.
+		layers := (*[1 << 10]C.ptts_voice_layer)(C.calloc(C.size_t(len(voice)), C.sizeof_ptts_voice_layer))
+		for i := range voice {
+			t.pins.Pin(&voice[i].Cache[0])
+			layers[i].cache = (*C.float)(unsafe.Pointer(&voice[i].Cache[0]))
+			layers[i].cache_tokens = C.int32_t(voice[i].CacheTokens)
+			layers[i].offset = C.int32_t(voice[i].Offset)
+		}
+		vkv = (*C.ptts_voice_kv)(C.calloc(1, C.sizeof_ptts_voice_kv))
+		vkv.layers = &layers[0]
+		vkv.n_layers = C.int32_t(len(voice))
+	}
+
+	rc := C.ptts_submit(e.h, (*C.int64_t)(unsafe.Pointer(&tokens[0])), C.int32_t(len(tokens)),
+		vemb, C.int32_t(voiceFrames), vkv, &g,
+		(*C.float)(unsafe.Pointer(&noise[0])), C.int32_t(len(noise)/C.PTTS_LATENT_DIM),
+		(*C.float)(unsafe.Pointer(&t.pcm[0])), C.int64_t(len(t.pcm)), &t.id)
+	if rc != 0 {
+		t.pins.Unpin()
+		return nil, lastError(rc)
+	}
+	return t, nil
+}
+
+// Wait blocks until the chunk is synthesised and returns a fresh PCM slice
+// owned by the caller (runtime_native_safetensors.go:237).
+func (e *Engine) Wait(t *Ticket) ([]float32, int, error) {
+	var res C.ptts_result
+	rc := C.ptts_wait(e.h, t.id, &res)
+	C.ptts_ticket_release(e.h, t.id)
+	t.pins.Unpin()
+	if rc != 0 {
+		return nil, 0, lastError(rc)
+	}
+	out := append([]float32(nil), t.pcm[:int(res.n_samples)]...)
+	return out, int(res.n_frames), nil
+}
+
+// Cancel evicts the request at the next step boundary.
+func (e *Engine) Cancel(t *Ticket) { C.ptts_cancel(e.h, t.id) }
