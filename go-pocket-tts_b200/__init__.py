@@ -24,7 +24,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libpockettts_cuda.so")
-CSRC = ["gemm.cu", "attention.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "safetensors.cpp"]
+CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "safetensors.cpp"]
 
 PTTS_OK, PTTS_EINVAL, PTTS_ECUDA, PTTS_ENOMEM, PTTS_ESTATE, PTTS_ECANCELED = 0, -1, -2, -3, -4, -5
 PTTS_REQ_NO_PCM_D2H = 1
@@ -109,6 +109,7 @@ EXPORTS = [
     "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
+    "ptts_debug_gemm", "ptts_debug_gemm_bench",
 ]
 
 _lib = None
@@ -156,6 +157,8 @@ def lib() -> C.CDLL:
     L.ptts_debug_fetch.argtypes = [vp, C.c_char_p, fp, C.c_int64]
     L.ptts_debug_fetch.restype = C.c_int64
     L.ptts_profile_enable.argtypes = [vp, C.c_int32]
+    L.ptts_debug_gemm_bench.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
+    L.ptts_debug_gemm.argtypes = [vp, fp, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, C.c_int32, fp]
     L.ptts_profile_report.argtypes = [vp, C.c_char_p, C.c_int32]
     _lib = L
     return L
@@ -271,11 +274,12 @@ class NativeCudaRuntime:
 
     def __init__(self, checkpoint: Optional[str] = None, *, device: int = 0, max_batch: int = 256,
                  max_seq_tokens: int = 1024, max_frames: int = 512, mimi_group_frames: int = 0,
-                 kv_pages: int = 0, tensors: Optional[dict] = None):
+                 kv_pages: int = 0, tensors: Optional[dict] = None, flags: int = 0):
         self._lib = lib()
         self._h = C.c_void_p()
         cfg = PttsConfig(device=device, max_batch=max_batch, max_seq_tokens=max_seq_tokens,
-                         max_frames=max_frames, mimi_group_frames=mimi_group_frames, kv_pages=kv_pages)
+                         max_frames=max_frames, mimi_group_frames=mimi_group_frames, kv_pages=kv_pages,
+                         flags=flags)
         _check(self._lib.ptts_create(C.byref(cfg), C.byref(self._h)))
         try:
             if checkpoint is not None:
@@ -439,6 +443,22 @@ class NativeCudaRuntime:
         t = PttsStageTimes()
         _check(self._lib.ptts_stage_times_get(self._h, C.byref(t), 1 if reset else 0))
         return {n: getattr(t, n) for n, _ in PttsStageTimes._fields_}
+
+    def debug_gemm(self, A, W, bias=None, act: int = 0, path: int = 0) -> np.ndarray:
+        """C = act(A @ W.T + bias) through path 0 (auto) / 1 (CUDA cores) / 2 (tcgen05)."""
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        out = np.empty((A.shape[0], W.shape[0]), dtype=np.float32)
+        _check(self._lib.ptts_debug_gemm(self._h, _fptr(A), A.shape[0], A.shape[1], _fptr(W), W.shape[0],
+                                         _fptr(b), act, path, _fptr(out)))
+        return out
+
+    def gemm_bench(self, M: int, K: int, N: int, path: int = 0, reps: int = 20, lda: int = 0) -> float:
+        """Average microseconds per launch of one GEMM shape."""
+        us = C.c_float(0)
+        _check(self._lib.ptts_debug_gemm_bench(self._h, M, K, N, lda, path, reps, C.byref(us)))
+        return float(us.value)
 
     def profile(self, on: bool):
         _check(self._lib.ptts_profile_enable(self._h, 1 if on else 0))

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ptts {
@@ -40,6 +41,7 @@ int Engine::create(const ptts_config *c) {
   if (cfg.device < 0 || cfg.device >= ndev)
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: device %d out of range [0,%d)", cfg.device, ndev);
   device = cfg.device;
+  tc_on = !(cfg.flags & PTTS_ENGINE_NO_TENSOR_CORES) && !getenv("PTTS_NO_TC");
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -66,6 +68,8 @@ Engine::~Engine() {
   }
   for (void *p : allocs)
     cudaFree(p);
+  for (TcWeight *t : tc_owned)
+    delete t;
   auto fh = [](void *p) {
     if (p)
       cudaFreeHost(p);
@@ -138,21 +142,187 @@ void Engine::prof_collect() {
   }
   prof_pending.clear();
 }
+static inline uint16_t f32_to_bf16_rn(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+  return (uint16_t)u;
+}
+static inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float x;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// Splits W [N,K] fp32 into bf16 hi rows [0,N) and lo rows [N,2N) (x ~= hi + lo,
+// ~16 mantissa bits), uploads it and builds the TMA descriptors.
+int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, int K) {
+  if (!tc_on || K % 8 != 0 || N % 16 != 0 || K < 32 || N < 32)
+    return PTTS_OK; // stays on the CUDA-core path
+  std::vector<uint16_t> sp((size_t)2 * N * K);
+  for (size_t i = 0; i < (size_t)N * K; i++) {
+    uint16_t h = f32_to_bf16_rn(w[i]);
+    sp[i] = h;
+    sp[(size_t)N * K + i] = f32_to_bf16_rn(w[i] - bf16_to_f32(h));
+  }
+  void *d = nullptr;
+  int rc = dmalloc(&d, sp.size() * 2);
+  if (rc)
+    return rc;
+  CUDA_TRY(cudaMemcpy(d, sp.data(), sp.size() * 2, cudaMemcpyHostToDevice));
+  TcWeight *t = new TcWeight();
+  tc_owned.push_back(t);
+  int r = tc_weight_init(t, d, N, K);
+  if (r)
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed (%d) for a [%d,%d] weight", r, N, K);
+  tc_map[d_w_fp32] = t;
+  return PTTS_OK;
+}
+
 int Engine::pgemm(const GemmArgs &g0) {
   GemmArgs g = g0;
   g.ws = gemm_ws;
   g.ws_floats = gemm_ws_floats;
   g.counters = gemm_counters;
   g.n_counters = gemm_n_counters;
-  if (!prof_on)
-    return gemm(g, st);
+  const TcWeight *tw = nullptr;
+  if (tc_on && g.M >= tc_min_m && tc_gemm_supported(g)) {
+    auto it = tc_map.find(g.W);
+    if (it != tc_map.end())
+      tw = it->second;
+  }
+  const char *variant = "";
   cudaEvent_t a, b;
-  prof_begin(&a, &b);
-  int n = gemm(g, st);
-  double kk = g.K < g.lda ? g.K : g.lda; // overlapping conv rows: unique A bytes
-  prof_end(a, b, gemm_last_variant(), 2.0 * g.M * g.N * g.K,
-           4.0 * ((double)g.N * g.K + (double)g.M * kk + (double)g.M * g.N));
+  if (prof_on)
+    prof_begin(&a, &b);
+  int n;
+  if (tw) {
+    n = tc_gemm(*tw, g, st, &variant);
+    if (n < 0) { // could not configure the kernel: fall back to the CUDA-core GEMM
+      n = gemm(g, st);
+      variant = gemm_last_variant();
+    }
+  } else {
+    n = gemm(g, st);
+    variant = gemm_last_variant();
+  }
+  if (prof_on) {
+    double kk = g.K < g.lda ? g.K : g.lda; // overlapping conv rows: unique A bytes
+    prof_end(a, b, variant, 2.0 * g.M * g.N * g.K,
+             4.0 * ((double)g.N * g.K + (double)g.M * kk + (double)g.M * g.N));
+  }
   return n;
+}
+
+// Stand-alone GEMM through a chosen path (0 auto, 1 CUDA cores, 2 tcgen05):
+// unit-test hook for the kernels.
+int Engine::debug_gemm(const float *A, int M, int K, const float *W, int N, const float *bias, int act,
+                       int path, float *C) {
+  float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
+  CUDA_TRY(cudaMalloc(&dA, (size_t)M * K * 4));
+  CUDA_TRY(cudaMalloc(&dW, (size_t)N * K * 4));
+  CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4));
+  CUDA_TRY(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dW, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
+  if (bias) {
+    CUDA_TRY(cudaMalloc(&dB, (size_t)N * 4));
+    CUDA_TRY(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+  }
+  GemmArgs g;
+  g.A = dA; g.lda = K; g.W = dW; g.ldw = K; g.M = M; g.N = N; g.K = K;
+  g.epi.bias = dB; g.epi.act = act; g.epi.C = dC; g.epi.ldc = N;
+  int rc = PTTS_OK;
+  const bool saved = tc_on;
+  const int saved_min = tc_min_m;
+  if (path == 2) {
+    tc_on = true;
+    tc_min_m = 1;
+    std::vector<float> hw(W, W + (size_t)N * K);
+    rc = make_tc(dW, hw, N, K);
+    if (rc == PTTS_OK && (!tc_map.count(dW) || !tc_gemm_supported(g))) {
+      set_error("native-cuda: debug_gemm: shape [%d,%d]x[%d,%d] not supported by the tcgen05 path", M, K, N, K);
+      rc = PTTS_EINVAL;
+    }
+  } else if (path == 1) {
+    tc_on = false;
+  }
+  if (rc == PTTS_OK) {
+    times.kernel_launches += pgemm(g);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+      e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("cuda: debug_gemm failed: %s", cudaGetErrorString(e));
+      rc = PTTS_ECUDA;
+    } else {
+      cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+    }
+  }
+  tc_on = saved;
+  tc_min_m = saved_min;
+  tc_map.erase(dW);
+  cudaFree(dA); cudaFree(dW); cudaFree(dC);
+  if (dB) cudaFree(dB);
+  return rc;
+}
+
+// Times one GEMM shape on device-resident data (CUDA events around `reps`
+// back-to-back launches).  lda < K exercises the overlapping-row conv form.
+int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us) {
+  if (lda <= 0)
+    lda = K;
+  float *dA = nullptr, *dW = nullptr, *dC = nullptr;
+  const size_t a_floats = (size_t)M * lda + K + 64;
+  CUDA_TRY(cudaMalloc(&dA, a_floats * 4));
+  CUDA_TRY(cudaMalloc(&dW, (size_t)N * K * 4));
+  CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4));
+  std::vector<float> hw((size_t)N * K), ha(a_floats);
+  for (size_t i = 0; i < hw.size(); i++)
+    hw[i] = (float)((int)(i * 2654435761u >> 20) % 2001 - 1000) * 1e-3f;
+  for (size_t i = 0; i < ha.size(); i++)
+    ha[i] = (float)((int)(i * 40503u >> 7) % 2001 - 1000) * 1e-3f;
+  CUDA_TRY(cudaMemcpy(dW, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dA, ha.data(), ha.size() * 4, cudaMemcpyHostToDevice));
+  GemmArgs g;
+  g.A = dA; g.lda = lda; g.W = dW; g.ldw = K; g.M = M; g.N = N; g.K = K;
+  g.epi.C = dC; g.epi.ldc = N;
+  const bool saved = tc_on, saved_prof = prof_on;
+  const int saved_min = tc_min_m;
+  prof_on = false;
+  int rc = PTTS_OK;
+  if (path == 2) {
+    tc_on = true;
+    tc_min_m = 1;
+    rc = make_tc(dW, hw, N, K);
+  } else if (path == 1) {
+    tc_on = false;
+  }
+  if (rc == PTTS_OK) {
+    for (int i = 0; i < 3; i++)
+      pgemm(g);
+    cudaEventRecord(ev[0], st);
+    for (int i = 0; i < reps; i++)
+      pgemm(g);
+    cudaEventRecord(ev[1], st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+      e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("cuda: debug_gemm_bench failed: %s", cudaGetErrorString(e));
+      rc = PTTS_ECUDA;
+    } else {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      *avg_us = 1e3f * ms / (float)reps;
+    }
+  }
+  tc_on = saved;
+  tc_min_m = saved_min;
+  prof_on = saved_prof;
+  tc_map.erase(dW);
+  cudaFree(dA); cudaFree(dW); cudaFree(dC);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------
@@ -240,6 +410,8 @@ struct Loader {
     int rc = e->upload(w->data, &l->w);
     if (rc)
       return rc;
+    if ((rc = e->make_tc(l->w, w->data, l->out, l->in)))
+      return rc;
     l->b = nullptr;
     if (with_bias) {
       const HostTensor *b = get(name + ".bias");
@@ -303,6 +475,8 @@ struct Loader {
     int rc = e->upload(wp, &c->w);
     if (rc)
       return rc;
+    if ((rc = e->make_tc(c->w, wp, c->N, c->K)))
+      return rc;
     c->b = nullptr;
     if (const HostTensor *b = get(p + ".bias"))
       if ((rc = e->upload(b->data, &c->b)))
@@ -334,6 +508,8 @@ struct Loader {
     c->cin = ci; c->cout = co; c->taps = J; c->stride = stride; c->N = stride * co; c->K = J * ci;
     int rc = e->upload(wp, &c->w);
     if (rc)
+      return rc;
+    if ((rc = e->make_tc(c->w, wp, c->N, c->K)))
       return rc;
     c->b = nullptr;
     if (const HostTensor *b = get(p + ".bias")) {
@@ -451,6 +627,7 @@ int Engine::finalize() {
   ada_all.in = C;
   ada_all.out = ada_n;
   if ((rc = upload(ada_w, &ada_all.w))) return rc;
+  if ((rc = make_tc(ada_all.w, ada_w, ada_n, C))) return rc;
   if ((rc = upload(ada_b, &ada_all.b))) return rc;
   if ((rc = ld.linear("flow_lm.flow_net.final_layer.linear", true, &final_linear))) return rc;
   if (final_linear.in != C || final_linear.out != ldim || cond_embed.in != D ||
@@ -510,6 +687,7 @@ int Engine::finalize() {
     proj.in = ic_n;
     proj.out = oc_n;
     if ((rc = upload(pw, &proj.w))) return rc;
+    if ((rc = make_tc(proj.w, pw, proj.out, proj.in))) return rc;
     if ((rc = upload(pb, &proj.b))) return rc;
   }
   {

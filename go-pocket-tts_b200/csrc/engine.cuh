@@ -107,6 +107,17 @@ struct Engine {
   } te[2];
   std::map<int, float *> tvec_cache; // lsd_steps -> device [steps, C]
 
+  // ---- tcgen05 path: split-bf16 copies of the GEMM weights, keyed by the fp32
+  //      device pointer the layer code passes as GemmArgs::W ----
+  bool tc_on = true;
+  int tc_min_m = 9; // M <= 8 stays on the weight-streaming GEMV
+  std::unordered_map<const float *, TcWeight *> tc_map;
+  std::vector<TcWeight *> tc_owned;
+  int make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, int K);
+  int debug_gemm(const float *A, int M, int K, const float *W, int N, const float *bias, int act,
+                 int path, float *C);
+  int debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us);
+
   // ---- split-K scratch for skinny GEMMs ----
   float *gemm_ws = nullptr;
   long gemm_ws_floats = 0;

@@ -12,37 +12,10 @@
 //               double-buffered shared-memory tiles.  (The tcgen05 split-bf16
 //               path replaces this for the batched regime; see DESIGN.md.)
 #include "kernels.cuh"
+#include "gemm_epi.cuh"
 #include <math.h>
 
 namespace ptts {
-
-__device__ __forceinline__ float act_apply(float v, int act) {
-  switch (act) {
-  case ACT_GELU:
-    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-  case ACT_SILU:
-    return v / (1.0f + expf(-v));
-  case ACT_ELU:
-    return v > 0.0f ? v : expf(v) - 1.0f;
-  default:
-    return v;
-  }
-}
-
-__device__ __forceinline__ float epi_one(const GemmEpi &e, float acc, int m, int n) {
-  float v = acc;
-  if (e.bias)
-    v += __ldg(e.bias + n);
-  v = act_apply(v, e.act);
-  if (e.colscale)
-    v *= __ldg(e.colscale + n);
-  if (e.mul)
-    v *= e.mul[(long)m * e.ldmul + n];
-  v *= e.alpha;
-  if (e.residual)
-    v += e.residual[(long)m * e.ldr + n];
-  return v;
-}
 
 __device__ __forceinline__ float4 ldg_stream(const float *p) {
   float4 r;
@@ -271,15 +244,24 @@ __global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)),
 #pragma unroll
     for (int i = 0; i < 4 * RM; i++)
 #pragma unroll
-      for (int rn = 0; rn < RN; rn++) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp = 0; sp < S; sp++) {
-          float4 u = __ldcg(wsp + ((long)sp * FR + (i * RN + rn)) * NT + tid);
-          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      for (int j = 0; j < 4 * RN; j++)
+        acc[i][j] = 0.0f;
+    // all FR fragments of one split are loaded back-to-back (FR independent
+    // L2 loads in flight) before they are accumulated
+    for (int sp = 0; sp < S; sp++) {
+      float4 u[FR];
+#pragma unroll
+      for (int f = 0; f < FR; f++)
+        u[f] = __ldcg(wsp + ((long)sp * FR + f) * NT + tid);
+#pragma unroll
+      for (int i = 0; i < 4 * RM; i++)
+#pragma unroll
+        for (int rn = 0; rn < RN; rn++) {
+          const float4 t = u[i * RN + rn];
+          acc[i][rn * 4 + 0] += t.x; acc[i][rn * 4 + 1] += t.y;
+          acc[i][rn * 4 + 2] += t.z; acc[i][rn * 4 + 3] += t.w;
         }
-        acc[i][rn * 4 + 0] = t.x; acc[i][rn * 4 + 1] = t.y;
-        acc[i][rn * 4 + 2] = t.z; acc[i][rn * 4 + 3] = t.w;
-      }
+    }
   }
 
   const GemmEpi &e = g.epi;
@@ -296,11 +278,8 @@ __global__ void __launch_bounds__((BM / (4 * RM)) * (BN / (4 * RN)),
         const int n = n0 + rn * (BN / RN) + tx * 4;
         if (n >= N)
           continue;
-        float4 v;
-        v.x = epi_one(e, acc[rm * 4 + i][rn * 4 + 0], m, n + 0);
-        v.y = epi_one(e, acc[rm * 4 + i][rn * 4 + 1], m, n + 1);
-        v.z = epi_one(e, acc[rm * 4 + i][rn * 4 + 2], m, n + 2);
-        v.w = epi_one(e, acc[rm * 4 + i][rn * 4 + 3], m, n + 3);
+        float4 v = epi_vec4(e, make_float4(acc[rm * 4 + i][rn * 4 + 0], acc[rm * 4 + i][rn * 4 + 1],
+                                           acc[rm * 4 + i][rn * 4 + 2], acc[rm * 4 + i][rn * 4 + 3]), m, n);
         if (!live)
           v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.C)

@@ -57,6 +57,19 @@ struct GemmArgs {
 int gemm(const GemmArgs &g, cudaStream_t st);
 // Name of the kernel variant the last gemm() call on this thread selected.
 const char *gemm_last_variant();
+// ---- tcgen05 path (tcgemm.cu) -------------------------------------------------
+// A weight matrix split once into bf16 hi/lo rows [2N, K] plus its TMA
+// descriptors (opaque 128-byte CUtensorMap blobs, 64-byte aligned).
+struct alignas(64) TcWeight {
+  unsigned char map32[128], map64[128], map128[128];
+  const void *d_split = nullptr;
+  int N = 0, K = 0;
+};
+int tc_weight_init(TcWeight *w, const void *d_split, int N, int K);
+bool tc_gemm_supported(const GemmArgs &g);
+// Same contract as gemm(); W is taken from `w` (g.W is ignored).
+int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant);
+
 // out[m] = dot(A[m,:K], w) + bias0   (N == 1 linear: out_eos)
 int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
            float *out, cudaStream_t st);

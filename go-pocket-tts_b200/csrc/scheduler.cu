@@ -659,6 +659,24 @@ int ptts_profile_report(ptts_engine *e, char *buf, int32_t cap) {
   return (int)s.size();
 }
 
+int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const float *W, int32_t N,
+                    const float *bias, int32_t act, int32_t path, float *C) {
+  if (!e || !A || !W || !C || M <= 0 || N <= 0 || K <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: debug_gemm: bad arguments");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  cudaSetDevice(e->impl.device);
+  return e->impl.debug_gemm(A, M, K, W, N, bias, act, path, C);
+}
+
+int ptts_debug_gemm_bench(ptts_engine *e, int32_t M, int32_t K, int32_t N, int32_t lda, int32_t path,
+                          int32_t reps, float *avg_us) {
+  if (!e || !avg_us || M <= 0 || N <= 0 || K <= 0 || reps <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: debug_gemm_bench: bad arguments");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  cudaSetDevice(e->impl.device);
+  return e->impl.debug_gemm_bench(M, K, N, lda, path, reps, avg_us);
+}
+
 int64_t ptts_debug_fetch(ptts_engine *e, const char *name, float *out, int64_t cap) {
   if (!e || !name)
     return -1;

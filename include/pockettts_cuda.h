@@ -58,6 +58,7 @@ typedef struct {
 } ptts_config;
 
 #define PTTS_ENGINE_NO_GRAPHS 1 /* disable CUDA-graph replay of the B<=8 step */
+#define PTTS_ENGINE_NO_TENSOR_CORES 2 /* keep every GEMM on the fp32 CUDA-core path */
 
 /* Per-call generation knobs: mirrors tts.RuntimeGenerateConfig
  * (reference internal/tts/runtime.go:11-31). */
@@ -224,6 +225,15 @@ int ptts_stage_times_get(ptts_engine *e, ptts_stage_times *out, int32_t reset);
  * bytes. */
 int ptts_profile_enable(ptts_engine *e, int32_t on);
 int ptts_profile_report(ptts_engine *e, char *buf, int32_t cap);
+/* Stand-alone C[M,N] = act(A[M,K] x W[N,K]^T + bias) through a chosen kernel
+ * path (0 = auto, 1 = CUDA-core SGEMM/GEMV, 2 = tcgen05 split-bf16): kernel
+ * unit-test hook. */
+int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const float *W, int32_t N,
+                    const float *bias, int32_t act, int32_t path, float *C);
+/* Times one GEMM shape on device data: average microseconds over `reps`
+ * launches (CUDA events on the engine stream).  lda < K = overlapping rows. */
+int ptts_debug_gemm_bench(ptts_engine *e, int32_t M, int32_t K, int32_t N, int32_t lda, int32_t path,
+                          int32_t reps, float *avg_us);
 /* Copies a named internal buffer of the last pass (debug / stage parity). */
 int64_t ptts_debug_fetch(ptts_engine *e, const char *name, float *out,
                          int64_t cap);
