@@ -178,6 +178,161 @@ __global__ void __launch_bounds__(ATT_THREADS)
   attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv);
 }
 
+// Multi-query windowed attention: MQ consecutive rows per CTA share every K/V
+// load (their windows overlap by ctx-1 rows), cutting the L2 traffic of the
+// one-row-per-CTA kernel ~MQ-fold.  Same arithmetic per (query, key) pair.
+constexpr int MQ = 8;
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_window_mq_kernel(const float *qkv, long ldq, float *out, long ldo, int rows, int D,
+                               const int32_t *row_pos, int ctx) {
+  extern __shared__ float smem[];          // scores [MQ][span_cap]
+  __shared__ __align__(16) float qs[MQ][HD];
+  __shared__ float4 pv[8][MQ][16];
+  __shared__ int s_lo[MQ], s_n[MQ];
+  __shared__ float s_inv[MQ];
+  const int tid = threadIdx.x, h = blockIdx.y;
+  const int r0 = blockIdx.x * MQ;
+  const int span_cap = ctx + MQ;
+  if (tid < MQ) {
+    const int r = r0 + tid;
+    int n = 0, lo = r;
+    if (r < rows) {
+      const int pos = row_pos[r];
+      if (pos >= 0) {
+        n = (ctx > 0 && pos + 1 > ctx) ? ctx : pos + 1;
+        lo = r - (n - 1);
+      }
+    }
+    s_lo[tid] = lo;
+    s_n[tid] = n;
+  }
+  for (int i = tid; i < MQ * HD; i += ATT_THREADS) {
+    const int qi = i / HD, d = i % HD;
+    const int r = r0 + qi;
+    qs[qi][d] = r < rows ? qkv[(long)r * ldq + h * HD + d] : 0.0f;
+  }
+  __syncthreads();
+  int lo_min = r0 + MQ, hi = r0 - 1;
+#pragma unroll
+  for (int i = 0; i < MQ; i++)
+    if (s_n[i] > 0) {
+      lo_min = min(lo_min, s_lo[i]);
+      hi = max(hi, r0 + i);
+    }
+  const int span = hi - lo_min + 1; // <= ctx + MQ - 1
+  const float *kbase = qkv + D + h * HD, *vbase = qkv + 2 * D + h * HD;
+  // phase 1: scores[q][jj] for every key row of the tile's span
+  {
+    const int part = tid & 7, kslot = tid >> 3;
+    const int my_lo = s_lo[part], my_hi = r0 + part, my_n = s_n[part];
+    for (int j0 = 0; j0 < span; j0 += 16) {
+      const int jj = j0 + kslot;
+      float sc[MQ];
+#pragma unroll
+      for (int i = 0; i < MQ; i++)
+        sc[i] = 0.0f;
+      if (jj < span) {
+        const float *kp = kbase + (long)(lo_min + jj) * ldq;
+        const float4 a = *reinterpret_cast<const float4 *>(kp + part * 4);
+        const float4 b = *reinterpret_cast<const float4 *>(kp + 32 + part * 4);
+#pragma unroll
+        for (int i = 0; i < MQ; i++) {
+          const float4 q0 = *reinterpret_cast<const float4 *>(&qs[i][part * 4]);
+          const float4 q1 = *reinterpret_cast<const float4 *>(&qs[i][32 + part * 4]);
+          float t = q0.x * a.x;
+          t = fmaf(q0.y, a.y, t); t = fmaf(q0.z, a.z, t); t = fmaf(q0.w, a.w, t);
+          t = fmaf(q1.x, b.x, t); t = fmaf(q1.y, b.y, t); t = fmaf(q1.z, b.z, t); t = fmaf(q1.w, b.w, t);
+          sc[i] = t;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MQ; i++) {
+        float t = sc[i];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        sc[i] = t;
+      }
+      if (jj < span) {
+        // lane `part` publishes the score of query `part`
+        float mine = 0.0f;
+#pragma unroll
+        for (int i = 0; i < MQ; i++)
+          if (i == part)
+            mine = sc[i];
+        const int j = lo_min + jj;
+        const bool ok = my_n > 0 && j >= my_lo && j <= my_hi;
+        smem[part * span_cap + jj] = ok ? mine * 0.125f : -INFINITY;
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: per-query max / exp / sum (one warp handles MQ/4 queries)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int qi = warp; qi < MQ; qi += ATT_THREADS / 32) {
+      float *sq = smem + qi * span_cap;
+      float m = -INFINITY;
+      for (int jj = lane; jj < span; jj += 32)
+        m = fmaxf(m, sq[jj]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.0f;
+      for (int jj = lane; jj < span; jj += 32) {
+        const float v = sq[jj];
+        const float e = v == -INFINITY ? 0.0f : expf(v - m);
+        sq[jj] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0)
+        s_inv[qi] = sum > 0.0f ? 1.0f / sum : 0.0f;
+    }
+  }
+  __syncthreads();
+  // phase 3: out[q] = sum_j p[q][j] v_j ; V row loaded once for all MQ queries
+  {
+    const int c4 = tid & 15, grp = tid >> 4;
+    float4 acc[MQ];
+#pragma unroll
+    for (int i = 0; i < MQ; i++)
+      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jj = grp; jj < span; jj += 8) {
+      const float4 v = *reinterpret_cast<const float4 *>(vbase + (long)(lo_min + jj) * ldq + c4 * 4);
+#pragma unroll
+      for (int i = 0; i < MQ; i++) {
+        const float w = smem[i * span_cap + jj] * s_inv[i];
+        if (w != 0.0f) { // masked keys are skipped, never multiplied (attention.go:403-406)
+          acc[i].x = fmaf(w, v.x, acc[i].x);
+          acc[i].y = fmaf(w, v.y, acc[i].y);
+          acc[i].z = fmaf(w, v.z, acc[i].z);
+          acc[i].w = fmaf(w, v.w, acc[i].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MQ; i++)
+      pv[grp][i][c4] = acc[i];
+  }
+  __syncthreads();
+  {
+    const int qi = tid >> 4, c4 = tid & 15; // 8 queries x 16 float4 columns = 128 threads
+    const int r = r0 + qi;
+    if (r < rows) {
+      float4 t = pv[0][qi][c4];
+#pragma unroll
+      for (int g2 = 1; g2 < 8; g2++) {
+        const float4 u = pv[g2][qi][c4];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      *reinterpret_cast<float4 *>(out + (long)r * ldo + h * HD + c4 * 4) = t;
+    }
+  }
+}
+
 int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
                     const int32_t *row_slot, const int32_t *row_pos,
                     const KvGeom &kv, int layer, int max_keys, cudaStream_t st) {
@@ -195,6 +350,12 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      cudaStream_t st) {
   if (rows <= 0)
     return 0;
+  if (ctx > 0 && ctx <= 1024) {
+    dim3 grid((rows + MQ - 1) / MQ, n_heads);
+    size_t sm = sizeof(float) * (size_t)MQ * (ctx + MQ);
+    attention_window_mq_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, rows, D, row_pos, ctx);
+    return 1;
+  }
   dim3 grid(rows, n_heads);
   int mk = ctx > 0 ? ctx : 8192;
   size_t sm = sizeof(float) * (size_t)((mk + 15) / 16 * 16);

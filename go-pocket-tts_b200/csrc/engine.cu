@@ -42,6 +42,7 @@ int Engine::create(const ptts_config *c) {
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: device %d out of range [0,%d)", cfg.device, ndev);
   device = cfg.device;
   tc_on = !(cfg.flags & PTTS_ENGINE_NO_TENSOR_CORES) && !getenv("PTTS_NO_TC");
+  graphs_on = !(cfg.flags & PTTS_ENGINE_NO_GRAPHS) && !getenv("PTTS_NO_GRAPHS");
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -70,6 +71,9 @@ Engine::~Engine() {
     cudaFree(p);
   for (TcWeight *t : tc_owned)
     delete t;
+  for (auto &kv : step_graphs)
+    if (kv.second.exec)
+      cudaGraphExecDestroy(kv.second.exec);
   auto fh = [](void *p) {
     if (p)
       cudaFreeHost(p);
@@ -809,11 +813,13 @@ int Engine::finalize() {
   CUDA_TRY(cudaMemset(d_pagetab, 0, h_pagetab.size() * sizeof(int32_t)));
   kvg.pool = kv_pool; kvg.pagetab = d_pagetab; kvg.max_pages = max_pages;
   kvg.page_tokens = page_tokens; kvg.n_layers = L; kvg.n_heads = H; kvg.head_dim = Dh;
-  if ((rc = dmalloc((void **)&d_hist, (size_t)max_batch * (max_frames + 1) * ldim * sizeof(float)))) return rc;
-  if ((rc = dmalloc((void **)&d_noise, (size_t)max_batch * max_frames * ldim * sizeof(float)))) return rc;
+  if ((rc = dmalloc((void **)&d_hist, (size_t)(max_batch + 1) * (max_frames + 1) * ldim * sizeof(float)))) return rc;
+  if ((rc = dmalloc((void **)&d_noise, (size_t)(max_batch + 1) * max_frames * ldim * sizeof(float)))) return rc;
+  CUDA_TRY(cudaMemset(d_noise, 0, (size_t)(max_batch + 1) * max_frames * ldim * sizeof(float)));
   {
     std::vector<float> nanrow((size_t)ldim, NAN);
-    for (int s = 0; s < max_batch; s++)
+    CUDA_TRY(cudaMemset(d_hist, 0, (size_t)(max_batch + 1) * (max_frames + 1) * ldim * sizeof(float)));
+    for (int s = 0; s <= max_batch; s++)
       CUDA_TRY(cudaMemcpy(d_hist + (size_t)s * (max_frames + 1) * ldim, nanrow.data(),
                           ldim * sizeof(float), cudaMemcpyHostToDevice));
   }
@@ -1215,7 +1221,37 @@ int Engine::flow_head(int B, int lsd_steps) {
   return PTTS_OK;
 }
 
-// One AR frame for B sequences (flow_lm.go:238-299).
+// The device work of one AR frame for Bp rows (flow_lm.go:238-299): input
+// gather / NaN->BOS / input_linear, 6 transformer layers, flow head, scatter of the
+// new latent into the per-slot history.  Only fixed device pointers are used, so
+// the sequence can be captured into a CUDA graph.
+int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise,
+                      bool timed) {
+  int64_t &nl = times.kernel_launches;
+  if (gather_frames)
+    nl += gather_rows(d_hist, d_off_a, fh_frames, Bp, ldim, st);
+  if (gather_noise)
+    nl += gather_rows(d_noise, d_off_c, fh_noise, Bp, ldim, st);
+  nl += nan_to_bos(fh_frames, bos, fh_in, Bp, ldim, st);
+  {
+    GemmArgs g;
+    g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = Bp; g.N = D; g.K = ldim;
+    g.epi.bias = input_linear.b; g.epi.C = x; g.epi.ldc = D;
+    nl += pgemm(g);
+  }
+  int rc = flow_forward(Bp, max_keys, false);
+  if (rc)
+    return rc;
+  if (timed)
+    cudaEventRecord(ev[3], st);
+  rc = flow_head(Bp, lsd_steps);
+  if (rc)
+    return rc;
+  nl += scatter_rows(fh_cur, d_hist, d_off_b, Bp, ldim, st);
+  return PTTS_OK;
+}
+
+// One AR frame for B sequences.
 //   frames_in_host: [B,ldim] or null (feed back hist[slot][frames]);
 //   noise_host:     [B,ldim] or null (use d_noise[slot][frames]).
 int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
@@ -1228,6 +1264,12 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: step batch %d exceeds max_batch %d", B, max_batch);
   if (lsd_steps <= 0)
     PTTS_FAIL(PTTS_EINVAL, "native: lsd decode steps must be >0");
+  // rows are padded to a bucket so a handful of graphs covers every batch size;
+  // pad rows have position -1 (skipped by RoPE/KV append/attention) and read /
+  // write the dummy slot max_batch.
+  int Bp = B <= 8 ? B : ((B + 15) / 16) * 16;
+  if (Bp > max_batch)
+    Bp = max_batch;
   int max_keys = 0;
   for (int i = 0; i < B; i++) {
     Seq *s = seqs[i];
@@ -1243,38 +1285,75 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     if (s->kv_len + 1 > max_keys)
       max_keys = s->kv_len + 1;
   }
-  int64_t &nl = times.kernel_launches;
+  for (int i = B; i < Bp; i++) {
+    h_row_slot[i] = 0;
+    h_row_pos[i] = -1;
+    h_off_a[i] = (int64_t)max_batch * (max_frames + 1) * ldim;
+    h_off_b[i] = ((int64_t)max_batch * (max_frames + 1) + 1) * ldim;
+    h_off_c[i] = (int64_t)max_batch * max_frames * ldim;
+  }
   cudaEventRecord(ev[2], st);
-  CUDA_TRY(cudaMemcpyAsync(d_row_slot, h_row_slot, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_row_pos, h_row_pos, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_off_b, h_off_b, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_row_slot, h_row_slot, (size_t)Bp * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_row_pos, h_row_pos, (size_t)Bp * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_off_b, h_off_b, (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
   if (frames_in_host) {
+    if (Bp > B)
+      CUDA_TRY(cudaMemsetAsync(fh_frames, 0, (size_t)Bp * ldim * 4, st));
     CUDA_TRY(cudaMemcpyAsync(fh_frames, frames_in_host, (size_t)B * ldim * 4, cudaMemcpyHostToDevice, st));
   } else {
-    CUDA_TRY(cudaMemcpyAsync(d_off_a, h_off_a, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    nl += gather_rows(d_hist, d_off_a, fh_frames, B, ldim, st);
+    CUDA_TRY(cudaMemcpyAsync(d_off_a, h_off_a, (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
   }
   if (noise_host) {
+    if (Bp > B)
+      CUDA_TRY(cudaMemsetAsync(fh_noise, 0, (size_t)Bp * ldim * 4, st));
     CUDA_TRY(cudaMemcpyAsync(fh_noise, noise_host, (size_t)B * ldim * 4, cudaMemcpyHostToDevice, st));
   } else {
-    CUDA_TRY(cudaMemcpyAsync(d_off_c, h_off_c, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    nl += gather_rows(d_noise, d_off_c, fh_noise, B, ldim, st);
+    CUDA_TRY(cudaMemcpyAsync(d_off_c, h_off_c, (size_t)Bp * 8, cudaMemcpyHostToDevice, st));
   }
-  nl += nan_to_bos(fh_frames, bos, fh_in, B, ldim, st);
-  {
-    GemmArgs g;
-    g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = B; g.N = D; g.K = ldim;
-    g.epi.bias = input_linear.b; g.epi.C = x; g.epi.ldc = D;
-    nl += pgemm(g);
-  }
-  int rc = flow_forward(B, max_keys, false);
+  float *tv = nullptr;
+  int rc = get_tvec(lsd_steps, &tv); // uploads on first use: must not happen inside a capture
   if (rc)
     return rc;
-  cudaEventRecord(ev[3], st);
-  rc = flow_head(B, lsd_steps);
-  if (rc)
-    return rc;
-  nl += scatter_rows(fh_cur, d_hist, d_off_b, B, ldim, st);
+  const bool gf = frames_in_host == nullptr, gn = noise_host == nullptr;
+  bool timed = true;
+  if (graphs_on && !prof_on) {
+    const uint64_t key = ((uint64_t)Bp << 32) | ((uint64_t)lsd_steps << 8) | (gf ? 2u : 0u) | (gn ? 1u : 0u);
+    StepGraph &sg = step_graphs[key];
+    sg.uses++;
+    if (sg.exec) {
+      CUDA_TRY(cudaGraphLaunch(sg.exec, st));
+      times.kernel_launches += sg.launches;
+      timed = false;
+    } else if (sg.uses >= 2) {
+      const int64_t before = times.kernel_launches;
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      // attention smem is sized for the per-sequence KV cap so one graph serves any length
+      rc = step_body(Bp, cfg.max_seq_tokens, lsd_steps, gf, gn, false);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc)
+        return rc;
+      if (ce != cudaSuccess)
+        PTTS_FAIL(PTTS_ECUDA, "cuda: graph capture of the AR step failed: %s", cudaGetErrorString(ce));
+      sg.launches = times.kernel_launches - before;
+      ce = cudaGraphInstantiate(&sg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        sg.exec = nullptr;
+        PTTS_FAIL(PTTS_ECUDA, "cuda: graph instantiate failed: %s", cudaGetErrorString(ce));
+      }
+      CUDA_TRY(cudaGraphLaunch(sg.exec, st));
+      timed = false;
+    } else {
+      rc = step_body(Bp, max_keys, lsd_steps, gf, gn, true);
+      if (rc)
+        return rc;
+    }
+  } else {
+    rc = step_body(Bp, max_keys, lsd_steps, gf, gn, true);
+    if (rc)
+      return rc;
+  }
   cudaEventRecord(ev[4], st);
   CUDA_TRY(cudaMemcpyAsync(h_eos, fh_eos, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (lat_out_host)
@@ -1293,8 +1372,10 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[2], ev[4]);
   times.step_ms += ms;
-  cudaEventElapsedTime(&ms, ev[3], ev[4]);
-  times.flow_head_ms += ms;
+  if (timed) {
+    cudaEventElapsedTime(&ms, ev[3], ev[4]);
+    times.flow_head_ms += ms;
+  }
   times.step_rows += B;
   times.steps += 1;
   debug_bufs["last_hidden"] = {fh_last, (size_t)B * D};

@@ -220,6 +220,17 @@ struct Engine {
               const std::vector<int> &ntok, const std::vector<const float *> &voice,
               const std::vector<int> &nvoice);
   int import_voice_kv(Seq *s, const ptts_voice_kv *vk);
+  // CUDA-graph replay of the step body, keyed by (padded rows, lsd steps, input
+  // sources); the first use of a key runs eagerly (also configures kernels),
+  // the second captures, later ones replay.
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+    int uses = 0;
+  };
+  bool graphs_on = true;
+  std::map<uint64_t, StepGraph> step_graphs;
+  int step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise, bool timed);
   int step(const std::vector<Seq *> &seqs, const float *frames_in_host,
            const float *noise_host, int lsd_steps, float *lat_out_host,
            float *eos_out_host);
