@@ -262,6 +262,10 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         info = rt.info
+        shapes = {k[6:]: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                          "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["ms"] else 0.0}
+                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if k.startswith("shape/")}
+        prof = {k: v for k, v in prof.items() if not k.startswith("shape/")}
         classes = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
         tot_ms = sum(v["ms"] for _, v in classes) or 1.0
         kc = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share_of_profiled": round(v["ms"] / tot_ms, 4),
@@ -298,7 +302,7 @@ def main():
                     "d2h_bytes_per_step": int(samples2 * 4 / max(args.steps, 1))},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": roofline,
-            "kernel_classes": kc,
+            "kernel_classes": kc, "gemm_shapes": shapes,
             "stage_ms_rank0": {k: round(st[k], 2) for k in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")},
             "mean_batch_occupancy": st["step_rows"] / max(st["steps"], 1),
             "steps_per_s_rank0": st["steps"] / (ms / 1e3),

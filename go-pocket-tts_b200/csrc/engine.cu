@@ -128,24 +128,40 @@ void Engine::prof_begin(cudaEvent_t *a, cudaEvent_t *b) {
   }
   cudaEventRecord(*a, st);
 }
-void Engine::prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes) {
+void Engine::prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes,
+                      const char *cls2) {
   cudaEventRecord(b, st);
-  prof_pending.push_back(ProfRec{a, b, cls, flops, bytes});
+  prof_pending.push_back(ProfRec{a, b, cls, flops, bytes, cls2 ? cls2 : ""});
 }
 void Engine::prof_collect() {
   for (auto &r : prof_pending) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-      ProfAcc &acc = prof_acc[r.cls];
-      acc.launches++;
-      acc.ms += ms;
-      acc.flops += r.flops;
-      acc.bytes += r.bytes;
+      for (const std::string *c : {&r.cls, &r.cls2}) {
+        if (c->empty())
+          continue;
+        ProfAcc &acc = prof_acc[*c];
+        acc.launches++;
+        acc.ms += ms;
+        acc.flops += r.flops;
+        acc.bytes += r.bytes;
+      }
     }
     prof_pool.push_back({r.a, r.b});
   }
   prof_pending.clear();
 }
+// Launches `call` (returns the launch count), timed as class `cls` when profiling.
+#define PK(cls, flops, bytes, call)                                            \
+  do {                                                                         \
+    if (prof_on) {                                                             \
+      cudaEvent_t _a, _b;                                                      \
+      prof_begin(&_a, &_b);                                                    \
+      nl += (call);                                                            \
+      prof_end(_a, _b, cls, (double)(flops), (double)(bytes));                 \
+    } else                                                                     \
+      nl += (call);                                                            \
+  } while (0)
 static inline uint16_t f32_to_bf16_rn(float x) {
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -213,8 +229,11 @@ int Engine::pgemm(const GemmArgs &g0) {
   }
   if (prof_on) {
     double kk = g.K < g.lda ? g.K : g.lda; // overlapping conv rows: unique A bytes
+    // second key: per weight shape ("shape/..." entries are a breakdown, not classes)
+    char shp[96];
+    snprintf(shp, sizeof shp, "shape/N%d_K%d_lda%ld_%s", g.N, g.K, g.lda, g.M <= 1024 ? "skinny" : "wide");
     prof_end(a, b, variant, 2.0 * g.M * g.N * g.K,
-             4.0 * ((double)g.N * g.K + (double)g.M * kk + (double)g.M * g.N));
+             4.0 * ((double)g.N * g.K + (double)g.M * kk + (double)g.M * g.N), shp);
   }
   return n;
 }
@@ -1033,12 +1052,12 @@ int Engine::flow_forward(int R, int max_keys, bool) {
       prof_keys += h_row_pos[r] + 1;
   for (int l = 0; l < L; l++) {
     DTLayer &ly = fl[l];
-    nl += layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st);
+    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st));
     GemmArgs g;
     g.A = nrm; g.lda = D; g.W = ly.in_proj.w; g.ldw = D; g.M = R; g.N = 3 * D; g.K = D;
     g.epi.C = qkv; g.epi.ldc = 3 * D;
     nl += pgemm(g);
-    nl += rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st);
+    PK("rope_kv_append", 0, 0, rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st));
     if (prof_on) {
       cudaEvent_t a, b;
       prof_begin(&a, &b);
@@ -1050,7 +1069,7 @@ int Engine::flow_forward(int R, int max_keys, bool) {
     o.A = att; o.lda = D; o.W = ly.out_proj.w; o.ldw = D; o.M = R; o.N = D; o.K = D;
     o.epi.residual = x; o.epi.ldr = D; o.epi.C = x; o.epi.ldc = D;
     nl += pgemm(o);
-    nl += layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st);
+    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st));
     GemmArgs f1;
     f1.A = nrm; f1.lda = D; f1.W = ly.l1.w; f1.ldw = D; f1.M = R; f1.N = F; f1.K = D;
     f1.epi.act = ACT_GELU; f1.epi.C = ff; f1.epi.ldc = F;
@@ -1170,8 +1189,8 @@ int Engine::flow_head(int B, int lsd_steps) {
   int rc = get_tvec(lsd_steps, &tvec);
   if (rc)
     return rc;
-  nl += layernorm(x, D, fh_last, D, B, D, out_norm.w, out_norm.b, out_norm.eps, nullptr, nullptr, 0, st);
-  nl += rowdot(fh_last, D, out_eos_lin.w, out_eos_bias, B, D, fh_eos, st);
+  PK("layernorm", 0, 0, layernorm(x, D, fh_last, D, B, D, out_norm.w, out_norm.b, out_norm.eps, nullptr, nullptr, 0, st));
+  PK("rowdot", 0, 0, rowdot(fh_last, D, out_eos_lin.w, out_eos_bias, B, D, fh_eos, st));
   {
     GemmArgs g;
     g.A = fh_last; g.lda = D; g.W = cond_embed.w; g.ldw = D; g.M = B; g.N = C; g.K = D;
@@ -1182,7 +1201,7 @@ int Engine::flow_head(int B, int lsd_steps) {
   const float inv = 1.0f / (float)lsd_steps;
   const int hid = rb[0].mlp0.out;
   for (int i = 0; i < lsd_steps; i++) {
-    nl += add_vec_silu(fh_cproj, tvec + (size_t)i * C, fh_sy, B, C, st);
+    PK("elementwise", 0, 0, add_vec_silu(fh_cproj, tvec + (size_t)i * C, fh_sy, B, C, st));
     {
       GemmArgs g;
       g.A = fh_sy; g.lda = C; g.W = ada_all.w; g.ldw = C; g.M = B; g.N = ada_n; g.K = C;
@@ -1197,8 +1216,8 @@ int Engine::flow_head(int B, int lsd_steps) {
     }
     for (int b = 0; b < depth; b++) {
       const float *shift = fh_ada + (size_t)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
-      nl += layernorm(fh_x, C, fh_h, C, B, C, rb[b].in_ln.w, rb[b].in_ln.b, rb[b].in_ln.eps,
-                      scale, shift, ada_n, st);
+      PK("layernorm", 0, 0, layernorm(fh_x, C, fh_h, C, B, C, rb[b].in_ln.w, rb[b].in_ln.b, rb[b].in_ln.eps,
+                      scale, shift, ada_n, st));
       GemmArgs g0;
       g0.A = fh_h; g0.lda = C; g0.W = rb[b].mlp0.w; g0.ldw = C; g0.M = B; g0.N = hid; g0.K = C;
       g0.epi.bias = rb[b].mlp0.b; g0.epi.act = ACT_SILU; g0.epi.C = fh_h2; g0.epi.ldc = hid;
@@ -1210,7 +1229,7 @@ int Engine::flow_head(int B, int lsd_steps) {
       nl += pgemm(g2);
     }
     const float *fshift = fh_ada + (size_t)depth * 3 * C, *fscale = fshift + C;
-    nl += layernorm(fh_x, C, fh_h, C, B, C, nullptr, nullptr, 1e-6f, fscale, fshift, ada_n, st);
+    PK("layernorm", 0, 0, layernorm(fh_x, C, fh_h, C, B, C, nullptr, nullptr, 1e-6f, fscale, fshift, ada_n, st));
     GemmArgs gf;
     gf.A = fh_h; gf.lda = C; gf.W = final_linear.w; gf.ldw = C; gf.M = B; gf.N = ldim; gf.K = C;
     gf.epi.bias = final_linear.b; gf.epi.alpha = inv;
@@ -1229,10 +1248,10 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
                       bool timed) {
   int64_t &nl = times.kernel_launches;
   if (gather_frames)
-    nl += gather_rows(d_hist, d_off_a, fh_frames, Bp, ldim, st);
+    PK("gather_scatter", 0, 0, gather_rows(d_hist, d_off_a, fh_frames, Bp, ldim, st));
   if (gather_noise)
-    nl += gather_rows(d_noise, d_off_c, fh_noise, Bp, ldim, st);
-  nl += nan_to_bos(fh_frames, bos, fh_in, Bp, ldim, st);
+    PK("gather_scatter", 0, 0, gather_rows(d_noise, d_off_c, fh_noise, Bp, ldim, st));
+  PK("elementwise", 0, 0, nan_to_bos(fh_frames, bos, fh_in, Bp, ldim, st));
   {
     GemmArgs g;
     g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = Bp; g.N = D; g.K = ldim;
@@ -1247,7 +1266,7 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
   rc = flow_head(Bp, lsd_steps);
   if (rc)
     return rc;
-  nl += scatter_rows(fh_cur, d_hist, d_off_b, Bp, ldim, st);
+  PK("gather_scatter", 0, 0, scatter_rows(fh_cur, d_hist, d_off_b, Bp, ldim, st));
   return PTTS_OK;
 }
 
@@ -1419,16 +1438,16 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     g.epi.bias = proj.b; g.epi.C = m_lat; g.epi.ldc = Md;
     nl += pgemm(g);
   }
-  nl += upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st);
+  PK("upsample_depthwise", 0, 0, upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st));
   // decoder transformer (mimi.go:245-441)
   for (int l = 0; l < ML; l++) {
     DTLayer &ly = ml[l];
-    nl += layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st);
+    PK("layernorm", 0, 0, layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st));
     GemmArgs g;
     g.A = m_nrm; g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
     g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
     nl += pgemm(g);
-    nl += rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st);
+    PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st));
     if (prof_on) {
       double keys = 0;
       for (int r = 0; r < Rb; r++)
@@ -1444,7 +1463,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     o.A = m_att; o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
     o.epi.colscale = ly.ls1; o.epi.residual = m_x; o.epi.ldr = Md; o.epi.C = m_x; o.epi.ldc = Md;
     nl += pgemm(o);
-    nl += layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st);
+    PK("layernorm", 0, 0, layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st));
     GemmArgs f1;
     f1.A = m_nrm; f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
     f1.epi.act = ACT_GELU; f1.epi.C = m_ff; f1.epi.ldc = MF;
@@ -1482,7 +1501,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     conv_gemm(res2[s], m_he[s], rows, div, nullptr, m_ye[s], m_y[s]); // elu(x + conv2(..))
     cur = m_ye[s];
   }
-  nl += final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, m_pcm, st);
+  PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, m_pcm, st));
   cudaEventRecord(ev[6], st);
   const int spb = div; // samples per base row
   if (d2h) {

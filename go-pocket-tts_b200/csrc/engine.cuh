@@ -179,6 +179,7 @@ struct Engine {
     cudaEvent_t a, b;
     std::string cls;
     double flops, bytes;
+    std::string cls2;
   };
   bool prof_on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
@@ -186,7 +187,8 @@ struct Engine {
   std::map<std::string, ProfAcc> prof_acc;
   int pgemm(const GemmArgs &g);
   void prof_begin(cudaEvent_t *a, cudaEvent_t *b);
-  void prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes);
+  void prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes,
+                const char *cls2 = nullptr);
   void prof_collect(); // after a stream sync
 
   // ---- scheduler ----

@@ -61,7 +61,7 @@ const char *gemm_last_variant();
 // A weight matrix split once into bf16 hi/lo rows [2N, K] plus its TMA
 // descriptors (opaque 128-byte CUtensorMap blobs, 64-byte aligned).
 struct alignas(64) TcWeight {
-  unsigned char map32[128], map64[128], map128[128];
+  unsigned char map32[128], map64[128], map128[128], map256[128];
   const void *d_split = nullptr;
   int N = 0, K = 0;
 };

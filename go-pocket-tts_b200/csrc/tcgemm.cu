@@ -29,6 +29,9 @@
 #include "gemm_epi.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace ptts {
 
@@ -37,7 +40,8 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64; // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_CONV_THREADS = 256;
-constexpr int TC_THREADS = 64 + TC_CONV_THREADS;
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_THREADS = 64 + TC_CONV_THREADS + TC_EPI_WARPS * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -57,7 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 2000;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
@@ -115,35 +119,144 @@ __device__ __forceinline__ void split8(const float4 &u, const float4 &v, uint4 &
   split2(v.z, v.w, hi.w, lo.w);
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+// Fused epilogue of one 32x32 accumulator chunk held in a warp's staging buffer: lane
+// (rsub, cf) owns columns n..n+3 of rows rsub, rsub+4, ... (8 rows).  `rows` bit j = row
+// in range, bit 8+j = row live (not masked).  FULL: every row in range, no checks.
+// OUT: 1 = C, 2 = C2 (= elu), 3 = both.  Rare operands (mul, alpha) only when GENERIC.
+template <int ACT, int OUT, bool FULL, bool GENERIC>
+__device__ __forceinline__ void epi_rows(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
+                                         uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
+                                         bool have_res) {
+  float *cp = (OUT & 1) ? e.C + m_first * e.ldc + n : nullptr;
+  float *cp2 = (OUT & 2) ? e.C2 + m_first * e.ldc2 + n : nullptr;
+  const float *mp = GENERIC && e.mul ? e.mul + m_first * e.ldmul + n : nullptr;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (FULL || ((rows >> j) & 1)) {
+      float4 o = lds128(stg_addr + j * 4 * stg_ld_bytes);
+      o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+      if (ACT != ACT_NONE) {
+        o.x = act_apply(o.x, ACT); o.y = act_apply(o.y, ACT);
+        o.z = act_apply(o.z, ACT); o.w = act_apply(o.w, ACT);
+      }
+      o.x *= cs4.x; o.y *= cs4.y; o.z *= cs4.z; o.w *= cs4.w;
+      if (GENERIC) {
+        if (mp) {
+          const float4 t = *reinterpret_cast<const float4 *>(mp + (long)j * 4 * e.ldmul);
+          o.x *= t.x; o.y *= t.y; o.z *= t.z; o.w *= t.w;
+        }
+        o.x *= e.alpha; o.y *= e.alpha; o.z *= e.alpha; o.w *= e.alpha;
+      }
+      if (have_res) {
+        o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w;
+      }
+      if (!((rows >> (8 + j)) & 1))
+        o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (OUT & 1)
+        *reinterpret_cast<float4 *>(cp + (long)j * 4 * e.ldc) = o;
+      if (OUT & 2) {
+        float4 u;
+        u.x = act_apply(o.x, ACT_ELU);
+        u.y = act_apply(o.y, ACT_ELU);
+        u.z = act_apply(o.z, ACT_ELU);
+        u.w = act_apply(o.w, ACT_ELU);
+        *reinterpret_cast<float4 *>(cp2 + (long)j * 4 * e.ldc2) = u;
+      }
+    }
+  }
+}
+template <int ACT, int OUT>
+__device__ __forceinline__ void epi_rows_sel(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
+                                             uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
+                                             bool have_res, bool full, bool generic) {
+  if (generic)
+    epi_rows<ACT, OUT, false, true>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
+  else if (full)
+    epi_rows<ACT, OUT, true, false>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
+  else
+    epi_rows<ACT, OUT, false, false>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
+}
+template <int ACT>
+__device__ __forceinline__ void epi_rows_out(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
+                                             uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
+                                             bool have_res, bool full, bool generic) {
+  if (e.C && e.C2)
+    epi_rows_sel<ACT, 3>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+  else if (e.C2)
+    epi_rows_sel<ACT, 2>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+  else if (e.C)
+    epi_rows_sel<ACT, 1>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+}
+
+int tc_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_TILE = TC_BM * TC_BK * 2; // bytes per bf16 A tile (16 KB)
   static constexpr int W_TILE = BN * TC_BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STG_LD = 36;                 // staging row stride (floats): conflict-free v4 both ways
+  static constexpr int STG_WARP = 32 * STG_LD * 4;  // one 32x32 fp32 chunk per epilogue warp
+  static constexpr int BYTES = STAGES * STAGE + TC_EPI_WARPS * STG_WARP + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Work decomposition shared by every warp role: item i -> (m tile, n tile, k split).
+// Splits of one tile are adjacent items so they run at the same time.
+struct TcItems {
+  long total;
+  int ntn, S, kb_per, nkb_all;
+  __device__ __forceinline__ void decode(long i, int &m0, int &n0, int &kb_begin, int &nkb, int &z, int &tile,
+                                         int bn) const {
+    z = (int)(i % S);
+    tile = i / S;
+    const int nt = (int)(tile % ntn);
+    const int mt = (int)(tile / ntn);
+    m0 = mt * TC_BM;
+    n0 = nt * bn;
+    kb_begin = z * kb_per;
+    nkb = min(nkb_all - kb_begin, kb_per);
+  }
+};
+
+// Persistent, warp-specialised kernel: each CTA walks items blockIdx.x, +gridDim.x, ...
+// The accumulator is double-buffered in TMEM so the epilogue of item i overlaps the
+// main loop of item i+1; the smem operand ring runs straight through item boundaries.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    tc_gemm_kernel(const __grid_constant__ CUtensorMap wmap, GemmArgs g, int n_rows_hi) {
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap wmap, GemmArgs g, int n_rows_hi, TcItems items) {
   using SM = TcSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * SM::STAGE);
+  uint8_t *stg_base = smem + STAGES * SM::STAGE;
+  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + TC_EPI_WARPS * SM::STG_WARP);
   uint64_t *empty = full + STAGES;
-  uint64_t *acc_full = empty + STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+  uint64_t *acc_full = empty + STAGES; // [2]
+  uint64_t *acc_empty = acc_full + 2;  // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int M = g.M, N = g.N, K = g.K;
-  const int nkb_all = (K + TC_BK - 1) / TC_BK;
-  const int S = gridDim.z;
-  const int kb_per = (nkb_all + S - 1) / S;
-  const int kb_begin = blockIdx.z * kb_per;
-  const int nkb = max(0, min(nkb_all - kb_begin, kb_per)); // k-blocks of this split (host keeps it > 0)
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  __shared__ int s_last;
+  const int S = items.S;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
@@ -151,7 +264,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&full[s], TC_CONV_THREADS + 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], TC_EPI_WARPS * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -166,56 +282,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer: W hi + lo tiles of this k-block =====
+    // ===== TMA producer: W hi + lo tiles of every k-block of every item =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES)
-          mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-        uint8_t *st = smem + s * SM::STAGE;
-        mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE);
-        tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], (kb_begin + kb) * TC_BK, n0);
-        tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], (kb_begin + kb) * TC_BK, n_rows_hi + n0);
+      long it = 0;
+      for (long i = blockIdx.x; i < items.total; i += gridDim.x) {
+        int m0, n0, kb_begin, nkb, z;
+        int tile;
+        items.decode(i, m0, n0, kb_begin, nkb, z, tile, BN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = (int)(it % STAGES);
+          if (it >= STAGES)
+            mbar_wait(&empty[s], (uint32_t)((it / STAGES) - 1) & 1);
+          uint8_t *st = smem + s * SM::STAGE;
+          mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE);
+          tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], (kb_begin + kb) * TC_BK, n0);
+          tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], (kb_begin + kb) * TC_BK, n_rows_hi + n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        mbar_wait(&full[s], (kb / STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(smem + s * SM::STAGE);
-        const uint32_t a_lo = a_hi + SM::A_TILE;
-        const uint32_t w_hi = a_hi + 2 * SM::A_TILE;
-        const uint32_t w_lo = w_hi + SM::W_TILE;
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; k++) {
-          const uint32_t ko = k * 32; // 16 bf16 = 32 bytes along the swizzled row
-          const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
-          const uint64_t dwh = make_smem_desc(w_hi + ko), dwl = make_smem_desc(w_lo + ko);
-          umma_bf16(tmem_base, dal, dwh, idesc, (kb | k) != 0);
-          umma_bf16(tmem_base, dah, dwl, idesc, 1);
-          umma_bf16(tmem_base, dah, dwh, idesc, 1);
+      long it = 0, li = 0;
+      for (long i = blockIdx.x; i < items.total; i += gridDim.x, li++) {
+        int m0, n0, kb_begin, nkb, z;
+        int tile;
+        items.decode(i, m0, n0, kb_begin, nkb, z, tile, BN);
+        const int b = (int)(li & 1);
+        if (li >= 2) { // the epilogue must have drained this accumulator buffer
+          mbar_wait(&acc_empty[b], (uint32_t)((li >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        umma_commit(&empty[s]); // frees the smem stage once these MMAs have read it
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * BN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = (int)(it % STAGES);
+          mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem + s * SM::STAGE);
+          const uint32_t a_lo = a_hi + SM::A_TILE;
+          const uint32_t w_hi = a_hi + 2 * SM::A_TILE;
+          const uint32_t w_lo = w_hi + SM::W_TILE;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; k++) {
+            const uint32_t ko = k * 32; // 16 bf16 = 32 bytes along the swizzled row
+            const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
+            const uint64_t dwh = make_smem_desc(w_hi + ko), dwl = make_smem_desc(w_lo + ko);
+            umma_bf16(tmem_d, dal, dwh, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, dah, dwl, idesc, 1);
+            umma_bf16(tmem_d, dah, dwh, idesc, 1);
+          }
+          umma_commit(&empty[s]); // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&acc_full[b]);
       }
-      umma_commit(acc_full);
     }
-  } else {
+  } else if (warp < 2 + TC_CONV_THREADS / 32) {
     // ===== A converters: fp32 global -> (hi, lo) bf16 swizzled smem =====
     const int ct = threadIdx.x - 64;
-    // Three k-blocks of A stay in flight per thread (3 x 8 float4 registers): a
-    // single outstanding block left the loop bound by L2/HBM latency.
+    // PF k-blocks of A stay in flight per thread, across item boundaries.
     constexpr int PF = 3;
     float4 r[PF][4][2];
-    auto load_kb = [&](int kb, float4(&dst)[4][2]) {
+    struct Cur {
+      long item;
+      int kb, nkb, m0, kb_begin;
+    };
+    auto setup = [&](Cur &c) {
+      if (c.item < items.total) {
+        int n0, z;
+        int tile;
+        items.decode(c.item, c.m0, n0, c.kb_begin, c.nkb, z, tile, BN);
+      } else
+        c.nkb = 0;
+      c.kb = 0;
+    };
+    auto advance = [&](Cur &c) {
+      if (++c.kb >= c.nkb) {
+        c.item += gridDim.x;
+        setup(c);
+      }
+    };
+    auto load_kb = [&](const Cur &c, float4(&dst)[4][2]) {
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         const int idx = p * TC_CONV_THREADS + ct;
-        const int row = idx >> 3, c = idx & 7;
-        const int gm = m0 + row, gk = (kb_begin + kb) * TC_BK + c * 8;
+        const int row = idx >> 3, cc = idx & 7;
+        const int gm = c.m0 + row, gk = (c.kb_begin + c.kb) * TC_BK + cc * 8;
         float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
         if (gm < M) {
           const float *src = g.A + (long)gm * g.lda + gk;
@@ -228,51 +380,83 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         dst[p][1] = v;
       }
     };
-    auto convert_kb = [&](int kb, float4(&src)[4][2]) {
-      const int s = kb % STAGES;
-      if (kb >= STAGES)
-        mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
-      uint8_t *a_hi = smem + s * SM::STAGE, *a_lo = a_hi + SM::A_TILE;
+    Cur lc, cc;
+    lc.item = blockIdx.x;
+    setup(lc);
+    cc = lc;
 #pragma unroll
-      for (int p = 0; p < 4; p++) {
-        const int idx = p * TC_CONV_THREADS + ct;
-        const int row = idx >> 3, c = idx & 7;
-        uint4 hi, lo;
-        split8(src[p][0], src[p][1], hi, lo);
-        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+    for (int j = 0; j < PF; j++) {
+      if (lc.nkb > 0) {
+        load_kb(lc, r[j]);
+        advance(lc);
       }
-      if (kb + PF < nkb)
-        load_kb(kb + PF, src);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes -> tensor-core reads
-      mbar_arrive(&full[s]);
-    };
-#pragma unroll
-    for (int j = 0; j < PF; j++)
-      if (j < nkb)
-        load_kb(j, r[j]);
-    for (int kb0 = 0; kb0 < nkb; kb0 += PF) {
-#pragma unroll
-      for (int j = 0; j < PF; j++)
-        if (kb0 + j < nkb)
-          convert_kb(kb0 + j, r[j]);
     }
-    // ===== epilogue: TMEM -> smem staging (warps 2..5), then all 8 warps run
-    //       the coalesced, vectorised epilogue -> HBM =====
-    constexpr int LDS = BN + 4; // padded staging row stride (floats)
-    if (warp < 6) {
-      mbar_wait(acc_full, 0);
+    long it = 0;
+    while (cc.nkb > 0) {
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        if (cc.nkb > 0) {
+          const int s = (int)(it % STAGES);
+          if (it >= STAGES)
+            mbar_wait(&empty[s], (uint32_t)((it / STAGES) - 1) & 1);
+          uint8_t *a_hi = smem + s * SM::STAGE, *a_lo = a_hi + SM::A_TILE;
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            const int idx = p * TC_CONV_THREADS + ct;
+            const int row = idx >> 3, c8 = idx & 7;
+            uint4 hi, lo;
+            split8(r[j][p][0], r[j][p][1], hi, lo);
+            const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c8 ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+          }
+          if (lc.nkb > 0) {
+            load_kb(lc, r[j]);
+            advance(lc);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes -> tensor-core reads
+          mbar_arrive(&full[s]);
+          advance(cc);
+          it++;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> per-warp smem transpose -> coalesced fused epilogue =====
+    const GemmEpi &e = g.epi;
+    const int q = warp & 3; // TMEM lane quarter this warp may access
+    const uint32_t stg_addr = smem_u32(stg_base + (warp - (2 + TC_CONV_THREADS / 32)) * SM::STG_WARP);
+    const bool generic = e.mul != nullptr || e.alpha != 1.0f;
+    const int et = threadIdx.x - (64 + TC_CONV_THREADS); // 0..127
+    const int rsub = lane >> 3, cf = (lane & 7) * 4;     // coalesced phase: 4 rows x 32 columns per instruction
+    uint32_t li = 0;
+    for (int i = blockIdx.x; i < items.total; i += gridDim.x, li++) {
+      int m0, n0, kb_begin, nkb, z;
+      int tile;
+      items.decode(i, m0, n0, kb_begin, nkb, z, tile, BN);
+      const int b = (int)(li & 1);
+      // row state of the 8 rows this lane touches: bit j = in range, bit 8+j = live (not masked)
+      uint32_t rows = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int m = m0 + q * 32 + j * 4 + rsub;
+        if (m < M) {
+          rows |= 1u << j;
+          if (!e.rowmask || e.rowmask[m / e.mask_div])
+            rows |= 0x100u << j;
+        }
+      }
+      const bool full = __all_sync(0xffffffffu, (rows & 0xFFu) == 0xFFu);
+      float *tile_ws = g.ws + ((long)tile * S) * (long)(TC_BM * BN);
+      float *mine = tile_ws + (long)z * TC_BM * BN;
+      mbar_wait(&acc_full[b], (uint32_t)(li >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // One accumulator row per thread -> padded smem tile.  (Writing C straight
-      // from the row-per-thread registers scattered every store over 32 rows.)
-      // The operand stages are free once acc_full fired.
-      const int q = warp & 3; // TMEM lane quarter this warp may access
-      float *stg = reinterpret_cast<float *>(smem) + (size_t)q * 32 * LDS;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n = n0 + c0 + cf;
+        const bool nok = n < N;
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
@@ -283,77 +467,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr)
             : "memory");
+        // operands of this chunk that depend on the column only / the residual rows are
+        // requested while the accumulator load is in flight
+        float4 res[8];
+        const bool have_res = (S == 1) && e.residual != nullptr;
+        if (have_res) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int m = m0 + q * 32 + j * 4 + rsub;
+            res[j] = (nok && ((rows >> j) & 1)) ? *reinterpret_cast<const float4 *>(e.residual + (long)m * e.ldr + n)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (S == 1 && nok) {
+          if (e.bias)
+            bias4 = __ldg(reinterpret_cast<const float4 *>(e.bias + n));
+          if (e.colscale)
+            cs4 = __ldg(reinterpret_cast<const float4 *>(e.colscale + n));
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4 *>(stg + (size_t)lane * LDS + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory"); // staging tile complete (warps 2..9)
-    {
-      const GemmEpi &e = g.epi;
-      const float *stile = reinterpret_cast<const float *>(smem);
-      const int w8 = warp - 2; // 0..7: 16 tile rows each
-      // coalesced phase: a warp instruction covers RPI rows x BN columns
-      constexpr int F4 = BN / 4, RPI = 32 / F4;
-      const int rsub = lane / F4, cf = (lane % F4) * 4;
-      const int n = n0 + cf;
-      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-      float *tile_ws = g.ws + ((long)tile * S) * TC_BM * BN;
-      bool do_epilogue = true;
-      if (S > 1) {
-        // split-K: publish the partial tile; the last CTA to arrive sums the
-        // partials in split order (deterministic) and runs the epilogue.
-        float *mine = tile_ws + (long)blockIdx.z * TC_BM * BN;
-#pragma unroll 4
-        for (int r0 = 0; r0 < 16; r0 += RPI) {
-          const int row = w8 * 16 + r0 + rsub;
-          *reinterpret_cast<float4 *>(mine + (long)row * BN + cf) =
-              *reinterpret_cast<const float4 *>(stile + (size_t)row * LDS + cf);
-        }
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
-          const int prev = atomicAdd(g.counters + tile, 1);
-          s_last = (prev == S - 1);
-          if (s_last)
-            g.counters[tile] = 0;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        do_epilogue = s_last != 0;
-        if (do_epilogue)
-          __threadfence();
-      }
-      if (do_epilogue) {
-#pragma unroll 2
-        for (int r0 = 0; r0 < 16; r0 += RPI) {
-          const int row = w8 * 16 + r0 + rsub;
-          const int m = m0 + row;
-          float4 a;
-          if (S == 1) {
-            a = *reinterpret_cast<const float4 *>(stile + (size_t)row * LDS + cf);
-          } else {
-            a = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float *src = tile_ws + (long)row * BN + cf;
-#pragma unroll 4
-            for (int sp = 0; sp < S; sp++) {
-              const float4 u = __ldcg(reinterpret_cast<const float4 *>(src + (long)sp * TC_BM * BN));
-              a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
-            }
+          sts128(stg_addr + (uint32_t)(lane * SM::STG_LD + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const uint32_t rd_addr = stg_addr + (uint32_t)(rsub * SM::STG_LD + cf) * 4;
+        if (S > 1) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int row = j * 4 + rsub;
+            *reinterpret_cast<float4 *>(mine + (long)(q * 32 + row) * BN + c0 + cf) =
+                lds128(rd_addr + j * 4 * SM::STG_LD * 4);
           }
-          if (m < M && n < N) {
-            float4 o = epi_vec4(e, a, m, n);
-            if (e.rowmask && !e.rowmask[m / e.mask_div])
-              o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.C)
-              *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = o;
-            if (e.C2) {
-              float4 u;
-              u.x = act_apply(o.x, ACT_ELU);
-              u.y = act_apply(o.y, ACT_ELU);
-              u.z = act_apply(o.z, ACT_ELU);
-              u.w = act_apply(o.w, ACT_ELU);
-              *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u;
+        } else if (nok) {
+          const long m_first = m0 + q * 32 + rsub;
+          switch (e.act) {
+          case ACT_GELU:
+            epi_rows_out<ACT_GELU>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+            break;
+          case ACT_SILU:
+            epi_rows_out<ACT_SILU>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+            break;
+          case ACT_ELU:
+            epi_rows_out<ACT_ELU>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+            break;
+          default:
+            epi_rows_out<ACT_NONE>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+            break;
+          }
+        }
+        __syncwarp(); // staging is rewritten by the next chunk
+      }
+      // this accumulator buffer may be overwritten by the MMA warp from here on
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acc_empty[b]);
+      if (S > 1) {
+        // split-K: the last CTA to publish its partial tile sums all partials in split
+        // order (deterministic) and runs the epilogue.
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int prev = atomicAdd(g.counters + tile, 1);
+          const int last = (prev == S - 1);
+          if (last)
+            g.counters[tile] = 0;
+          *s_last = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool do_epilogue = *s_last != 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory"); // s_last is rewritten by the next item
+        if (do_epilogue) {
+          __threadfence();
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int n = n0 + c0 + cf;
+#pragma unroll 2
+            for (int j = 0; j < 8; j++) {
+              const int row = q * 32 + j * 4 + rsub;
+              const int m = m0 + row;
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float *src = tile_ws + (long)row * BN + c0 + cf;
+#pragma unroll 4
+              for (int sp = 0; sp < S; sp++) {
+                const float4 u = __ldcg(reinterpret_cast<const float4 *>(src + (long)sp * TC_BM * BN));
+                a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+              }
+              if (m < M && n < N) {
+                float4 o = epi_vec4(e, a, m, n);
+                if (!((rows >> (8 + j)) & 1))
+                  o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.C)
+                  *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = o;
+                if (e.C2) {
+                  float4 u;
+                  u.x = act_apply(o.x, ACT_ELU);
+                  u.y = act_apply(o.y, ACT_ELU);
+                  u.z = act_apply(o.z, ACT_ELU);
+                  u.w = act_apply(o.w, ACT_ELU);
+                  *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u;
+                }
+              }
             }
           }
         }
@@ -384,7 +597,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int BN, int STAGES>
-int launch_tc(const TcWeight &w, const GemmArgs &g, cudaStream_t st) {
+int launch_tc(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -393,23 +606,80 @@ int launch_tc(const TcWeight &w, const GemmArgs &g, cudaStream_t st) {
       return -1;
     configured = true;
   }
-  const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(BN == 128 ? w.map128 : (BN == 64 ? w.map64 : w.map32));
-  dim3 grid((g.N + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, 1);
-  // split-K when the tile grid cannot keep the SMs streaming weights
-  const long tiles = (long)grid.x * grid.y;
-  const int nkb = (g.K + TC_BK - 1) / TC_BK;
-  int S = 1;
-  if (g.ws && g.counters && tiles < 100 && tiles <= g.n_counters && nkb >= 4) {
-    S = (int)((148 + tiles - 1) / tiles);
-    if (S > nkb / 2) S = nkb / 2;
-    if (S > 4) S = 4;
-    while (S > 1 && tiles * S * (long)TC_BM * BN > g.ws_floats) S--;
-    while (S > 1 && (long)((nkb + S - 1) / S) * (S - 1) >= nkb) S--; // every split owns >= 1 k-block
-    if (S < 1) S = 1;
-  }
-  grid.z = S;
-  tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, SM::BYTES, st>>>(*map, g, w.N);
+  const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(
+      BN == 256 ? w.map256 : (BN == 128 ? w.map128 : (BN == 64 ? w.map64 : w.map32)));
+  TcItems it;
+  it.ntn = (g.N + BN - 1) / BN;
+  const long tiles = (long)it.ntn * ((g.M + TC_BM - 1) / TC_BM);
+  it.nkb_all = (g.K + TC_BK - 1) / TC_BK;
+  if (S < 1 || !g.ws || !g.counters || tiles > g.n_counters)
+    S = 1;
+  if (S > it.nkb_all)
+    S = it.nkb_all;
+  while (S > 1 && tiles * S * (long)TC_BM * BN > g.ws_floats)
+    S--;
+  it.kb_per = (it.nkb_all + S - 1) / S;
+  S = (it.nkb_all + it.kb_per - 1) / it.kb_per; // every split owns >= 1 k-block
+  it.S = S;
+  it.total = tiles * S;
+  const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
+  tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, SM::BYTES, st>>>(*map, g, w.N, it);
   return 1;
+}
+
+// Tile width and split-K for one GEMM.  Wide problems (many m tiles) take the widest
+// tile that divides N (fewest A re-reads); skinny ones (the AR step, M <= 512) are
+// bound by what one SM can pull through L2, so the choice minimises the bytes a CTA
+// streams, (128 + BN) * 256 B per k-block, over one wave of CTAs.
+void choose_tile(const GemmArgs &g, int &bn, int &S) {
+  static int force_bn = -1, force_s = 0;
+  if (force_bn < 0) {
+    force_bn = 0;
+    if (const char *f = getenv("PTTS_TC_FORCE"))
+      sscanf(f, "%d,%d", &force_bn, &force_s);
+  }
+  const long mt = (g.M + TC_BM - 1) / TC_BM;
+  const int nkb = (g.K + TC_BK - 1) / TC_BK;
+  const int sms = tc_num_sms();
+  const int cand[4] = {256, 128, 64, 32};
+  if (force_bn > 0) {
+    bn = force_bn;
+    S = force_s > 0 ? force_s : 1;
+    while (bn > 32 && bn / 2 >= g.N)
+      bn /= 2;
+    return;
+  }
+  double best = 1e30;
+  bn = 32;
+  S = 1;
+  for (int c = 0; c < 4; c++) {
+    const int b = cand[c];
+    if (b / 2 >= g.N && b > 32)
+      continue; // more than half the tile would be padding
+    const long ntn = (g.N + b - 1) / b;
+    const long tiles = mt * ntn;
+    const int smax = tiles >= sms ? 1 : 8;
+    for (int s = 1; s <= smax && s <= nkb; s++) {
+      const int kb_per = (nkb + s - 1) / s;
+      if ((long)kb_per * (s - 1) >= nkb)
+        continue;
+      const long items = tiles * s;
+      const long per_cta = (items + sms - 1) / sms; // items a CTA runs back to back
+      // us: operand bytes through L2 at ~65 GB/s per SM, or the MMA issue time, whichever
+      // is larger; + fixed cost per item (pipeline fill, epilogue); + split-K fix-up
+      const double t_mem = (128.0 + b) * 256.0 * kb_per / 65e3;
+      const double t_mma = 128.0 * b * 64.0 * 6.0 * kb_per / 7.0e6; // ~7 TFLOP/s issued per SM
+      double t = (t_mem > t_mma ? t_mem : t_mma) + 1.0 + 128.0 * b * 4.0 * 2.5 / 65e3;
+      if (s > 1)
+        t += 1.5 + 128.0 * b * 4.0 * (1 + s) / 65e3 / (double)s;
+      t = t * per_cta + 3.0;
+      if (t < best) {
+        best = t;
+        bn = b;
+        S = s;
+      }
+    }
+  }
 }
 
 } // namespace
@@ -423,9 +693,9 @@ int tc_weight_init(TcWeight *w, const void *d_split, int N, int K) {
   w->d_split = d_split;
   w->N = N;
   w->K = K;
-  const int boxes[3] = {32, 64, 128};
-  void *maps[3] = {w->map32, w->map64, w->map128};
-  for (int i = 0; i < 3; i++) {
+  const int boxes[4] = {32, 64, 128, 256};
+  void *maps[4] = {w->map32, w->map64, w->map128, w->map256};
+  for (int i = 0; i < 4; i++) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)(2 * (cuuint64_t)N)};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)boxes[i]};
@@ -446,25 +716,22 @@ bool tc_gemm_supported(const GemmArgs &g) {
 }
 
 int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant) {
-  // Narrower N tiles first (more CTAs streaming weights when M is skinny), then a
-  // small split-K; wide tiles when the grid is already large (less A re-reading).
-  const long mt = (g.M + TC_BM - 1) / TC_BM;
-  auto tiles = [&](int bn) { return mt * ((g.N + bn - 1) / bn); };
-  int bn = 128;
-  if (g.N < 128 || tiles(128) < 96)
-    bn = 64;
-  if (g.N < 64 || (bn == 64 && tiles(64) < 96))
-    bn = 32;
-  if (bn == 128) {
+  int bn, S;
+  choose_tile(g, bn, S);
+  switch (bn) {
+  case 256:
+    *variant = "tcgen05_128x256";
+    return launch_tc<256, 2>(w, g, S, st);
+  case 128:
     *variant = "tcgen05_128x128";
-    return launch_tc<128, 3>(w, g, st);
-  }
-  if (bn == 64) {
+    return launch_tc<128, 3>(w, g, S, st);
+  case 64:
     *variant = "tcgen05_128x64";
-    return launch_tc<64, 4>(w, g, st);
+    return launch_tc<64, 4>(w, g, S, st);
+  default:
+    *variant = "tcgen05_128x32";
+    return launch_tc<32, 4>(w, g, S, st);
   }
-  *variant = "tcgen05_128x32";
-  return launch_tc<32, 4>(w, g, st);
 }
 
 } // namespace ptts

@@ -40,7 +40,10 @@ def test_cuda_core_paths(small_rt, M, K, N):
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 128), (128, 1024, 128), (64, 1024, 3072), (200, 512, 10240),
                                    (256, 4096, 1024), (1000, 192, 32), (4097, 768, 128), (333, 3584, 512),
-                                   (129, 32, 64), (2000, 128, 256), (777, 1024, 640), (300, 256, 2048)])
+                                   (129, 32, 64), (2000, 128, 256), (777, 1024, 640), (300, 256, 2048),
+                                   # > 148 tiles: the persistent loop, TMEM double buffering, ring wrap-around
+                                   (40000, 64, 64), (30000, 192, 32), (25000, 256, 256), (21000, 128, 512),
+                                   (512, 1024, 3072), (48, 4096, 1024), (16, 512, 512)])
 def test_tcgen05_split_bf16_path(small_rt, M, K, N):
     A, W, b = _case(M, K, N, M + N + 1)
     _check(small_rt.debug_gemm(A, W, b, act=0, path=2), A, W, b, 0, 4e-5)
