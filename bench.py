@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native-cuda", choices=["native-cuda", "reference"])
     ap.add_argument("--utterances", type=int, default=TOTAL_UTTERANCES // MAX_GPUS, help="per GPU")
-    ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--arch", default="full", choices=["full", "small"])
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -109,7 +109,7 @@ EXPORTS = [
     "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
-    "ptts_debug_gemm", "ptts_debug_gemm_bench",
+    "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force",
 ]
 
 _lib = None
@@ -157,6 +157,7 @@ def lib() -> C.CDLL:
     L.ptts_debug_fetch.argtypes = [vp, C.c_char_p, fp, C.c_int64]
     L.ptts_debug_fetch.restype = C.c_int64
     L.ptts_profile_enable.argtypes = [vp, C.c_int32]
+    L.ptts_debug_tc_force.argtypes = [C.c_int32, C.c_int32]
     L.ptts_debug_gemm_bench.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     L.ptts_debug_gemm.argtypes = [vp, fp, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, C.c_int32, fp]
     L.ptts_profile_report.argtypes = [vp, C.c_char_p, C.c_int32]
@@ -453,6 +454,9 @@ class NativeCudaRuntime:
         _check(self._lib.ptts_debug_gemm(self._h, _fptr(A), A.shape[0], A.shape[1], _fptr(W), W.shape[0],
                                          _fptr(b), act, path, _fptr(out)))
         return out
+
+    def tc_force(self, bn: int = 0, s: int = 0):
+        _check(self._lib.ptts_debug_tc_force(bn, s))
 
     def gemm_bench(self, M: int, K: int, N: int, path: int = 0, reps: int = 20, lda: int = 0) -> float:
         """Average microseconds per launch of one GEMM shape."""

@@ -15,6 +15,7 @@
 // A KV page (16 tokens x 64 floats for one head) is one contiguous 4 KB run, so
 // phase 1 and 3 read whole 128-byte lines.
 #include "kernels.cuh"
+#include "split.cuh"
 #include <math.h>
 
 namespace ptts {
@@ -55,7 +56,8 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
 template <class KeyFn, class ValFn>
 __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp,
                                            ValFn valp, float *out, float *scores,
-                                           float *red, float4 *pv) {
+                                           float *red, float4 *pv, const SplitOut &sp, long sp_row,
+                                           int sp_col) {
   const int tid = threadIdx.x;
   const float scale = 0.125f; // 1/sqrt(64)
   // phase 1
@@ -119,23 +121,31 @@ __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp
       float4 t = pv[g2 * 16 + tid];
       r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
     }
-    *reinterpret_cast<float4 *>(out + tid * 4) = r;
+    if (out)
+      *reinterpret_cast<float4 *>(out + tid * 4) = r;
+    if (sp.hi)
+      split_store4(sp, sp_row, sp_col + tid * 4, r);
   }
 }
 
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_kernel(const float *qkv, long ldq, float *out, long ldo,
                            const int32_t *row_slot, const int32_t *row_pos,
-                           KvGeom kv, int layer) {
+                           KvGeom kv, int layer, SplitOut sp) {
   extern __shared__ float smem[];
   __shared__ float red[ATT_THREADS / 32];
   __shared__ float4 pv[8 * 16];
   const int r = blockIdx.x, h = blockIdx.y;
   const int slot = row_slot[r], pos = row_pos[r];
-  float *o = out + (long)r * ldo + h * HD;
+  float *o = out ? out + (long)r * ldo + h * HD : nullptr;
   if (pos < 0) {
-    if (threadIdx.x < 16)
-      *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < 16) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o)
+        *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = z;
+      if (sp.hi)
+        split_store4(sp, r, h * HD + threadIdx.x * 4, z);
+    }
     return;
   }
   const int nkeys = pos + 1;
@@ -151,21 +161,26 @@ __global__ void __launch_bounds__(ATT_THREADS)
   auto valp = [&](int j) {
     return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
   };
-  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv);
+  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_window_kernel(const float *qkv, long ldq, float *out, long ldo,
-                            int D, const int32_t *row_pos, int ctx) {
+                            int D, const int32_t *row_pos, int ctx, SplitOut sp) {
   extern __shared__ float smem[];
   __shared__ float red[ATT_THREADS / 32];
   __shared__ float4 pv[8 * 16];
   const int r = blockIdx.x, h = blockIdx.y;
   const int pos = row_pos[r];
-  float *o = out + (long)r * ldo + h * HD;
+  float *o = out ? out + (long)r * ldo + h * HD : nullptr;
   if (pos < 0) {
-    if (threadIdx.x < 16)
-      *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < 16) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o)
+        *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = z;
+      if (sp.hi)
+        split_store4(sp, r, h * HD + threadIdx.x * 4, z);
+    }
     return;
   }
   // allowed keys: 0 <= pos - pk < ctx  ->  the last min(ctx, pos+1) rows
@@ -175,7 +190,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const float *vbase = qkv + 2 * D + h * HD;
   auto keyp = [&](int j) { return kbase + (long)(first + j) * ldq; };
   auto valp = [&](int j) { return vbase + (long)(first + j) * ldq; };
-  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv);
+  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
 }
 
 // Multi-query windowed attention: MQ consecutive rows per CTA share every K/V
@@ -184,7 +199,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 constexpr int MQ = 8;
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_window_mq_kernel(const float *qkv, long ldq, float *out, long ldo, int rows, int D,
-                               const int32_t *row_pos, int ctx) {
+                               const int32_t *row_pos, int ctx, SplitOut sp) {
   extern __shared__ float smem[];          // scores [MQ][span_cap]
   __shared__ __align__(16) float qs[MQ][HD];
   __shared__ float4 pv[8][MQ][16];
@@ -328,39 +343,42 @@ __global__ void __launch_bounds__(ATT_THREADS)
         const float4 u = pv[g2][qi][c4];
         t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
       }
-      *reinterpret_cast<float4 *>(out + (long)r * ldo + h * HD + c4 * 4) = t;
+      if (out)
+        *reinterpret_cast<float4 *>(out + (long)r * ldo + h * HD + c4 * 4) = t;
+      if (sp.hi)
+        split_store4(sp, r, h * HD + c4 * 4, t);
     }
   }
 }
 
 int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
                     const int32_t *row_slot, const int32_t *row_pos,
-                    const KvGeom &kv, int layer, int max_keys, cudaStream_t st) {
+                    const KvGeom &kv, int layer, int max_keys, cudaStream_t st, SplitOut sp) {
   if (rows <= 0)
     return 0;
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
   attention_paged_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, row_slot,
-                                                        row_pos, kv, layer);
+                                                        row_pos, kv, layer, sp);
   return 1;
 }
 
 int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      int D, int n_heads, const int32_t *row_pos, int ctx,
-                     cudaStream_t st) {
+                     cudaStream_t st, SplitOut sp) {
   if (rows <= 0)
     return 0;
   if (ctx > 0 && ctx <= 1024) {
     dim3 grid((rows + MQ - 1) / MQ, n_heads);
     size_t sm = sizeof(float) * (size_t)MQ * (ctx + MQ);
-    attention_window_mq_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, rows, D, row_pos, ctx);
+    attention_window_mq_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, rows, D, row_pos, ctx, sp);
     return 1;
   }
   dim3 grid(rows, n_heads);
   int mk = ctx > 0 ? ctx : 8192;
   size_t sm = sizeof(float) * (size_t)((mk + 15) / 16 * 16);
   attention_window_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, D,
-                                                         row_pos, ctx);
+                                                         row_pos, ctx, sp);
   return 1;
 }
 

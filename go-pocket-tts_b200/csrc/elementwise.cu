@@ -1,5 +1,6 @@
 // elementwise.cu — row-wise and gather/scatter kernels of the hot path.
 #include "kernels.cuh"
+#include "split.cuh"
 #include <math.h>
 
 namespace ptts {
@@ -10,7 +11,7 @@ namespace ptts {
 __global__ void __launch_bounds__(256)
     layernorm_kernel(const float *x, long ldx, float *out, long ldo, int rows,
                      int D, const float *w, const float *b, float eps,
-                     const float *scale, const float *shift, long ldmod) {
+                     const float *scale, const float *shift, long ldmod, SplitOut sp) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows)
@@ -51,18 +52,22 @@ __global__ void __launch_bounds__(256)
         t = t * (scale[(long)row * ldmod + i + j] + 1.0f) + shift[(long)row * ldmod + i + j];
       n[j] = t;
     }
-    *reinterpret_cast<float4 *>(orow + i) = make_float4(n[0], n[1], n[2], n[3]);
+    const float4 o = make_float4(n[0], n[1], n[2], n[3]);
+    if (out)
+      *reinterpret_cast<float4 *>(orow + i) = o;
+    if (sp.hi)
+      split_store4(sp, row, i, o);
   }
 }
 
 int layernorm(const float *x, long ldx, float *out, long ldo, int rows, int D,
               const float *w, const float *b, float eps, const float *scale,
-              const float *shift, long ldmod, cudaStream_t st) {
+              const float *shift, long ldmod, cudaStream_t st, SplitOut sp) {
   if (rows <= 0)
     return 0;
   int ctas = (rows + 7) / 8;
   layernorm_kernel<<<ctas, 256, 0, st>>>(x, ldx, out, ldo, rows, D, w, b, eps, scale,
-                                         shift, ldmod);
+                                         shift, ldmod, sp);
   return 1;
 }
 
@@ -86,53 +91,79 @@ int embed_gather(const int64_t *ids, const float *table, float *out, int rows,
 }
 
 __global__ void nan_to_bos_kernel(const float *frames, const float *bos, float *out,
-                                  int n, int ldim) {
+                                  int n, int ldim, SplitOut sp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   float v = frames[i];
-  out[i] = isnan(v) ? bos[i % ldim] : v;
+  v = isnan(v) ? bos[i % ldim] : v;
+  out[i] = v;
+  if (sp.hi)
+    split_store1(sp, i / ldim, i % ldim, v);
 }
 int nan_to_bos(const float *frames, const float *bos, float *out, int rows,
-               int ldim, cudaStream_t st) {
+               int ldim, cudaStream_t st, SplitOut sp) {
   int n = rows * ldim;
   if (n <= 0)
     return 0;
-  nan_to_bos_kernel<<<(n + 255) / 256, 256, 0, st>>>(frames, bos, out, n, ldim);
+  nan_to_bos_kernel<<<(n + 255) / 256, 256, 0, st>>>(frames, bos, out, n, ldim, sp);
   return 1;
 }
 
 __global__ void add_vec_silu_kernel(const float *a, const float *tvec, float *out,
-                                    int n, int C) {
+                                    int n, int C, SplitOut sp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   float y = tvec[i % C] + a[i];
-  out[i] = y / (1.0f + expf(-y));
+  y = y / (1.0f + expf(-y));
+  out[i] = y;
+  if (sp.hi)
+    split_store1(sp, i / C, i % C, y);
 }
 int add_vec_silu(const float *a, const float *tvec, float *out, int rows, int C,
-                 cudaStream_t st) {
+                 cudaStream_t st, SplitOut sp) {
   int n = rows * C;
   if (n <= 0)
     return 0;
-  add_vec_silu_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, tvec, out, n, C);
+  add_vec_silu_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, tvec, out, n, C, sp);
+  return 1;
+}
+
+__global__ void copy_rows_kernel(const float *src, float *dst, int n, int width, SplitOut sp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float v = src[i];
+  dst[i] = v;
+  if (sp.hi)
+    split_store1(sp, i / width, i % width, v);
+}
+int copy_rows(const float *src, float *dst, int rows, int width, cudaStream_t st, SplitOut sp) {
+  int n = rows * width;
+  if (n <= 0)
+    return 0;
+  copy_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, width, sp);
   return 1;
 }
 
 __global__ void gather_rows_kernel(const float *src, const int64_t *off, float *dst,
-                                   int rows, int width) {
+                                   int rows, int width, SplitOut sp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * width)
     return;
   int r = i / width, c = i % width;
-  dst[i] = src[off[r] + c];
+  const float v = src[off[r] + c];
+  dst[i] = v;
+  if (sp.hi)
+    split_store1(sp, r, c, v);
 }
 int gather_rows(const float *src, const int64_t *src_off, float *dst, int rows,
-                int width, cudaStream_t st) {
+                int width, cudaStream_t st, SplitOut sp) {
   int n = rows * width;
   if (n <= 0)
     return 0;
-  gather_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, src_off, dst, rows, width);
+  gather_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, src_off, dst, rows, width, sp);
   return 1;
 }
 __global__ void scatter_rows_kernel(const float *src, float *dst, const int64_t *off,

@@ -71,6 +71,8 @@ Engine::~Engine() {
     cudaFree(p);
   for (TcWeight *t : tc_owned)
     delete t;
+  for (void *m : host_maps)
+    free(m);
   for (auto &kv : step_graphs)
     if (kv.second.exec)
       cudaGraphExecDestroy(kv.second.exec);
@@ -200,6 +202,41 @@ int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, i
   return PTTS_OK;
 }
 
+int Engine::make_act(ActSplit &a, long rows_cap, int K, int lead) {
+  a.rows_cap = rows_cap;
+  a.K = K;
+  a.lead = lead;
+  a.plane_rows = rows_cap + lead;
+  const size_t elems = (size_t)2 * a.plane_rows * K;
+  int rc = dmalloc((void **)&a.base, elems * 2);
+  if (rc)
+    return rc;
+  CUDA_TRY(cudaMemset(a.base, 0, elems * 2));
+  a.p = a.base + (size_t)lead * K;
+  if (!tc_on)
+    return PTTS_OK;
+  a.map = aligned_alloc(64, 128);
+  host_maps.push_back(a.map);
+  if (tc_act_map_init(a.map, a.p, a.plane_rows + rows_cap, K, 0, 0))
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed for a [%ld,%d] activation", rows_cap, K);
+  return PTTS_OK;
+}
+
+int Engine::make_conv_map(const ActSplit &a, int cin, int taps, void **out) {
+  *out = nullptr;
+  if (!tc_on)
+    return PTTS_OK;
+  if (a.lead < taps - 1 || cin != a.K)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: conv map needs %d slack rows of %d channels", taps - 1, cin);
+  void *m = aligned_alloc(64, 128);
+  host_maps.push_back(m);
+  // row m, tap t -> plane row m - (taps-1) + t
+  if (tc_act_map_init(m, a.p - (size_t)(taps - 1) * cin, a.plane_rows + a.rows_cap + taps - 1, cin * taps, cin, taps))
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed for a conv map (cin %d, taps %d)", cin, taps);
+  *out = m;
+  return PTTS_OK;
+}
+
 int Engine::pgemm(const GemmArgs &g0) {
   GemmArgs g = g0;
   g.ws = gemm_ws;
@@ -211,6 +248,13 @@ int Engine::pgemm(const GemmArgs &g0) {
     auto it = tc_map.find(g.W);
     if (it != tc_map.end())
       tw = it->second;
+  }
+  if (!tw) {
+    g.amap = nullptr; // CUDA-core paths read the fp32 activation
+    if (!g.A) {
+      set_error("native-cuda: GEMM [%d,%d]x[%d] has no fp32 A and no tensor-core path", g.M, g.K, g.N);
+      return 0;
+    }
   }
   const char *variant = "";
   cudaEvent_t a, b;
@@ -293,22 +337,37 @@ int Engine::debug_gemm(const float *A, int M, int K, const float *W, int N, cons
 // Times one GEMM shape on device-resident data (CUDA events around `reps`
 // back-to-back launches).  lda < K exercises the overlapping-row conv form.
 int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us) {
+  // path 3 = tcgen05 with the weight rotated over enough copies to defeat the L2
+  // (the AR step streams 341 MB of weights per frame, nothing stays cached)
   if (lda <= 0)
     lda = K;
-  float *dA = nullptr, *dW = nullptr, *dC = nullptr;
+  // path 4 = path 3 with A pre-split into bf16 planes and fetched by TMA
+  const bool atma = path == 4;
+  const bool rotate = path == 3 || atma;
+  if (rotate)
+    path = 2;
+  int copies = 1;
+  if (rotate) {
+    copies = (int)((size_t)200e6 / ((size_t)N * K * 4)) + 1;
+    if (copies > 24) copies = 24;
+  }
+  float *dA = nullptr, *dC = nullptr;
+  std::vector<float *> dW(copies, nullptr);
   const size_t a_floats = (size_t)M * lda + K + 64;
   CUDA_TRY(cudaMalloc(&dA, a_floats * 4));
-  CUDA_TRY(cudaMalloc(&dW, (size_t)N * K * 4));
+  for (auto &w : dW)
+    CUDA_TRY(cudaMalloc(&w, (size_t)N * K * 4));
   CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4));
   std::vector<float> hw((size_t)N * K), ha(a_floats);
   for (size_t i = 0; i < hw.size(); i++)
     hw[i] = (float)((int)(i * 2654435761u >> 20) % 2001 - 1000) * 1e-3f;
   for (size_t i = 0; i < ha.size(); i++)
     ha[i] = (float)((int)(i * 40503u >> 7) % 2001 - 1000) * 1e-3f;
-  CUDA_TRY(cudaMemcpy(dW, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  for (auto &w : dW)
+    CUDA_TRY(cudaMemcpy(w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(dA, ha.data(), ha.size() * 4, cudaMemcpyHostToDevice));
   GemmArgs g;
-  g.A = dA; g.lda = lda; g.W = dW; g.ldw = K; g.M = M; g.N = N; g.K = K;
+  g.A = dA; g.lda = lda; g.ldw = K; g.M = M; g.N = N; g.K = K;
   g.epi.C = dC; g.epi.ldc = N;
   const bool saved = tc_on, saved_prof = prof_on;
   const int saved_min = tc_min_m;
@@ -317,16 +376,32 @@ int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, f
   if (path == 2) {
     tc_on = true;
     tc_min_m = 1;
-    rc = make_tc(dW, hw, N, K);
+    for (auto &w : dW)
+      if (rc == PTTS_OK)
+        rc = make_tc(w, hw, N, K);
   } else if (path == 1) {
     tc_on = false;
   }
+  ActSplit tmp;
+  float *dA2 = nullptr;
+  if (rc == PTTS_OK && atma && lda == K) {
+    rc = make_act(tmp, M, K, 0);
+    if (rc == PTTS_OK) {
+      CUDA_TRY(cudaMalloc(&dA2, (size_t)M * K * 4));
+      copy_rows(dA, dA2, M, K, st, tmp.out());
+      use_act(g, tmp);
+    }
+  }
   if (rc == PTTS_OK) {
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      g.W = dW[i % copies];
       pgemm(g);
+    }
     cudaEventRecord(ev[0], st);
-    for (int i = 0; i < reps; i++)
+    for (int i = 0; i < reps; i++) {
+      g.W = dW[i % copies];
       pgemm(g);
+    }
     cudaEventRecord(ev[1], st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess)
@@ -339,12 +414,40 @@ int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, f
       cudaEventElapsedTime(&ms, ev[0], ev[1]);
       *avg_us = 1e3f * ms / (float)reps;
     }
+    if (getenv("PTTS_GEMM_TIMELINE")) { // CTA 0's timeline of one more launch (tools only)
+      unsigned long long *dd = nullptr, hd[128];
+      cudaMalloc(&dd, sizeof hd);
+      cudaMemset(dd, 0, sizeof hd);
+      g.W = dW[reps % copies];
+      g.dbg = dd;
+      pgemm(g);
+      g.dbg = nullptr;
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hd, dd, sizeof hd, cudaMemcpyDeviceToHost);
+      cudaFree(dd);
+      fprintf(stderr, "timeline M=%d K=%d N=%d: prologue %lld", M, K, N, (long long)(hd[1] - hd[0]));
+      const char *lbl[3] = {"mma-ready", "A-written", "tma-issue"};
+      const int base[3] = {2, 48, 96};
+      for (int t = 0; t < 3; t++) {
+        fprintf(stderr, "\n  %s:", lbl[t]);
+        for (int i = 0; i < 32; i++)
+          if (hd[base[t] + i])
+            fprintf(stderr, " %lld", (long long)(hd[base[t] + i] - hd[0]));
+      }
+      fprintf(stderr, "\n  mma-all-issued %lld  epi-acc-ready %lld  epi-tile-done %lld  epi-exit %lld  cta-sync %lld\n",
+              (long long)(hd[40] - hd[0]), (long long)(hd[41] - hd[0]), (long long)(hd[42] - hd[0]),
+              (long long)(hd[43] - hd[0]), (long long)(hd[44] - hd[0]));
+    }
   }
   tc_on = saved;
   tc_min_m = saved_min;
   prof_on = saved_prof;
-  tc_map.erase(dW);
-  cudaFree(dA); cudaFree(dW); cudaFree(dC);
+  for (auto &w : dW) {
+    tc_map.erase(w);
+    cudaFree(w);
+  }
+  cudaFree(dA); cudaFree(dC);
+  if (dA2) cudaFree(dA2);
   return rc;
 }
 
@@ -881,6 +984,15 @@ int Engine::finalize() {
   if ((rc = dmalloc((void **)&fh_x, (size_t)B * C * 4))) return rc;
   if ((rc = dmalloc((void **)&fh_h, (size_t)B * C * 4))) return rc;
   if ((rc = dmalloc((void **)&fh_h2, (size_t)B * rb[0].mlp0.out * 4))) return rc;
+  if ((rc = make_act(s_nrm, max_rows, D, 0))) return rc;
+  if ((rc = make_act(s_att, max_rows, D, 0))) return rc;
+  if ((rc = make_act(s_ff, max_rows, F, 0))) return rc;
+  if ((rc = make_act(s_in, B, ldim, 0))) return rc;
+  if ((rc = make_act(s_last, B, D, 0))) return rc;
+  if ((rc = make_act(s_sy, B, C, 0))) return rc;
+  if ((rc = make_act(s_cur, B, ldim, 0))) return rc;
+  if ((rc = make_act(s_h, B, C, 0))) return rc;
+  if ((rc = make_act(s_h2, B, rb[0].mlp0.out, 0))) return rc;
 
   // ---- Mimi workspaces (front slack rows stay zero: causal left context) ----
   mimi_frames_cap = cfg.mimi_group_frames;
@@ -914,6 +1026,29 @@ int Engine::finalize() {
     if ((rc = slack_alloc(&m_he[s], rows, res1[s].cout))) return rc;
   }
   if ((rc = slack_alloc(&m_pcm, rows, 1))) return rc;
+  {
+    // split planes of every Mimi activation that is a GEMM / conv input (8 zero slack rows
+    // in front = the causal left context of the first segment)
+    const int lead = 8;
+    if ((rc = make_act(sm_latin, mimi_frames_cap, ldim, 0))) return rc;
+    if ((rc = make_act(sm_nrm, Rb, Md, lead))) return rc;
+    if ((rc = make_act(sm_att, Rb, Md, lead))) return rc;
+    if ((rc = make_act(sm_ff, Rb, MF, lead))) return rc;
+    if ((rc = make_act(sm_x, Rb, Md, lead))) return rc;
+    if ((rc = make_act(sm_y0e, Rb, init_conv.cout, lead))) return rc;
+    if ((rc = make_conv_map(sm_x, init_conv.cin, init_conv.taps, &init_conv.amap))) return rc;
+    size_t r2 = Rb;
+    for (int s = 0; s < 3; s++) {
+      const ActSplit &src = s == 0 ? sm_y0e : sm_ye[s - 1];
+      if ((rc = make_conv_map(src, up[s].cin, up[s].taps, &up[s].amap))) return rc;
+      r2 *= (size_t)up[s].stride;
+      if ((rc = make_act(sm_ye[s], r2, up[s].cout, lead))) return rc;
+      if ((rc = make_act(sm_he[s], r2, res1[s].cout, lead))) return rc;
+      if ((rc = make_conv_map(sm_ye[s], res1[s].cin, res1[s].taps, &res1[s].amap))) return rc;
+      if (res2[s].taps != 1)
+        if ((rc = make_conv_map(sm_he[s], res2[s].cin, res2[s].taps, &res2[s].amap))) return rc;
+    }
+  }
   if ((rc = dmalloc((void **)&d_mrow_pos, Rb * 4))) return rc;
   if ((rc = dmalloc((void **)&d_mrow_frame0, Rb * 4))) return rc;
   if ((rc = dmalloc((void **)&d_mmask, Rb))) return rc;
@@ -1052,31 +1187,35 @@ int Engine::flow_forward(int R, int max_keys, bool) {
       prof_keys += h_row_pos[r] + 1;
   for (int l = 0; l < L; l++) {
     DTLayer &ly = fl[l];
-    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st));
+    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st, s_nrm.out()));
     GemmArgs g;
     g.A = nrm; g.lda = D; g.W = ly.in_proj.w; g.ldw = D; g.M = R; g.N = 3 * D; g.K = D;
     g.epi.C = qkv; g.epi.ldc = 3 * D;
+    use_act(g, s_nrm);
     nl += pgemm(g);
     PK("rope_kv_append", 0, 0, rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st));
     if (prof_on) {
       cudaEvent_t a, b;
       prof_begin(&a, &b);
-      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st);
+      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st, s_att.out());
       prof_end(a, b, "attention_paged", 4.0 * prof_keys * D, 8.0 * prof_keys * D);
     } else
-      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st);
+      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st, s_att.out());
     GemmArgs o;
     o.A = att; o.lda = D; o.W = ly.out_proj.w; o.ldw = D; o.M = R; o.N = D; o.K = D;
     o.epi.residual = x; o.epi.ldr = D; o.epi.C = x; o.epi.ldc = D;
+    use_act(o, s_att);
     nl += pgemm(o);
-    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st));
+    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st, s_nrm.out()));
     GemmArgs f1;
     f1.A = nrm; f1.lda = D; f1.W = ly.l1.w; f1.ldw = D; f1.M = R; f1.N = F; f1.K = D;
-    f1.epi.act = ACT_GELU; f1.epi.C = ff; f1.epi.ldc = F;
+    f1.epi.act = ACT_GELU; f1.epi.C = ff; f1.epi.ldc = F; f1.epi.Cs = s_ff.out();
+    use_act(f1, s_nrm);
     nl += pgemm(f1);
     GemmArgs f2;
     f2.A = ff; f2.lda = F; f2.W = ly.l2.w; f2.ldw = F; f2.M = R; f2.N = D; f2.K = F;
     f2.epi.residual = x; f2.epi.ldr = D; f2.epi.C = x; f2.epi.ldc = D;
+    use_act(f2, s_ff);
     nl += pgemm(f2);
   }
   CUDA_TRY(cudaGetLastError());
@@ -1189,51 +1328,59 @@ int Engine::flow_head(int B, int lsd_steps) {
   int rc = get_tvec(lsd_steps, &tvec);
   if (rc)
     return rc;
-  PK("layernorm", 0, 0, layernorm(x, D, fh_last, D, B, D, out_norm.w, out_norm.b, out_norm.eps, nullptr, nullptr, 0, st));
+  PK("layernorm", 0, 0, layernorm(x, D, fh_last, D, B, D, out_norm.w, out_norm.b, out_norm.eps, nullptr, nullptr, 0, st, s_last.out()));
   PK("rowdot", 0, 0, rowdot(fh_last, D, out_eos_lin.w, out_eos_bias, B, D, fh_eos, st));
   {
     GemmArgs g;
     g.A = fh_last; g.lda = D; g.W = cond_embed.w; g.ldw = D; g.M = B; g.N = C; g.K = D;
     g.epi.bias = cond_embed.b; g.epi.C = fh_cproj; g.epi.ldc = C;
+    use_act(g, s_last);
     nl += pgemm(g);
   }
-  CUDA_TRY(cudaMemcpyAsync(fh_cur, fh_noise, (size_t)B * ldim * 4, cudaMemcpyDeviceToDevice, st));
+  PK("elementwise", 0, 0, copy_rows(fh_noise, fh_cur, B, ldim, st, s_cur.out()));
   const float inv = 1.0f / (float)lsd_steps;
   const int hid = rb[0].mlp0.out;
   for (int i = 0; i < lsd_steps; i++) {
-    PK("elementwise", 0, 0, add_vec_silu(fh_cproj, tvec + (size_t)i * C, fh_sy, B, C, st));
+    PK("elementwise", 0, 0, add_vec_silu(fh_cproj, tvec + (size_t)i * C, fh_sy, B, C, st, s_sy.out()));
     {
       GemmArgs g;
       g.A = fh_sy; g.lda = C; g.W = ada_all.w; g.ldw = C; g.M = B; g.N = ada_n; g.K = C;
       g.epi.bias = ada_all.b; g.epi.C = fh_ada; g.epi.ldc = ada_n;
+      use_act(g, s_sy);
       nl += pgemm(g);
     }
     {
       GemmArgs g;
       g.A = fh_cur; g.lda = ldim; g.W = input_proj.w; g.ldw = ldim; g.M = B; g.N = C; g.K = ldim;
       g.epi.bias = input_proj.b; g.epi.C = fh_x; g.epi.ldc = C;
+      use_act(g, s_cur);
       nl += pgemm(g);
     }
     for (int b = 0; b < depth; b++) {
       const float *shift = fh_ada + (size_t)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
       PK("layernorm", 0, 0, layernorm(fh_x, C, fh_h, C, B, C, rb[b].in_ln.w, rb[b].in_ln.b, rb[b].in_ln.eps,
-                      scale, shift, ada_n, st));
+                      scale, shift, ada_n, st, s_h.out()));
       GemmArgs g0;
       g0.A = fh_h; g0.lda = C; g0.W = rb[b].mlp0.w; g0.ldw = C; g0.M = B; g0.N = hid; g0.K = C;
       g0.epi.bias = rb[b].mlp0.b; g0.epi.act = ACT_SILU; g0.epi.C = fh_h2; g0.epi.ldc = hid;
+      g0.epi.Cs = s_h2.out();
+      use_act(g0, s_h);
       nl += pgemm(g0);
       GemmArgs g2;
       g2.A = fh_h2; g2.lda = hid; g2.W = rb[b].mlp2.w; g2.ldw = hid; g2.M = B; g2.N = C; g2.K = hid;
       g2.epi.bias = rb[b].mlp2.b; g2.epi.mul = gate; g2.epi.ldmul = ada_n;
       g2.epi.residual = fh_x; g2.epi.ldr = C; g2.epi.C = fh_x; g2.epi.ldc = C;
+      use_act(g2, s_h2);
       nl += pgemm(g2);
     }
     const float *fshift = fh_ada + (size_t)depth * 3 * C, *fscale = fshift + C;
-    PK("layernorm", 0, 0, layernorm(fh_x, C, fh_h, C, B, C, nullptr, nullptr, 1e-6f, fscale, fshift, ada_n, st));
+    PK("layernorm", 0, 0, layernorm(fh_x, C, fh_h, C, B, C, nullptr, nullptr, 1e-6f, fscale, fshift, ada_n, st, s_h.out()));
     GemmArgs gf;
     gf.A = fh_h; gf.lda = C; gf.W = final_linear.w; gf.ldw = C; gf.M = B; gf.N = ldim; gf.K = C;
     gf.epi.bias = final_linear.b; gf.epi.alpha = inv;
     gf.epi.residual = fh_cur; gf.epi.ldr = ldim; gf.epi.C = fh_cur; gf.epi.ldc = ldim;
+    gf.epi.Cs = s_cur.out();
+    use_act(gf, s_h);
     nl += pgemm(gf);
   }
   CUDA_TRY(cudaGetLastError());
@@ -1251,11 +1398,12 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     PK("gather_scatter", 0, 0, gather_rows(d_hist, d_off_a, fh_frames, Bp, ldim, st));
   if (gather_noise)
     PK("gather_scatter", 0, 0, gather_rows(d_noise, d_off_c, fh_noise, Bp, ldim, st));
-  PK("elementwise", 0, 0, nan_to_bos(fh_frames, bos, fh_in, Bp, ldim, st));
+  PK("elementwise", 0, 0, nan_to_bos(fh_frames, bos, fh_in, Bp, ldim, st, s_in.out()));
   {
     GemmArgs g;
     g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = Bp; g.N = D; g.K = ldim;
     g.epi.bias = input_linear.b; g.epi.C = x; g.epi.ldc = D;
+    use_act(g, s_in);
     nl += pgemm(g);
   }
   int rc = flow_forward(Bp, max_keys, false);
@@ -1431,21 +1579,31 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
   CUDA_TRY(cudaMemcpyAsync(d_mrow_pos, h_mrow_pos, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_mrow_frame0, h_mrow_frame0, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_mmask, h_mmask, (size_t)Rb, cudaMemcpyHostToDevice, st));
-  // latent -> mimi projection (folded denorm + 1x1 conv)
+  // With the tensor-core path on, every GEMM / conv input is produced directly as split
+  // bf16 planes (fetched by TMA) and its fp32 copy is not written.
+  const bool sp_on = tc_on;
+  auto f32 = [&](float *p) { return sp_on ? nullptr : p; };
+  auto spo = [&](const ActSplit &a) { return sp_on ? a.out() : SplitOut(); };
+  // latent -> mimi projection (folded denorm + 1x1 conv); m_latin is filled by the
+  // caller (gather from the frame history, or host latents), split here
+  if (sp_on && total_frames >= tc_min_m)
+    PK("elementwise", 0, 0, copy_rows(m_latin, m_latin, total_frames, ldim, st, sm_latin.out()));
   {
     GemmArgs g;
     g.A = m_latin; g.lda = ldim; g.W = proj.w; g.ldw = ldim; g.M = total_frames; g.N = Md; g.K = ldim;
     g.epi.bias = proj.b; g.epi.C = m_lat; g.epi.ldc = Md;
+    use_act(g, sm_latin);
     nl += pgemm(g);
   }
   PK("upsample_depthwise", 0, 0, upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st));
   // decoder transformer (mimi.go:245-441)
   for (int l = 0; l < ML; l++) {
     DTLayer &ly = ml[l];
-    PK("layernorm", 0, 0, layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st));
+    PK("layernorm", 0, 0, layernorm(m_x, Md, f32(m_nrm), Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st, spo(sm_nrm)));
     GemmArgs g;
-    g.A = m_nrm; g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
+    g.A = f32(m_nrm); g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
     g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
+    use_act(g, sm_nrm);
     nl += pgemm(g);
     PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st));
     if (prof_on) {
@@ -1455,51 +1613,74 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
           keys += h_mrow_pos[r] + 1 < Mctx ? h_mrow_pos[r] + 1 : Mctx;
       cudaEvent_t a, b;
       prof_begin(&a, &b);
-      nl += attention_window(m_qkv, 3 * Md, m_att, Md, Rb, Md, MH, d_mrow_pos, Mctx, st);
+      nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
       prof_end(a, b, "attention_window", 4.0 * keys * Md, 8.0 * keys * Md);
     } else
-      nl += attention_window(m_qkv, 3 * Md, m_att, Md, Rb, Md, MH, d_mrow_pos, Mctx, st);
+      nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
     GemmArgs o;
-    o.A = m_att; o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
+    o.A = f32(m_att); o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
     o.epi.colscale = ly.ls1; o.epi.residual = m_x; o.epi.ldr = Md; o.epi.C = m_x; o.epi.ldc = Md;
+    use_act(o, sm_att);
     nl += pgemm(o);
-    PK("layernorm", 0, 0, layernorm(m_x, Md, m_nrm, Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st));
+    PK("layernorm", 0, 0, layernorm(m_x, Md, f32(m_nrm), Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st, spo(sm_nrm)));
     GemmArgs f1;
-    f1.A = m_nrm; f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
-    f1.epi.act = ACT_GELU; f1.epi.C = m_ff; f1.epi.ldc = MF;
+    f1.A = f32(m_nrm); f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
+    f1.epi.act = ACT_GELU; f1.epi.C = f32(m_ff); f1.epi.ldc = MF; f1.epi.Cs = spo(sm_ff);
+    use_act(f1, sm_nrm);
     nl += pgemm(f1);
     GemmArgs f2;
-    f2.A = m_ff; f2.lda = MF; f2.W = ly.l2.w; f2.ldw = MF; f2.M = Rb; f2.N = Md; f2.K = MF;
+    f2.A = f32(m_ff); f2.lda = MF; f2.W = ly.l2.w; f2.ldw = MF; f2.M = Rb; f2.N = Md; f2.K = MF;
     f2.epi.colscale = ly.ls2; f2.epi.residual = m_x; f2.epi.ldr = Md; f2.epi.C = m_x; f2.epi.ldc = Md;
     if (l == ML - 1) { // pad rows must be zero again: they are the conv left context
       f2.epi.rowmask = d_mmask;
       f2.epi.mask_div = 1;
+      f2.epi.Cs = spo(sm_x); // the SEANet input
     }
+    use_act(f2, sm_ff);
     nl += pgemm(f2);
   }
   debug_bufs["mimi_transformer"] = {m_x, (size_t)Rb * Md};
   // SEANet (mimi.go:745-787): convs as GEMMs over overlapping channels-last rows
-  auto conv_gemm = [&](const DConvG &c, const float *in, int rows, int div, float *raw,
-                       float *elu, const float *residual) {
+  auto conv_gemm = [&](const DConvG &c, const float *in, const ActSplit &ins, int rows, int div, float *raw,
+                       float *elu, const ActSplit *elus, const float *residual) {
     GemmArgs g;
-    g.A = in - (size_t)(c.taps - 1) * c.cin; g.lda = c.cin; g.W = c.w; g.ldw = c.K;
+    g.A = sp_on ? nullptr : in - (size_t)(c.taps - 1) * c.cin; g.lda = c.cin; g.W = c.w; g.ldw = c.K;
     g.M = rows; g.N = c.N; g.K = c.K;
-    g.epi.bias = c.b; g.epi.C = raw; g.epi.ldc = c.N; g.epi.C2 = elu; g.epi.ldc2 = c.N;
+    g.epi.bias = c.b; g.epi.C = raw; g.epi.ldc = c.N;
+    g.epi.C2 = elu; g.epi.ldc2 = c.N;
+    if (elus && sp_on) {
+      // a stride-s transposed conv writes s output rows per input row: the split planes of
+      // its output have c.N / s channels per row, the same memory seen as [rows, c.N]
+      g.epi.C2s = elus->out();
+      g.epi.C2s.ld = c.N;
+    }
     g.epi.residual = residual; g.epi.ldr = c.N;
     g.epi.rowmask = d_mmask; g.epi.mask_div = div;
+    if (sp_on) {
+      if (c.taps > 1) {
+        g.amap = c.amap;
+        g.a_lo_row = (int)ins.plane_rows;
+        g.a_cin = c.cin;
+      } else
+        use_act(g, ins);
+    }
     nl += pgemm(g);
   };
-  conv_gemm(init_conv, m_x, Rb, 1, nullptr, m_y0e, nullptr);
-  debug_bufs["mimi_init_elu"] = {m_y0e, (size_t)Rb * init_conv.cout};
+  conv_gemm(init_conv, m_x, sm_x, Rb, 1, nullptr, f32(m_y0e), &sm_y0e, nullptr);
   const float *cur = m_y0e;
+  const ActSplit *curs = &sm_y0e;
   int rows = Rb, div = 1;
   for (int s = 0; s < 3; s++) {
-    conv_gemm(up[s], cur, rows, div, m_y[s], m_ye[s], nullptr); // rows*stride outputs
+    conv_gemm(up[s], cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr); // rows*stride outputs
     rows *= up[s].stride;
     div *= up[s].stride;
-    conv_gemm(res1[s], m_ye[s], rows, div, nullptr, m_he[s], nullptr);
-    conv_gemm(res2[s], m_he[s], rows, div, nullptr, m_ye[s], m_y[s]); // elu(x + conv2(..))
+    conv_gemm(res1[s], m_ye[s], sm_ye[s], rows, div, nullptr, f32(m_he[s]), &sm_he[s], nullptr);
+    // elu(x + conv2(..)); the last stage feeds the fp32 final conv
+    const bool last = s == 2;
+    conv_gemm(res2[s], m_he[s], sm_he[s], rows, div, nullptr, (last || !sp_on) ? m_ye[s] : nullptr,
+              last ? nullptr : &sm_ye[s], m_y[s]);
     cur = m_ye[s];
+    curs = &sm_ye[s];
   }
   PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, m_pcm, st));
   cudaEventRecord(ev[6], st);

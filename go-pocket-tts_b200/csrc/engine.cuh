@@ -55,10 +55,28 @@ struct DTLayer {
 struct DConvG {
   float *w = nullptr, *b = nullptr;
   int cin = 0, cout = 0, taps = 0, stride = 1, N = 0, K = 0;
+  void *amap = nullptr; // {cin, taps, rows} TMA map over the input's split planes (taps > 1)
 };
 struct DResBlk {
   DLayerNorm in_ln;
   DLinear mlp0, mlp2;
+};
+
+// bf16 (hi, lo) planes of an activation that feeds a tensor-core GEMM as its A operand,
+// written by the producing kernel (split.cuh) and fetched by TMA.
+// Layout: [lead slack rows | rows_cap rows] for hi, the same again for lo.
+struct ActSplit {
+  uint16_t *base = nullptr, *p = nullptr; // allocation / hi plane row 0
+  long plane_rows = 0, rows_cap = 0;
+  int K = 0, lead = 0;
+  void *map = nullptr; // CUtensorMap over {K, rows}: dense A (row stride K)
+  SplitOut out() const {
+    SplitOut o;
+    o.hi = p;
+    o.ld = K;
+    o.lo_off = plane_rows * (long)K;
+    return o;
+  }
 };
 
 struct Seq; // ptts_seq
@@ -117,6 +135,20 @@ struct Engine {
   int debug_gemm(const float *A, int M, int K, const float *W, int N, const float *bias, int act,
                  int path, float *C);
   int debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us);
+
+  // split activation planes (A operands of the tcgen05 GEMMs)
+  ActSplit s_nrm, s_att, s_ff, s_in, s_last, s_sy, s_cur, s_h, s_h2;
+  ActSplit sm_latin, sm_nrm, sm_att, sm_ff, sm_x, sm_y0e, sm_ye[3], sm_he[3];
+  std::vector<void *> host_maps;
+  int make_act(ActSplit &a, long rows_cap, int K, int lead);
+  // conv form of an activation's map: {cin, taps, rows} over the same planes
+  int make_conv_map(const ActSplit &a, int cin, int taps, void **out);
+  void use_act(GemmArgs &g, const ActSplit &a) const {
+    if (tc_on && a.map) {
+      g.amap = a.map;
+      g.a_lo_row = (int)a.plane_rows;
+    }
+  }
 
   // ---- split-K scratch for skinny GEMMs ----
   float *gemm_ws = nullptr;

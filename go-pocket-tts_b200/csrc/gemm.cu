@@ -28,7 +28,10 @@ __device__ __forceinline__ float4 ldg_stream(const float *p) {
 // ---------------------------------------------------------------------------
 // skinny kernel: MR rows (<= 8), NC output columns per warp pass
 // ---------------------------------------------------------------------------
-template <int MR, int NC>
+// KU = float4 weight loads per lane and column issued before the first FMA: the
+// kernel is HBM-bound and a lane that waits on one or two loads at a time leaves the
+// memory system idle (B=1 ran at 0.7 TB/s that way).  K <= 128*KU is a single trip.
+template <int MR, int NC, int KU>
 __global__ void __launch_bounds__(256) gemv_kernel(GemmArgs g) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -41,24 +44,32 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemmArgs g) {
 #pragma unroll
       for (int c = 0; c < NC; c++)
         acc[r][c] = 0.0f;
-#pragma unroll 2
-    for (int k = lane * 4; k < K; k += 128) {
-      float4 w[NC];
+    for (int k0 = lane * 4; k0 < K; k0 += 128 * KU) {
+      float4 w[KU][NC];
 #pragma unroll
-      for (int c = 0; c < NC; c++) {
-        int n = n0 + c < N ? n0 + c : N - 1;
-        w[c] = ldg_stream(g.W + (long)n * g.ldw + k);
-      }
-#pragma unroll
-      for (int r = 0; r < MR; r++) {
-        int rr = r < M ? r : M - 1;
-        float4 x = *reinterpret_cast<const float4 *>(g.A + (long)rr * g.lda + k);
+      for (int u = 0; u < KU; u++)
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-          acc[r][c] = fmaf(x.x, w[c].x, acc[r][c]);
-          acc[r][c] = fmaf(x.y, w[c].y, acc[r][c]);
-          acc[r][c] = fmaf(x.z, w[c].z, acc[r][c]);
-          acc[r][c] = fmaf(x.w, w[c].w, acc[r][c]);
+          const int n = n0 + c < N ? n0 + c : N - 1;
+          const int k = k0 + u * 128;
+          w[u][c] = k < K ? ldg_stream(g.W + (long)n * g.ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < KU; u++) {
+        const int k = k0 + u * 128;
+        if (k < K) {
+#pragma unroll
+          for (int r = 0; r < MR; r++) {
+            const int rr = r < M ? r : M - 1;
+            const float4 x = *reinterpret_cast<const float4 *>(g.A + (long)rr * g.lda + k);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+              acc[r][c] = fmaf(x.x, w[u][c].x, acc[r][c]);
+              acc[r][c] = fmaf(x.y, w[u][c].y, acc[r][c]);
+              acc[r][c] = fmaf(x.z, w[u][c].z, acc[r][c]);
+              acc[r][c] = fmaf(x.w, w[u][c].w, acc[r][c]);
+            }
+          }
         }
       }
     }
@@ -317,18 +328,24 @@ static void launch_sgemm(const GemmArgs &g, cudaStream_t st) {
 
 template <int MR>
 static void launch_gemv(const GemmArgs &g, cudaStream_t st) {
-  // one column per warp pass keeps every SM streaming for N ~ 1e3
+  // one column per warp pass keeps every SM streaming for N ~ 1e3; every warp issues
+  // all the weight loads of its pass (up to 2 KB per lane) before it consumes any
   const int warps_per_cta = 8;
   if (g.N >= 8192) {
     int ctas = (g.N / 2 + warps_per_cta - 1) / warps_per_cta;
     if (ctas > 148 * 8)
       ctas = 148 * 8;
-    gemv_kernel<MR, 2><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+    gemv_kernel<MR, 2, 4><<<ctas, warps_per_cta * 32, 0, st>>>(g);
   } else {
     int ctas = (g.N + warps_per_cta - 1) / warps_per_cta;
     if (ctas > 148 * 8)
       ctas = 148 * 8;
-    gemv_kernel<MR, 1><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+    if (g.K <= 512)
+      gemv_kernel<MR, 1, 4><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+    else if (g.K <= 1024 || MR > 2)
+      gemv_kernel<MR, 1, 8><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+    else
+      gemv_kernel<MR, 1, 16><<<ctas, warps_per_cta * 32, 0, st>>>(g);
   }
 }
 

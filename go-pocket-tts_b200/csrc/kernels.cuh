@@ -15,6 +15,13 @@ namespace ptts {
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_ELU = 3 };
 
+// Optional bf16 (hi, lo) mirror of an fp32 [rows, cols] output: hi plane row stride ld
+// (elements), lo plane lo_off elements after the hi plane.  See split.cuh.
+struct SplitOut {
+  uint16_t *hi = nullptr;
+  long ld = 0, lo_off = 0;
+};
+
 // Fused GEMM epilogue, applied in this order (matches the reference op order:
 // Linear bias -> activation -> LayerScale -> adaLN gate -> residual add):
 //   v = acc + bias[n]; v = act(v); v *= colscale[n]; v *= mul[m,n];
@@ -33,6 +40,7 @@ struct GemmEpi {
   long ldc = 0;
   float *C2 = nullptr;
   long ldc2 = 0;
+  SplitOut Cs, C2s; // split-bf16 copies of C / C2 for a following tensor-core GEMM
   const uint8_t *rowmask = nullptr; // row m is live iff rowmask[m / mask_div]
   int mask_div = 1;
 };
@@ -49,6 +57,14 @@ struct GemmArgs {
   long ws_floats = 0;
   int *counters = nullptr;
   int n_counters = 0;
+  // A already split into bf16 planes and described by a TMA map (tc_act_map_init):
+  // both operands are then fetched by TMA and A / lda are not read.  a_lo_row = row
+  // offset of the lo plane inside the map; a_cin > 0: implicit-GEMM conv over
+  // overlapping rows, map dims {cin, taps, rows}, k = tap * cin + c.
+  const void *amap = nullptr;
+  int a_lo_row = 0, a_cin = 0;
+  // optional timeline of CTA 0 (globaltimer ns; tools only)
+  unsigned long long *dbg = nullptr;
 };
 
 // C = epi(A * W^T).  Chooses the weight-streaming skinny kernel for M <= 8 and
@@ -66,7 +82,13 @@ struct alignas(64) TcWeight {
   int N = 0, K = 0;
 };
 int tc_weight_init(TcWeight *w, const void *d_split, int N, int K);
+// TMA map (128-byte blob, 64-byte aligned) over split activation planes: `base` points at
+// hi row 0, rows_total rows of K bf16 (hi plane then lo plane).  cin > 0 builds the 3-D
+// overlapping-row form {cin, taps, rows} for an implicit-GEMM conv (row stride cin).
+int tc_act_map_init(void *map, const void *base, long rows_total, int K, int cin, int taps);
 bool tc_gemm_supported(const GemmArgs &g);
+// Sweep hook: force the tile width / split-K of every following tc_gemm (bn <= 0: automatic).
+void tc_force_tile(int bn, int s);
 // Same contract as gemm(); W is taken from `w` (g.W is ignored).
 int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant);
 
@@ -79,7 +101,7 @@ int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
 // (linear.go:265-329, tensor_util.go:175-193)
 int layernorm(const float *x, long ldx, float *out, long ldo, int rows, int D,
               const float *w, const float *b, float eps, const float *scale,
-              const float *shift, long ldmod, cudaStream_t st);
+              const float *shift, long ldmod, cudaStream_t st, SplitOut sp = SplitOut());
 
 // out[r,:] = table[ids[r],:]   (conditioner.go:31-53)
 int embed_gather(const int64_t *ids, const float *table, float *out, int rows,
@@ -110,7 +132,8 @@ int kv_read_rows(float *out, int T, int slot, const KvGeom &kv, int layer,
 // q is read from qkv[r, 0:D], output to out[r, 0:D].
 int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
                     const int32_t *row_slot, const int32_t *row_pos,
-                    const KvGeom &kv, int layer, int max_keys, cudaStream_t st);
+                    const KvGeom &kv, int layer, int max_keys, cudaStream_t st,
+                    SplitOut sp = SplitOut());
 
 // RoPE in place on q and k of qkv [R, 3*D] with per-row positions (<0 = skip).
 int rope_inplace(float *qkv, int rows, int D, int n_heads, const int32_t *row_pos,
@@ -120,17 +143,20 @@ int rope_inplace(float *qkv, int rows, int D, int n_heads, const int32_t *row_po
 // (mimi.go:386-441, attention.go:473-484).  Pad rows (p < 0) produce zeros.
 int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      int D, int n_heads, const int32_t *row_pos, int ctx,
-                     cudaStream_t st);
+                     cudaStream_t st, SplitOut sp = SplitOut());
 
 // x_in[r,:] = isnan(frames[r,i]) ? bos[i] : frames[r,i]  (tensor_util.go:242-271)
 int nan_to_bos(const float *frames, const float *bos, float *out, int rows,
-               int ldim, cudaStream_t st);
+               int ldim, cudaStream_t st, SplitOut sp = SplitOut());
 // out = silu(a[m,:] + tvec[:])   (flow_net.go:334-343 + resblock SiLU(y))
 int add_vec_silu(const float *a, const float *tvec, float *out, int rows, int C,
-                 cudaStream_t st);
+                 cudaStream_t st, SplitOut sp = SplitOut());
 // gathers/scatters of [*,32] latent rows by index
 int gather_rows(const float *src, const int64_t *src_off, float *dst, int rows,
-                int width, cudaStream_t st);
+                int width, cudaStream_t st, SplitOut sp = SplitOut());
+// dst = src over [rows, width] (+ split copy)
+int copy_rows(const float *src, float *dst, int rows, int width, cudaStream_t st,
+              SplitOut sp = SplitOut());
 int scatter_rows(const float *src, float *dst, const int64_t *dst_off, int rows,
                  int width, cudaStream_t st);
 

@@ -668,6 +668,11 @@ int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const 
   return e->impl.debug_gemm(A, M, K, W, N, bias, act, path, C);
 }
 
+int ptts_debug_tc_force(int32_t bn, int32_t s) {
+  ptts::tc_force_tile(bn, s);
+  return PTTS_OK;
+}
+
 int ptts_debug_gemm_bench(ptts_engine *e, int32_t M, int32_t K, int32_t N, int32_t lda, int32_t path,
                           int32_t reps, float *avg_us) {
   if (!e || !avg_us || M <= 0 || N <= 0 || K <= 0 || reps <= 0)

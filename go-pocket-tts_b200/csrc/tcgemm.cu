@@ -27,6 +27,7 @@
 // issuer, warps 2..9 = A converters, warps 2..5 = epilogue.
 #include "kernels.cuh"
 #include "gemm_epi.cuh"
+#include "split.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -41,7 +42,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64; // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_CONV_THREADS = 256;
 constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_THREADS = 64 + TC_CONV_THREADS + TC_EPI_WARPS * 32;
+constexpr int TC_BASE_THREADS = 64 + TC_EPI_WARPS * 32; // TMA, MMA, epilogue warps
+constexpr int TC_THREADS = TC_BASE_THREADS + TC_CONV_THREADS; // + A converters (fp32 A only)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -61,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 2000;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
@@ -73,6 +75,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 B apart.
@@ -104,21 +114,6 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi).  Packed conversions
-// (cvt.rn.bf16x2.f32 -> one F2FP per pair) instead of scalar F2F: the scalar
-// form ran on the slow conversion pipe and bound the whole k-block.
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0)); // x0 -> low half
-  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
-}
-__device__ __forceinline__ void split8(const float4 &u, const float4 &v, uint4 &hi, uint4 &lo) {
-  split2(u.x, u.y, hi.x, lo.x);
-  split2(u.z, u.w, hi.y, lo.y);
-  split2(v.x, v.y, hi.z, lo.z);
-  split2(v.z, v.w, hi.w, lo.w);
-}
-
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -130,15 +125,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 
 // Fused epilogue of one 32x32 accumulator chunk held in a warp's staging buffer: lane
 // (rsub, cf) owns columns n..n+3 of rows rsub, rsub+4, ... (8 rows).  `rows` bit j = row
-// in range, bit 8+j = row live (not masked).  FULL: every row in range, no checks.
-// OUT: 1 = C, 2 = C2 (= elu), 3 = both.  Rare operands (mul, alpha) only when GENERIC.
-template <int ACT, int OUT, bool FULL, bool GENERIC>
-__device__ __forceinline__ void epi_rows(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
-                                         uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
-                                         bool have_res) {
-  float *cp = (OUT & 1) ? e.C + m_first * e.ldc + n : nullptr;
-  float *cp2 = (OUT & 2) ? e.C2 + m_first * e.ldc2 + n : nullptr;
-  const float *mp = GENERIC && e.mul ? e.mul + m_first * e.ldmul + n : nullptr;
+// in range, bit 8+j = row live (not masked).  Outputs (each optional): C fp32, Cs its
+// bf16 split, C2 = elu(C) fp32, C2s its split.
+//
+// The hot configurations are compiled as straight-line code (activation ACT, output set
+// MASK: 1 = C, 2 = Cs, 4 = C2, 8 = C2s, FULL = all 8 rows in range); anything else (adaLN
+// gate `mul`, `alpha`, unusual output sets) takes the generic path with runtime checks.
+__device__ __forceinline__ float4 elu4(const float4 &o) {
+  float4 u;
+  u.x = act_apply(o.x, ACT_ELU);
+  u.y = act_apply(o.y, ACT_ELU);
+  u.z = act_apply(o.z, ACT_ELU);
+  u.w = act_apply(o.w, ACT_ELU);
+  return u;
+}
+template <int ACT, int MASK, bool FULL>
+__device__ __forceinline__ void epi_rows_fast(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first,
+                                              int n, uint32_t rows, const float4 &bias4, const float4 &cs4,
+                                              const float4 *res, bool have_res) {
+  float *cp = (MASK & 1) ? e.C + m_first * e.ldc + n : nullptr;
+  float *cp2 = (MASK & 4) ? e.C2 + m_first * e.ldc2 + n : nullptr;
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     if (FULL || ((rows >> j) & 1)) {
@@ -149,52 +155,104 @@ __device__ __forceinline__ void epi_rows(const GemmEpi &e, uint32_t stg_addr, in
         o.z = act_apply(o.z, ACT); o.w = act_apply(o.w, ACT);
       }
       o.x *= cs4.x; o.y *= cs4.y; o.z *= cs4.z; o.w *= cs4.w;
-      if (GENERIC) {
-        if (mp) {
-          const float4 t = *reinterpret_cast<const float4 *>(mp + (long)j * 4 * e.ldmul);
-          o.x *= t.x; o.y *= t.y; o.z *= t.z; o.w *= t.w;
-        }
-        o.x *= e.alpha; o.y *= e.alpha; o.z *= e.alpha; o.w *= e.alpha;
-      }
       if (have_res) {
         o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w;
       }
       if (!((rows >> (8 + j)) & 1))
         o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (OUT & 1)
+      if (MASK & 1)
         *reinterpret_cast<float4 *>(cp + (long)j * 4 * e.ldc) = o;
-      if (OUT & 2) {
-        float4 u;
-        u.x = act_apply(o.x, ACT_ELU);
-        u.y = act_apply(o.y, ACT_ELU);
-        u.z = act_apply(o.z, ACT_ELU);
-        u.w = act_apply(o.w, ACT_ELU);
-        *reinterpret_cast<float4 *>(cp2 + (long)j * 4 * e.ldc2) = u;
+      if (MASK & 2)
+        split_store4(e.Cs, m_first + j * 4, n, o);
+      if (MASK & 12) {
+        const float4 u = elu4(o);
+        if (MASK & 4)
+          *reinterpret_cast<float4 *>(cp2 + (long)j * 4 * e.ldc2) = u;
+        if (MASK & 8)
+          split_store4(e.C2s, m_first + j * 4, n, u);
       }
     }
   }
 }
-template <int ACT, int OUT>
-__device__ __forceinline__ void epi_rows_sel(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
-                                             uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
-                                             bool have_res, bool full, bool generic) {
-  if (generic)
-    epi_rows<ACT, OUT, false, true>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
-  else if (full)
-    epi_rows<ACT, OUT, true, false>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
-  else
-    epi_rows<ACT, OUT, false, false>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
+__device__ __forceinline__ void epi_rows_generic(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
+                                              uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
+                                              bool have_res) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if ((rows >> j) & 1) {
+      const long m = m_first + j * 4;
+      float4 o = lds128(stg_addr + j * 4 * stg_ld_bytes);
+      o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+      if (e.act != ACT_NONE) {
+        o.x = act_apply(o.x, e.act); o.y = act_apply(o.y, e.act);
+        o.z = act_apply(o.z, e.act); o.w = act_apply(o.w, e.act);
+      }
+      o.x *= cs4.x; o.y *= cs4.y; o.z *= cs4.z; o.w *= cs4.w;
+      if (e.mul) {
+        const float4 t = *reinterpret_cast<const float4 *>(e.mul + m * e.ldmul + n);
+        o.x *= t.x; o.y *= t.y; o.z *= t.z; o.w *= t.w;
+      }
+      o.x *= e.alpha; o.y *= e.alpha; o.z *= e.alpha; o.w *= e.alpha;
+      if (have_res) {
+        o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w;
+      }
+      if (!((rows >> (8 + j)) & 1))
+        o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.C)
+        *reinterpret_cast<float4 *>(e.C + m * e.ldc + n) = o;
+      if (e.Cs.hi)
+        split_store4(e.Cs, m, n, o);
+      if (e.C2 || e.C2s.hi) {
+        const float4 u = elu4(o);
+        if (e.C2)
+          *reinterpret_cast<float4 *>(e.C2 + m * e.ldc2 + n) = u;
+        if (e.C2s.hi)
+          split_store4(e.C2s, m, n, u);
+      }
+    }
+  }
 }
-template <int ACT>
-__device__ __forceinline__ void epi_rows_out(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
-                                             uint32_t rows, const float4 &bias4, const float4 &cs4, const float4 *res,
-                                             bool have_res, bool full, bool generic) {
-  if (e.C && e.C2)
-    epi_rows_sel<ACT, 3>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
-  else if (e.C2)
-    epi_rows_sel<ACT, 2>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
-  else if (e.C)
-    epi_rows_sel<ACT, 1>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
+// Epilogue kinds with a compiled fast path: (activation << 4) | output mask.
+__host__ __device__ constexpr int epi_code(int act, int mask) { return (act << 4) | mask; }
+__host__ inline int epi_kind_of(const GemmEpi &e) {
+  if (e.mul || e.alpha != 1.0f)
+    return -1;
+  const int mask = (e.C ? 1 : 0) | (e.Cs.hi ? 2 : 0) | (e.C2 ? 4 : 0) | (e.C2s.hi ? 8 : 0);
+  const int code = epi_code(e.act, mask);
+  switch (code) {
+  case epi_code(ACT_NONE, 1): case epi_code(ACT_NONE, 3): case epi_code(ACT_NONE, 8): case epi_code(ACT_NONE, 9):
+  case epi_code(ACT_NONE, 4): case epi_code(ACT_NONE, 5): case epi_code(ACT_GELU, 1): case epi_code(ACT_GELU, 2):
+  case epi_code(ACT_GELU, 3): case epi_code(ACT_SILU, 3):
+    return code;
+  default:
+    return -1;
+  }
+}
+#define TC_EPI_CASE(ACT, MASK)                                                                                         \
+  case epi_code(ACT, MASK):                                                                                            \
+    if (full)                                                                                                          \
+      epi_rows_fast<ACT, MASK, true>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);          \
+    else                                                                                                               \
+      epi_rows_fast<ACT, MASK, false>(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);         \
+    break;
+__device__ __forceinline__ void epi_rows_dispatch(int kind, const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes,
+                                                  long m_first, int n, uint32_t rows, const float4 &bias4,
+                                                  const float4 &cs4, const float4 *res, bool have_res, bool full) {
+  switch (kind) {
+    TC_EPI_CASE(ACT_NONE, 1)
+    TC_EPI_CASE(ACT_NONE, 3)
+    TC_EPI_CASE(ACT_NONE, 8)
+    TC_EPI_CASE(ACT_NONE, 9)
+    TC_EPI_CASE(ACT_NONE, 4)
+    TC_EPI_CASE(ACT_NONE, 5)
+    TC_EPI_CASE(ACT_GELU, 1)
+    TC_EPI_CASE(ACT_GELU, 2)
+    TC_EPI_CASE(ACT_GELU, 3)
+    TC_EPI_CASE(ACT_SILU, 3)
+  default:
+    epi_rows_generic(e, stg_addr, stg_ld_bytes, m_first, n, rows, bias4, cs4, res, have_res);
+    break;
+  }
 }
 
 int tc_num_sms() {
@@ -207,6 +265,17 @@ int tc_num_sms() {
   }
   return n;
 }
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i)                                                            \
+  do {                                                                         \
+    if (g.dbg && blockIdx.x == 0)                                              \
+      g.dbg[i] = gtimer();                                                     \
+  } while (0)
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -221,9 +290,10 @@ struct TcSmem {
 // Work decomposition shared by every warp role: item i -> (m tile, n tile, k split).
 // Splits of one tile are adjacent items so they run at the same time.
 struct TcItems {
-  long total;
+  int total;
   int ntn, S, kb_per, nkb_all;
-  __device__ __forceinline__ void decode(long i, int &m0, int &n0, int &kb_begin, int &nkb, int &z, int &tile,
+  int epi_kind; // epi_code() of a compiled epilogue, or -1: generic
+  __device__ __forceinline__ void decode(int i, int &m0, int &n0, int &kb_begin, int &nkb, int &z, int &tile,
                                          int bn) const {
     z = (int)(i % S);
     tile = i / S;
@@ -239,9 +309,12 @@ struct TcItems {
 // Persistent, warp-specialised kernel: each CTA walks items blockIdx.x, +gridDim.x, ...
 // The accumulator is double-buffered in TMEM so the epilogue of item i overlaps the
 // main loop of item i+1; the smem operand ring runs straight through item boundaries.
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-    tc_gemm_kernel(const __grid_constant__ CUtensorMap wmap, GemmArgs g, int n_rows_hi, TcItems items) {
+// ATMA: A is already split into bf16 planes behind `amap`; the TMA warp fetches both
+// operands and the converter warps are not launched.
+template <int BN, int STAGES, bool ATMA>
+__global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap, GemmArgs g,
+                   int n_rows_hi, TcItems items) {
   using SM = TcSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,9 +332,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   if (threadIdx.x == 0) {
+    TC_STAMP(0);
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    if (ATMA)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full[s], TC_CONV_THREADS + 1);
+      mbar_init(&full[s], ATMA ? 1 : TC_CONV_THREADS + 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; b++) {
@@ -280,6 +356,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0)
+    TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer: W hi + lo tiles of every k-block of every item =====
@@ -294,9 +372,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (it >= STAGES)
             mbar_wait(&empty[s], (uint32_t)((it / STAGES) - 1) & 1);
           uint8_t *st = smem + s * SM::STAGE;
-          mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE);
-          tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], (kb_begin + kb) * TC_BK, n0);
-          tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], (kb_begin + kb) * TC_BK, n_rows_hi + n0);
+          if (it < 32)
+            TC_STAMP(96 + it);
+          mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE + (ATMA ? 2 * SM::A_TILE : 0));
+          const int k0 = (kb_begin + kb) * TC_BK;
+          if (ATMA) {
+            if (g.a_cin > 0) { // conv over overlapping rows: k = tap * cin + c
+              const int tap = k0 / g.a_cin, c0 = k0 - tap * g.a_cin;
+              tma_load_3d(st, &amap, &full[s], c0, tap, m0);
+              tma_load_3d(st + SM::A_TILE, &amap, &full[s], c0, tap, g.a_lo_row + m0);
+            } else {
+              tma_load_2d(st, &amap, &full[s], k0, m0);
+              tma_load_2d(st + SM::A_TILE, &amap, &full[s], k0, g.a_lo_row + m0);
+            }
+          }
+          tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], k0, n0);
+          tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], k0, n_rows_hi + n0);
         }
       }
     }
@@ -319,6 +410,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int s = (int)(it % STAGES);
           mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (it < 32)
+            TC_STAMP(2 + it);
           const uint32_t a_hi = smem_u32(smem + s * SM::STAGE);
           const uint32_t a_lo = a_hi + SM::A_TILE;
           const uint32_t w_hi = a_hi + 2 * SM::A_TILE;
@@ -335,11 +428,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           umma_commit(&empty[s]); // frees the smem stage once these MMAs have read it
         }
         umma_commit(&acc_full[b]);
+        if (li == 0)
+          TC_STAMP(40);
       }
     }
-  } else if (warp < 2 + TC_CONV_THREADS / 32) {
+  } else if (warp >= TC_BASE_THREADS / 32) {
     // ===== A converters: fp32 global -> (hi, lo) bf16 swizzled smem =====
-    const int ct = threadIdx.x - 64;
+    const int ct = threadIdx.x - TC_BASE_THREADS;
     // PF k-blocks of A stay in flight per thread, across item boundaries.
     constexpr int PF = 3;
     float4 r[PF][4][2];
@@ -415,6 +510,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             advance(lc);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes -> tensor-core reads
+          if (ct == 0 && it < 32)
+            TC_STAMP(48 + it);
           mbar_arrive(&full[s]);
           advance(cc);
           it++;
@@ -425,9 +522,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===== epilogue warps: TMEM -> per-warp smem transpose -> coalesced fused epilogue =====
     const GemmEpi &e = g.epi;
     const int q = warp & 3; // TMEM lane quarter this warp may access
-    const uint32_t stg_addr = smem_u32(stg_base + (warp - (2 + TC_CONV_THREADS / 32)) * SM::STG_WARP);
-    const bool generic = e.mul != nullptr || e.alpha != 1.0f;
-    const int et = threadIdx.x - (64 + TC_CONV_THREADS); // 0..127
+    const uint32_t stg_addr = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
+    const int et = threadIdx.x - 64; // 0..127
     const int rsub = lane >> 3, cf = (lane & 7) * 4;     // coalesced phase: 4 rows x 32 columns per instruction
     uint32_t li = 0;
     for (int i = blockIdx.x; i < items.total; i += gridDim.x, li++) {
@@ -451,6 +547,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       float *mine = tile_ws + (long)z * TC_BM * BN;
       mbar_wait(&acc_full[b], (uint32_t)(li >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (et == 0 && li == 0)
+        TC_STAMP(41);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const int n = n0 + c0 + cf;
@@ -501,26 +599,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         } else if (nok) {
           const long m_first = m0 + q * 32 + rsub;
-          switch (e.act) {
-          case ACT_GELU:
-            epi_rows_out<ACT_GELU>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
-            break;
-          case ACT_SILU:
-            epi_rows_out<ACT_SILU>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
-            break;
-          case ACT_ELU:
-            epi_rows_out<ACT_ELU>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
-            break;
-          default:
-            epi_rows_out<ACT_NONE>(e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res, full, generic);
-            break;
-          }
+          epi_rows_dispatch(items.epi_kind, e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res,
+                            full);
         }
         __syncwarp(); // staging is rewritten by the next chunk
       }
       // this accumulator buffer may be overwritten by the MMA warp from here on
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&acc_empty[b]);
+      if (et == 0 && li == 0)
+        TC_STAMP(42);
       if (S > 1) {
         // split-K: the last CTA to publish its partial tile sums all partials in split
         // order (deterministic) and runs the epilogue.
@@ -558,13 +646,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                   o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (e.C)
                   *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = o;
-                if (e.C2) {
+                if (e.Cs.hi)
+                  split_store4(e.Cs, m, n, o);
+                if (e.C2 || e.C2s.hi) {
                   float4 u;
                   u.x = act_apply(o.x, ACT_ELU);
                   u.y = act_apply(o.y, ACT_ELU);
                   u.z = act_apply(o.z, ACT_ELU);
                   u.w = act_apply(o.w, ACT_ELU);
-                  *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u;
+                  if (e.C2)
+                    *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u;
+                  if (e.C2s.hi)
+                    split_store4(e.C2s, m, n, u);
                 }
               }
             }
@@ -573,8 +666,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   }
+  if (threadIdx.x == 64)
+    TC_STAMP(43);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0)
+    TC_STAMP(44);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -596,13 +693,13 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, int STAGES>
-int launch_tc(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
+template <int BN, int STAGES, bool ATMA>
+int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SM::BYTES) != cudaSuccess)
       return -1;
     configured = true;
   }
@@ -621,18 +718,25 @@ int launch_tc(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   it.kb_per = (it.nkb_all + S - 1) / S;
   S = (it.nkb_all + it.kb_per - 1) / it.kb_per; // every split owns >= 1 k-block
   it.S = S;
-  it.total = tiles * S;
+  it.total = (int)(tiles * S);
+  it.epi_kind = epi_kind_of(g.epi);
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
-  tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, SM::BYTES, st>>>(*map, g, w.N, it);
+  const CUtensorMap *am = ATMA ? reinterpret_cast<const CUtensorMap *>(g.amap) : map;
+  tc_gemm_kernel<BN, STAGES, ATMA><<<grid, ATMA ? TC_BASE_THREADS : TC_THREADS, SM::BYTES, st>>>(*map, *am, g, w.N, it);
   return 1;
+}
+template <int BN, int STAGES>
+int launch_tc(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
+  return g.amap ? launch_tc_a<BN, STAGES, true>(w, g, S, st) : launch_tc_a<BN, STAGES, false>(w, g, S, st);
 }
 
 // Tile width and split-K for one GEMM.  Wide problems (many m tiles) take the widest
 // tile that divides N (fewest A re-reads); skinny ones (the AR step, M <= 512) are
 // bound by what one SM can pull through L2, so the choice minimises the bytes a CTA
 // streams, (128 + BN) * 256 B per k-block, over one wave of CTAs.
+int force_bn = -1, force_s = 0; // PTTS_TC_FORCE="bn,s" or tc_force_tile(): sweeps only
+
 void choose_tile(const GemmArgs &g, int &bn, int &S) {
-  static int force_bn = -1, force_s = 0;
   if (force_bn < 0) {
     force_bn = 0;
     if (const char *f = getenv("PTTS_TC_FORCE"))
@@ -710,9 +814,42 @@ int tc_weight_init(TcWeight *w, const void *d_split, int N, int K) {
   return 0;
 }
 
+int tc_act_map_init(void *map, const void *base, long rows_total, int K, int cin, int taps) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc)
+    return -1;
+  CUresult r;
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (cin > 0) {
+    // {cin, taps, rows}: tap t of row m is row m + t of the plane (A rows overlap)
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)rows_total};
+    cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, 1, (cuuint32_t)TC_BM};
+    r = enc(reinterpret_cast<CUtensorMap *>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows_total};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    r = enc(reinterpret_cast<CUtensorMap *>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+void tc_force_tile(int bn, int s) {
+  force_bn = bn > 0 ? bn : 0;
+  force_s = s;
+}
+
 bool tc_gemm_supported(const GemmArgs &g) {
-  return g.M >= 1 && g.N >= 32 && g.N % 16 == 0 && g.K >= 32 && g.K % 8 == 0 && g.lda % 4 == 0 &&
-         (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+  if (g.M < 1 || g.N < 32 || g.N % 16 != 0 || g.K < 32 || g.K % 8 != 0)
+    return false;
+  if (g.amap)
+    return true;
+  return g.A != nullptr && g.lda % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
 }
 
 int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant) {

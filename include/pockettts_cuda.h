@@ -232,6 +232,8 @@ int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const 
                     const float *bias, int32_t act, int32_t path, float *C);
 /* Times one GEMM shape on device data: average microseconds over `reps`
  * launches (CUDA events on the engine stream).  lda < K = overlapping rows. */
+/* Sweep hook: force tile width / split-K of the tcgen05 GEMM (bn <= 0 restores the heuristic). */
+int ptts_debug_tc_force(int32_t bn, int32_t s);
 int ptts_debug_gemm_bench(ptts_engine *e, int32_t M, int32_t K, int32_t N, int32_t lda, int32_t path,
                           int32_t reps, float *avg_us);
 /* Copies a named internal buffer of the last pass (debug / stage parity). */
