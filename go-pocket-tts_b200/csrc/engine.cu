@@ -391,6 +391,19 @@ int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, f
       copy_rows(dA, dA2, M, K, st, tmp.out());
       use_act(g, tmp);
     }
+  } else if (rc == PTTS_OK && atma && K % lda == 0) { // conv form: taps = K / lda overlapping rows
+    const int taps = K / lda;
+    rc = make_act(tmp, M, lda, 8);
+    void *cm = nullptr;
+    if (rc == PTTS_OK)
+      rc = make_conv_map(tmp, lda, taps, &cm);
+    if (rc == PTTS_OK) {
+      CUDA_TRY(cudaMalloc(&dA2, (size_t)M * lda * 4));
+      copy_rows(dA, dA2, M, lda, st, tmp.out());
+      g.amap = cm;
+      g.a_lo_row = (int)tmp.plane_rows;
+      g.a_cin = lda;
+    }
   }
   if (rc == PTTS_OK) {
     for (int i = 0; i < 3; i++) {
@@ -426,7 +439,7 @@ int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, f
       cudaMemcpy(hd, dd, sizeof hd, cudaMemcpyDeviceToHost);
       cudaFree(dd);
       fprintf(stderr, "timeline M=%d K=%d N=%d: prologue %lld", M, K, N, (long long)(hd[1] - hd[0]));
-      const char *lbl[3] = {"mma-ready", "A-written", "tma-issue"};
+      const char *lbl[3] = {"mma-ready", "A-written / item-epilogue-done", "tma-issue"};
       const int base[3] = {2, 48, 96};
       for (int t = 0; t < 3; t++) {
         fprintf(stderr, "\n  %s:", lbl[t]);

@@ -41,9 +41,11 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64; // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_CONV_THREADS = 256;
-constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_BASE_THREADS = 64 + TC_EPI_WARPS * 32; // TMA, MMA, epilogue warps
-constexpr int TC_THREADS = TC_BASE_THREADS + TC_CONV_THREADS; // + A converters (fp32 A only)
+// threads: warp 0 TMA, warp 1 MMA, EW epilogue warps (4, or 8 = two per TMEM lane quarter
+// for the short-K shapes whose epilogue is the bottleneck), then 8 A-converter warps when
+// A is fp32 in HBM.
+__host__ __device__ constexpr int tc_base_threads(int ew) { return 64 + ew * 32; }
+__host__ __device__ constexpr int tc_threads(int ew, bool atma) { return tc_base_threads(ew) + (atma ? 0 : TC_CONV_THREADS); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -131,13 +133,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // The hot configurations are compiled as straight-line code (activation ACT, output set
 // MASK: 1 = C, 2 = Cs, 4 = C2, 8 = C2s, FULL = all 8 rows in range); anything else (adaLN
 // gate `mul`, `alpha`, unusual output sets) takes the generic path with runtime checks.
+// ELU with the hardware exponential (ex2.approx): abs error ~1e-7 on values in (-1, 0],
+// far inside the waveform tolerance; the full-precision expf was most of the epilogue's
+// instructions on the HBM-bound SEANet layers.
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.0f ? v : __expf(v) - 1.0f; }
 __device__ __forceinline__ float4 elu4(const float4 &o) {
-  float4 u;
-  u.x = act_apply(o.x, ACT_ELU);
-  u.y = act_apply(o.y, ACT_ELU);
-  u.z = act_apply(o.z, ACT_ELU);
-  u.w = act_apply(o.w, ACT_ELU);
-  return u;
+  return make_float4(elu_fast(o.x), elu_fast(o.y), elu_fast(o.z), elu_fast(o.w));
 }
 template <int ACT, int MASK, bool FULL>
 __device__ __forceinline__ void epi_rows_fast(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first,
@@ -277,14 +278,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
       g.dbg[i] = gtimer();                                                     \
   } while (0)
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW = 4>
 struct TcSmem {
   static constexpr int A_TILE = TC_BM * TC_BK * 2; // bytes per bf16 A tile (16 KB)
   static constexpr int W_TILE = BN * TC_BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
   static constexpr int STG_LD = 36;                 // staging row stride (floats): conflict-free v4 both ways
   static constexpr int STG_WARP = 32 * STG_LD * 4;  // one 32x32 fp32 chunk per epilogue warp
-  static constexpr int BYTES = STAGES * STAGE + TC_EPI_WARPS * STG_WARP + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int BYTES = STAGES * STAGE + EW * STG_WARP + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // Work decomposition shared by every warp role: item i -> (m tile, n tile, k split).
@@ -311,15 +312,15 @@ struct TcItems {
 // main loop of item i+1; the smem operand ring runs straight through item boundaries.
 // ATMA: A is already split into bf16 planes behind `amap`; the TMA warp fetches both
 // operands and the converter warps are not launched.
-template <int BN, int STAGES, bool ATMA>
-__global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
+template <int BN, int STAGES, bool ATMA, int EW>
+__global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap, GemmArgs g,
                    int n_rows_hi, TcItems items) {
-  using SM = TcSmem<BN, STAGES>;
+  using SM = TcSmem<BN, STAGES, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *stg_base = smem + STAGES * SM::STAGE;
-  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + TC_EPI_WARPS * SM::STG_WARP);
+  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + EW * SM::STG_WARP);
   uint64_t *empty = full + STAGES;
   uint64_t *acc_full = empty + STAGES; // [2]
   uint64_t *acc_empty = acc_full + 2;  // [2]
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], TC_EPI_WARPS * 32);
+      mbar_init(&acc_empty[b], EW * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -432,9 +433,9 @@ __global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
           TC_STAMP(40);
       }
     }
-  } else if (warp >= TC_BASE_THREADS / 32) {
+  } else if (warp >= tc_base_threads(EW) / 32) {
     // ===== A converters: fp32 global -> (hi, lo) bf16 swizzled smem =====
-    const int ct = threadIdx.x - TC_BASE_THREADS;
+    const int ct = threadIdx.x - tc_base_threads(EW);
     // PF k-blocks of A stay in flight per thread, across item boundaries.
     constexpr int PF = 3;
     float4 r[PF][4][2];
@@ -523,7 +524,10 @@ __global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
     const GemmEpi &e = g.epi;
     const int q = warp & 3; // TMEM lane quarter this warp may access
     const uint32_t stg_addr = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
-    const int et = threadIdx.x - 64; // 0..127
+    const int et = threadIdx.x - 64; // 0..EW*32-1
+    // with 8 epilogue warps, warps 2..5 take the even 32-column chunks, 6..9 the odd ones
+    const int c_first = EW == 8 ? ((warp - 2) >> 2) * 32 : 0;
+    constexpr int C_STEP = EW == 8 ? 64 : 32;
     const int rsub = lane >> 3, cf = (lane & 7) * 4;     // coalesced phase: 4 rows x 32 columns per instruction
     uint32_t li = 0;
     for (int i = blockIdx.x; i < items.total; i += gridDim.x, li++) {
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
       if (et == 0 && li == 0)
         TC_STAMP(41);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
         const int n = n0 + c0 + cf;
         const bool nok = n < N;
         uint32_t v[32];
@@ -609,11 +613,13 @@ __global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
       mbar_arrive(&acc_empty[b]);
       if (et == 0 && li == 0)
         TC_STAMP(42);
+      if (ATMA && et == 0 && li < 32)
+        TC_STAMP(48 + li); // per-item epilogue completion (the converter slots are free)
       if (S > 1) {
         // split-K: the last CTA to publish its partial tile sums all partials in split
         // order (deterministic) and runs the epilogue.
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         if (et == 0) {
           const int prev = atomicAdd(g.counters + tile, 1);
           const int last = (prev == S - 1);
@@ -621,13 +627,13 @@ __global__ void __launch_bounds__(ATMA ? TC_BASE_THREADS : TC_THREADS, 1)
             g.counters[tile] = 0;
           *s_last = last;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         const bool do_epilogue = *s_last != 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory"); // s_last is rewritten by the next item
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); // s_last is rewritten by the next item
         if (do_epilogue) {
           __threadfence();
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
             const int n = n0 + c0 + cf;
 #pragma unroll 2
             for (int j = 0; j < 8; j++) {
@@ -693,12 +699,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, int STAGES, bool ATMA>
+template <int BN, int STAGES, bool ATMA, int EW = 4>
 int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
-  using SM = TcSmem<BN, STAGES>;
+  using SM = TcSmem<BN, STAGES, EW>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SM::BYTES) != cudaSuccess)
       return -1;
     configured = true;
@@ -722,12 +728,18 @@ int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   it.epi_kind = epi_kind_of(g.epi);
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
   const CUtensorMap *am = ATMA ? reinterpret_cast<const CUtensorMap *>(g.amap) : map;
-  tc_gemm_kernel<BN, STAGES, ATMA><<<grid, ATMA ? TC_BASE_THREADS : TC_THREADS, SM::BYTES, st>>>(*map, *am, g, w.N, it);
+  tc_gemm_kernel<BN, STAGES, ATMA, EW><<<grid, tc_threads(EW, ATMA), SM::BYTES, st>>>(*map, *am, g, w.N, it);
   return 1;
 }
 template <int BN, int STAGES>
 int launch_tc(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   return g.amap ? launch_tc_a<BN, STAGES, true>(w, g, S, st) : launch_tc_a<BN, STAGES, false>(w, g, S, st);
+}
+// Short-K TMA-fed shapes (the SEANet tail): the epilogue is the bottleneck, so it gets
+// eight warps and the operand ring one stage less.
+template <int BN, int STAGES>
+int launch_tc_ew8(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
+  return launch_tc_a<BN, STAGES, true, 8>(w, g, S, st);
 }
 
 // Tile width and split-K for one GEMM.  Wide problems (many m tiles) take the widest
@@ -855,6 +867,17 @@ bool tc_gemm_supported(const GemmArgs &g) {
 int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant) {
   int bn, S;
   choose_tile(g, bn, S);
+  static const bool no_ew8 = getenv("PTTS_TC_NO_EW8") != nullptr;
+  if (g.amap && g.K <= 512 && g.M >= 4096 && g.N >= 64 && g.N <= 256 && S == 1 && !no_ew8) {
+    if (bn > 128)
+      bn = 128; // two n tiles re-read A from L2, but the epilogue gets 8 warps
+    if (bn == 128) {
+      *variant = "tcgen05_128x128_ew8";
+      return launch_tc_ew8<128, 2>(w, g, S, st);
+    }
+    *variant = "tcgen05_128x64_ew8";
+    return launch_tc_ew8<64, 3>(w, g, S, st);
+  }
   switch (bn) {
   case 256:
     *variant = "tcgen05_128x256";

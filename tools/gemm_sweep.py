@@ -31,6 +31,6 @@ for name, M, K, N, lda in only:
     fl = 2.0 * M * K * N
     reps = 5 if fl > 5e10 else 20
     a = rt.gemm_bench(M, K, N, path=1, reps=reps, lda=lda) if os.environ.get("SWEEP_CUDA_CORE") else float("nan")
-    b = rt.gemm_bench(M, K, N, path=2, reps=reps, lda=lda)
+    b = rt.gemm_bench(M, K, N, path=int(os.environ.get('GEMM_PATH', '4')), reps=reps, lda=lda)
     print(f"{name:20s} {M:7d} {K:5d} {N:6d} | {a:12.1f} {fl / a / 1e6:7.1f} | {b:11.1f} {fl / b / 1e6:7.1f}")
 rt.close()
