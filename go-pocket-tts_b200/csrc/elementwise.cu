@@ -223,7 +223,61 @@ int upsample_depthwise(const float *lat, const float *w, float *out, int rows,
   return 1;
 }
 
-// Final Conv1d (Cout = 1): one thread per output sample, weights in smem.
+// Final Conv1d (Cout = 1, Cin = 64, k <= 4) over channels-last rows.  A CTA owns 256
+// consecutive output rows: every input row (plus k-1 rows of left context) is read once
+// with fully coalesced float4 loads by a 16-lane group, which forms the row's k partial
+// dot products d_t[row] = sum_c w[t][c] * x[row][c]; then pcm[r] = bias + sum_t d_t[r-(k-1)+t].
+// (The one-thread-per-sample version read each row k times at a 256-byte lane stride.)
+constexpr int FC_ROWS = 256;
+__global__ void __launch_bounds__(256)
+    final_conv64_kernel(const float *x, int rows, int k, const float *w, float bias,
+                        const uint8_t *rowmask, int mask_div, float *pcm) {
+  __shared__ float d[4][FC_ROWS + 4];
+  const int lane16 = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const long r0 = (long)blockIdx.x * FC_ROWS;
+  float4 wt[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+    wt[t] = t < k ? *reinterpret_cast<const float4 *>(w + t * 64 + lane16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int span = FC_ROWS + k - 1;
+  for (int i = grp; i < span; i += 16) {
+    const long r = r0 - (k - 1) + i; // rows before the buffer start are the zeroed slack
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows)
+      v = *reinterpret_cast<const float4 *>(x + r * 64 + lane16 * 4);
+    float p[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      float a = v.x * wt[t].x;
+      a = fmaf(v.y, wt[t].y, a);
+      a = fmaf(v.z, wt[t].z, a);
+      a = fmaf(v.w, wt[t].w, a);
+      p[t] = a;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        p[t] += __shfl_xor_sync(0xffffffffu, p[t], o);
+    if (lane16 == 0) {
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        d[t][i] = p[t];
+    }
+  }
+  __syncthreads();
+  const long r = r0 + threadIdx.x;
+  if (r >= rows)
+    return;
+  float s = bias;
+  for (int t = 0; t < k; t++)
+    s += d[t][threadIdx.x + t]; // input row r-(k-1)+t sits at index threadIdx.x + t
+  if (rowmask && !rowmask[r / mask_div])
+    s = 0.0f;
+  pcm[r] = s;
+}
+
+// Generic fallback: one thread per output sample, weights in smem.
 __global__ void __launch_bounds__(256)
     final_conv_kernel(const float *x, int rows, int Cin, int k, const float *w,
                       float bias, const uint8_t *rowmask, int mask_div, float *pcm) {
@@ -255,6 +309,10 @@ int final_conv(const float *x, int rows, int Cin, int k, const float *w, float b
                const uint8_t *rowmask, int mask_div, float *pcm, cudaStream_t st) {
   if (rows <= 0)
     return 0;
+  if (Cin == 64 && k <= 4) {
+    final_conv64_kernel<<<(rows + FC_ROWS - 1) / FC_ROWS, 256, 0, st>>>(x, rows, k, w, bias, rowmask, mask_div, pcm);
+    return 1;
+  }
   final_conv_kernel<<<(rows + 255) / 256, 256, sizeof(float) * Cin * k, st>>>(
       x, rows, Cin, k, w, bias, rowmask, mask_div, pcm);
   return 1;

@@ -617,53 +617,70 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
         TC_STAMP(48 + li); // per-item epilogue completion (the converter slots are free)
       if (S > 1) {
         // split-K: the last CTA to publish its partial tile sums all partials in split
-        // order (deterministic) and runs the epilogue.
-        __threadfence();
+        // order (deterministic) and runs the epilogue.  One thread publishes for the CTA:
+        // the named barrier orders every epilogue thread's partial stores before its
+        // gpu-scope fence + counter increment (cumulativity), and after them on the reader.
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         if (et == 0) {
+          __threadfence();
           const int prev = atomicAdd(g.counters + tile, 1);
           const int last = (prev == S - 1);
           if (last)
             g.counters[tile] = 0;
+          __threadfence();
           *s_last = last;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         const bool do_epilogue = *s_last != 0;
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); // s_last is rewritten by the next item
         if (do_epilogue) {
-          __threadfence();
 #pragma unroll 1
           for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
             const int n = n0 + c0 + cf;
-#pragma unroll 2
-            for (int j = 0; j < 8; j++) {
-              const int row = q * 32 + j * 4 + rsub;
-              const int m = m0 + row;
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float *src = tile_ws + (long)row * BN + c0 + cf;
-#pragma unroll 4
-              for (int sp = 0; sp < S; sp++) {
-                const float4 u = __ldcg(reinterpret_cast<const float4 *>(src + (long)sp * TC_BM * BN));
-                a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 8; j0 += 4) {
+              float4 acc[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; jj++)
+                acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+              // 16 partial loads in flight per lane (4 rows x 4 splits), summed in split order
+              for (int sp0 = 0; sp0 < S; sp0 += 4) {
+                float4 u[4][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                  const float *src = tile_ws + (long)(q * 32 + (j0 + jj) * 4 + rsub) * BN + c0 + cf;
+#pragma unroll
+                  for (int t = 0; t < 4; t++)
+                    u[jj][t] = sp0 + t < S ? __ldcg(reinterpret_cast<const float4 *>(src + (long)(sp0 + t) * TC_BM * BN))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                  for (int t = 0; t < 4; t++) {
+                    acc[jj].x += u[jj][t].x; acc[jj].y += u[jj][t].y;
+                    acc[jj].z += u[jj][t].z; acc[jj].w += u[jj][t].w;
+                  }
               }
-              if (m < M && n < N) {
-                float4 o = epi_vec4(e, a, m, n);
-                if (!((rows >> (8 + j)) & 1))
-                  o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e.C)
-                  *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = o;
-                if (e.Cs.hi)
-                  split_store4(e.Cs, m, n, o);
-                if (e.C2 || e.C2s.hi) {
-                  float4 u;
-                  u.x = act_apply(o.x, ACT_ELU);
-                  u.y = act_apply(o.y, ACT_ELU);
-                  u.z = act_apply(o.z, ACT_ELU);
-                  u.w = act_apply(o.w, ACT_ELU);
-                  if (e.C2)
-                    *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u;
-                  if (e.C2s.hi)
-                    split_store4(e.C2s, m, n, u);
+#pragma unroll
+              for (int jj = 0; jj < 4; jj++) {
+                const int j = j0 + jj;
+                const int m = m0 + q * 32 + j * 4 + rsub;
+                if (m < M && n < N) {
+                  float4 o = epi_vec4(e, acc[jj], m, n);
+                  if (!((rows >> (8 + j)) & 1))
+                    o = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (e.C)
+                    *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = o;
+                  if (e.Cs.hi)
+                    split_store4(e.Cs, m, n, o);
+                  if (e.C2 || e.C2s.hi) {
+                    const float4 u2 = elu4(o);
+                    if (e.C2)
+                      *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u2;
+                    if (e.C2s.hi)
+                      split_store4(e.C2s, m, n, u2);
+                  }
                 }
               }
             }
@@ -765,6 +782,16 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
       bn /= 2;
     return;
   }
+  // Cost model (us), fitted to CTA timelines on B200 (tools/gemm_timeline.py):
+  //  * a k-block takes >= 0.58 us with TMA-fed operands (latency of the 3-4 stage ring),
+  //    1.3 us when A goes through the converter warps, or longer when the CTA's operand
+  //    bytes (~105 GB/s per SM) or the MMA issue rate bound it;
+  //  * the whole grid cannot pull more than ~8 TB/s through L2;
+  //  * the epilogue costs ~0.9 us per 32-column chunk; persistent CTAs overlap it with
+  //    the next item's main loop;
+  //  * the split-K fix-up (partials through L2, last CTA sums) is expensive: 5 us + 2.5 us
+  //    per 64 columns + 1 us per 64 columns and split.
+  const bool atma = g.amap != nullptr;
   double best = 1e30;
   bn = 32;
   S = 1;
@@ -781,14 +808,21 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
         continue;
       const long items = tiles * s;
       const long per_cta = (items + sms - 1) / sms; // items a CTA runs back to back
-      // us: operand bytes through L2 at ~65 GB/s per SM, or the MMA issue time, whichever
-      // is larger; + fixed cost per item (pipeline fill, epilogue); + split-K fix-up
-      const double t_mem = (128.0 + b) * 256.0 * kb_per / 65e3;
-      const double t_mma = 128.0 * b * 64.0 * 6.0 * kb_per / 7.0e6; // ~7 TFLOP/s issued per SM
-      double t = (t_mem > t_mma ? t_mem : t_mma) + 1.0 + 128.0 * b * 4.0 * 2.5 / 65e3;
+      const double kb_bytes = (128.0 + b) * 256.0;
+      double t_kb = atma ? 0.58 : 1.3;
+      if (kb_bytes / 105e3 > t_kb)
+        t_kb = kb_bytes / 105e3;
+      const double t_mma = 128.0 * b * 64.0 * 6.0 / 9.0e6; // ~9 TFLOP/s issued per SM
+      if (t_mma > t_kb)
+        t_kb = t_mma;
+      const double t_loop = t_kb * kb_per;
+      const double t_epi = 0.9 * (b / 32.0);
+      double t = 1.7 + per_cta * t_loop + t_epi + (per_cta > 1 ? (per_cta - 1) * (t_epi > t_loop ? t_epi - t_loop : 0.0) : 0.0);
+      const double l2_floor = (double)items * kb_per * kb_bytes / 8.0e6;
+      if (l2_floor > t)
+        t = l2_floor;
       if (s > 1)
-        t += 1.5 + 128.0 * b * 4.0 * (1 + s) / 65e3 / (double)s;
-      t = t * per_cta + 3.0;
+        t += 5.0 + (b / 64.0) * (2.5 + 1.0 * s);
       if (t < best) {
         best = t;
         bn = b;
