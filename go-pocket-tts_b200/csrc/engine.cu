@@ -63,6 +63,13 @@ Engine::~Engine() {
   q_cv.notify_all();
   if (sched.joinable())
     sched.join();
+  {
+    std::unique_lock<std::mutex> lk(fin_mu);
+    fin_stop = true;
+  }
+  fin_cv.notify_all();
+  if (finisher.joinable())
+    finisher.join();
   if (st) {
     cudaSetDevice(device);
     cudaStreamSynchronize(st);
@@ -82,6 +89,15 @@ Engine::~Engine() {
   };
   fh(h_row_slot); fh(h_row_pos); fh(h_ids); fh(h_off_a); fh(h_off_b); fh(h_off_c);
   fh(h_eos); fh(h_lat); fh(h_stage); fh(h_mrow_pos); fh(h_mrow_frame0); fh(h_mmask); fh(h_moff);
+  for (int i = 0; i < NPCM; i++) {
+    fh(h_pcm_ring[i]);
+    fh(h_lat_ring[i]);
+    for (cudaEvent_t e2 : {ev_dec0[i], ev_pcm_ready[i], ev_copied[i]})
+      if (e2)
+        cudaEventDestroy(e2);
+  }
+  if (st_copy)
+    cudaStreamDestroy(st_copy);
   for (auto &e : ev)
     if (e)
       cudaEventDestroy(e);
@@ -1039,6 +1055,15 @@ int Engine::finalize() {
     if ((rc = slack_alloc(&m_he[s], rows, res1[s].cout))) return rc;
   }
   if ((rc = slack_alloc(&m_pcm, rows, 1))) return rc;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < NPCM; i++) {
+    if ((rc = slack_alloc(&m_pcm_ring[i], rows, 1))) return rc;
+    CUDA_TRY(cudaMallocHost((void **)&h_pcm_ring[i], rows * sizeof(float)));
+    CUDA_TRY(cudaMallocHost((void **)&h_lat_ring[i], (size_t)mimi_frames_cap * ldim * sizeof(float)));
+    CUDA_TRY(cudaEventCreate(&ev_dec0[i]));
+    CUDA_TRY(cudaEventCreate(&ev_pcm_ready[i]));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+  }
   {
     // split planes of every Mimi activation that is a GEMM / conv input (8 zero slack rows
     // in front = the causal left context of the first segment)
@@ -1567,7 +1592,8 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
 // Mimi decode of a ragged batch (model.go:141-167 + mimi.go:719-789).
 // m_latin holds the gathered latent frames [total_frames, ldim].
 // ---------------------------------------------------------------------------
-int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) {
+int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, PcmJob *job) {
+  float *pcm = job ? m_pcm_ring[job->buf] : m_pcm;
   int64_t &nl = times.kernel_launches;
   const int P = mimi_pad;
   int Rb = 0;
@@ -1588,7 +1614,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
   }
   if (Rb > mimi_rows_cap || total_frames > mimi_frames_cap)
     PTTS_FAIL(PTTS_ENOMEM, "native-cuda: mimi group (%d frames, %d rows) exceeds workspace", total_frames, Rb);
-  cudaEventRecord(ev[5], st);
+  cudaEventRecord(job ? ev_dec0[job->buf] : ev[5], st);
   CUDA_TRY(cudaMemcpyAsync(d_mrow_pos, h_mrow_pos, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_mrow_frame0, h_mrow_frame0, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_mmask, h_mmask, (size_t)Rb, cudaMemcpyHostToDevice, st));
@@ -1695,13 +1721,33 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
     cur = m_ye[s];
     curs = &sm_ye[s];
   }
-  PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, m_pcm, st));
-  cudaEventRecord(ev[6], st);
+  PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, pcm, st));
   const int spb = div; // samples per base row
+  debug_bufs["mimi_pcm"] = {pcm, (size_t)rows};
+  times.mimi_frames += total_frames;
+  if (job) {
+    // asynchronous return: the copy stream takes over once the PCM is final; the
+    // finisher thread waits on ev_copied, fills the callers' buffers and completes them
+    const int k = job->buf;
+    cudaEventRecord(ev_pcm_ready[k], st);
+    CUDA_TRY(cudaStreamWaitEvent(st_copy, ev_pcm_ready[k], 0));
+    if (job->copy)
+      CUDA_TRY(cudaMemcpyAsync(h_pcm_ring[k], pcm, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, st_copy));
+    cudaEventRecord(ev_copied[k], st_copy);
+    for (size_t i = 0; i < segs.size(); i++)
+      job->segs[i].pcm_off = (size_t)(segs[i].row0 + P) * spb;
+    CUDA_TRY(cudaGetLastError());
+    if (prof_on) {
+      CUDA_TRY(cudaStreamSynchronize(st));
+      prof_collect();
+    }
+    return PTTS_OK;
+  }
+  cudaEventRecord(ev[6], st);
   if (d2h) {
     for (auto &sg : segs)
       if (sg.host_out)
-        CUDA_TRY(cudaMemcpyAsync(sg.host_out, m_pcm + (size_t)(sg.row0 + P) * spb,
+        CUDA_TRY(cudaMemcpyAsync(sg.host_out, pcm + (size_t)(sg.row0 + P) * spb,
                                  (size_t)sg.n_frames * up_stride * spb * 4, cudaMemcpyDeviceToHost, st));
   }
   cudaEventRecord(ev[7], st);
@@ -1713,8 +1759,83 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h) 
   times.mimi_ms += ms;
   cudaEventElapsedTime(&ms, ev[6], ev[7]);
   times.d2h_ms += ms;
-  times.mimi_frames += total_frames;
-  debug_bufs["mimi_pcm"] = {m_pcm, (size_t)rows};
+  return PTTS_OK;
+}
+
+// Scheduler path: gather + Mimi-decode the finished requests in workspace-sized groups
+// and hand each group to the finisher thread (PCM D2H and request completion overlap the
+// following AR steps).  The sequences can be released as soon as this returns: every read
+// of their frame history is already ordered on the stream.
+int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
+  ensure_finisher();
+  size_t i = 0;
+  const int max_segs = (mimi_rows_cap - up_stride * mimi_frames_cap) / mimi_pad;
+  while (i < reqs.size()) {
+    PcmJob job;
+    std::vector<MimiSeg> segs;
+    int tf = 0;
+    const int k = pcm_next;
+    {
+      std::unique_lock<std::mutex> lk(fin_mu);
+      fin_cv.wait(lk, [&] { return !buf_busy[k]; });
+      buf_busy[k] = true;
+    }
+    pcm_next = (pcm_next + 1) % NPCM;
+    job.buf = k;
+    while (i < reqs.size() && (int)segs.size() < max_segs) {
+      const std::shared_ptr<Request> &r = reqs[i];
+      const int n = r->seq->frames;
+      if (n <= 0 || n > mimi_frames_cap) {
+        std::unique_lock<std::mutex> lk(fin_mu);
+        buf_busy[k] = false;
+        PTTS_FAIL(PTTS_ENOMEM, "native-cuda: %d frames exceed mimi_group_frames %d", n, mimi_frames_cap);
+      }
+      if (tf + n > mimi_frames_cap)
+        break;
+      MimiSeg sg;
+      sg.n_frames = n;
+      sg.frame0 = tf;
+      sg.row0 = 0;
+      sg.host_out = nullptr;
+      for (int f = 0; f < n; f++)
+        h_moff[tf + f] = ((int64_t)r->seq->slot * (max_frames + 1) + f + 1) * ldim;
+      PcmJob::Seg js;
+      js.r = r;
+      js.lat_off = (size_t)tf * ldim;
+      js.n_frames = n;
+      job.segs.push_back(js);
+      if (!(r->cfg.flags & PTTS_REQ_NO_PCM_D2H) && r->pcm_out)
+        job.copy = true;
+      tf += n;
+      segs.push_back(sg);
+      i++;
+    }
+    int rc = PTTS_OK;
+    if (cudaMemcpyAsync(d_moff, h_moff, (size_t)tf * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      rc = PTTS_ECUDA;
+    if (rc == PTTS_OK) {
+      times.kernel_launches += gather_rows(d_hist, d_moff, m_latin, tf, ldim, st);
+      cudaMemcpyAsync(h_lat_ring[k], m_latin, (size_t)tf * ldim * 4, cudaMemcpyDeviceToHost, st);
+      // h_moff is rewritten by the next group: its H2D must have been consumed
+      rc = mimi_decode(segs, tf, false, &job);
+      if (rc == PTTS_OK && i < reqs.size())
+        cudaStreamSynchronize(st);
+    }
+    if (rc) {
+      job.rc = rc;
+      job.msg = last_error();
+      // make the events valid for the finisher even though nothing ran
+      cudaEventRecord(ev_dec0[k], st);
+      cudaEventRecord(ev_pcm_ready[k], st);
+      cudaStreamWaitEvent(st_copy, ev_pcm_ready[k], 0);
+      cudaEventRecord(ev_copied[k], st_copy);
+    }
+    {
+      std::unique_lock<std::mutex> lk(fin_mu);
+      fin_q.push_back(std::move(job));
+    }
+    fin_cv.notify_all();
+  }
   return PTTS_OK;
 }
 

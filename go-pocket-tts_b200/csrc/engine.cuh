@@ -197,6 +197,37 @@ struct Engine {
   uint8_t *h_mmask = nullptr;
   int64_t *d_moff = nullptr, *h_moff = nullptr;
 
+  // ---- asynchronous PCM return (scheduler path): a decode's PCM goes device ->
+  //      pinned ring on a copy stream while the next AR steps run; a finisher thread
+  //      copies it into the callers' buffers and completes the requests ----
+  static constexpr int NPCM = 3;
+  cudaStream_t st_copy = nullptr;
+  float *m_pcm_ring[NPCM] = {nullptr, nullptr, nullptr};
+  float *h_pcm_ring[NPCM] = {nullptr, nullptr, nullptr}, *h_lat_ring[NPCM] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_dec0[NPCM]{}, ev_pcm_ready[NPCM]{}, ev_copied[NPCM]{};
+  struct PcmJob {
+    int buf = 0, rc = 0;
+    bool copy = false;
+    std::string msg;
+    struct Seg {
+      std::shared_ptr<Request> r;
+      size_t pcm_off = 0, lat_off = 0;
+      int n_frames = 0;
+    };
+    std::vector<Seg> segs;
+  };
+  std::mutex fin_mu;
+  std::condition_variable fin_cv;
+  std::deque<PcmJob> fin_q;
+  bool buf_busy[NPCM] = {false, false, false};
+  std::thread finisher;
+  bool fin_running = false, fin_stop = false;
+  int pcm_next = 0;
+  double fin_mimi_ms = 0, fin_d2h_ms = 0;
+  void finisher_loop();
+  void ensure_finisher();
+  int decode_async(const std::vector<std::shared_ptr<Request>> &reqs);
+
   // ---- timing / counters ----
   ptts_stage_times times{};
   cudaEvent_t ev[8]{};
@@ -270,7 +301,9 @@ struct Engine {
            float *eos_out_host);
   int flow_head(int B, int lsd_steps);
   int get_tvec(int lsd_steps, float **out);
-  int mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h);
+  // d2h: copy each segment's PCM to its host_out and wait (stage API).  job != null: the
+  // asynchronous scheduler path (no wait; PCM lands in the job's pinned ring buffer).
+  int mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, PcmJob *job = nullptr);
   int decode_seqs(const std::vector<Seq *> &seqs, const std::vector<int> &first,
                   const std::vector<int> &count, const std::vector<float *> &outs,
                   bool d2h);

@@ -47,6 +47,57 @@ void Engine::ensure_sched() {
   }
 }
 
+void Engine::ensure_finisher() {
+  std::unique_lock<std::mutex> lk(fin_mu);
+  if (!fin_running) {
+    fin_running = true;
+    finisher = std::thread([this] { finisher_loop(); });
+  }
+}
+
+// Completes decoded requests: waits for the group's PCM to land in the pinned ring,
+// copies each request's samples / latents into its own buffers, signals the waiter.
+void Engine::finisher_loop() {
+  cudaSetDevice(device);
+  for (;;) {
+    PcmJob job;
+    {
+      std::unique_lock<std::mutex> lk(fin_mu);
+      fin_cv.wait(lk, [&] { return fin_stop || !fin_q.empty(); });
+      if (fin_q.empty())
+        break; // fin_stop and drained
+      job = std::move(fin_q.front());
+      fin_q.pop_front();
+    }
+    const int k = job.buf;
+    cudaError_t ce = cudaEventSynchronize(ev_copied[k]);
+    if (ce != cudaSuccess && job.rc == PTTS_OK) {
+      job.rc = PTTS_ECUDA;
+      job.msg = std::string("cuda: mimi decode failed: ") + cudaGetErrorString(ce);
+    }
+    float ms = 0;
+    if (job.rc == PTTS_OK && cudaEventElapsedTime(&ms, ev_dec0[k], ev_pcm_ready[k]) == cudaSuccess) {
+      std::unique_lock<std::mutex> lk(fin_mu);
+      fin_mimi_ms += ms;
+    }
+    const int spf = info.samples_per_frame;
+    for (auto &sg : job.segs) {
+      Request &r = *sg.r;
+      if (job.rc == PTTS_OK) {
+        r.latents.assign(h_lat_ring[k] + sg.lat_off, h_lat_ring[k] + sg.lat_off + (size_t)sg.n_frames * ldim);
+        if (!(r.cfg.flags & PTTS_REQ_NO_PCM_D2H) && r.pcm_out)
+          memcpy(r.pcm_out, h_pcm_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(float));
+      }
+      complete(sg.r, job.rc, job.rc ? job.msg.c_str() : nullptr);
+    }
+    {
+      std::unique_lock<std::mutex> lk(fin_mu);
+      buf_busy[k] = false;
+    }
+    fin_cv.notify_all();
+  }
+}
+
 void Engine::sched_loop() {
   cudaSetDevice(device);
   std::vector<std::shared_ptr<Request>> active, pending;
@@ -235,30 +286,19 @@ void Engine::sched_loop() {
                     iter - pending.front()->finished_at_iter >= 16 ||
                     (int)(active.size() + pending.size()) >= max_batch);
     if (trigger) {
-      std::vector<Seq *> seqs;
-      std::vector<int> first, count;
-      std::vector<float *> outs;
-      for (auto &r : pending) {
-        int n = r->seq->frames;
-        r->latents.resize((size_t)n * ldim);
-        cudaMemcpyAsync(r->latents.data(),
-                        d_hist + ((size_t)r->seq->slot * (max_frames + 1) + 1) * ldim,
-                        (size_t)n * ldim * 4, cudaMemcpyDeviceToHost, st);
-        seqs.push_back(r->seq);
-        first.push_back(0);
-        count.push_back(n);
-        outs.push_back((r->cfg.flags & PTTS_REQ_NO_PCM_D2H) ? nullptr : r->pcm_out);
-      }
-      int rc = decode_seqs(seqs, first, count, outs, true);
-      cudaStreamSynchronize(st);
-      std::string msg = rc ? last_error() : "";
       for (auto &r : pending) {
         r->res.n_frames = r->seq->frames;
         r->res.n_samples = (int64_t)r->seq->frames * info.samples_per_frame;
+      }
+      int rc = decode_async(pending);
+      std::string msg = rc ? last_error() : "";
+      for (auto &r : pending) {
+        // every read of this sequence's state is ordered on the stream already
         seq_free(r->seq);
         delete reinterpret_cast<ptts_seq *>(r->seq);
         r->seq = nullptr;
-        complete(r, rc, rc ? msg.c_str() : nullptr);
+        if (rc && !r->done)
+          complete(r, rc, msg.c_str()); // requests of a group that never reached the finisher
       }
       pending.clear();
       pending_frames = 0;
@@ -621,10 +661,16 @@ int ptts_stage_times_get(ptts_engine *e, ptts_stage_times *out, int32_t reset) {
   if (!e)
     PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
   std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
-  if (out)
+  if (out) {
     *out = e->impl.times;
-  if (reset)
+    std::unique_lock<std::mutex> lk(e->impl.fin_mu);
+    out->mimi_ms += e->impl.fin_mimi_ms;
+  }
+  if (reset) {
     e->impl.times = ptts_stage_times{};
+    std::unique_lock<std::mutex> lk(e->impl.fin_mu);
+    e->impl.fin_mimi_ms = 0;
+  }
   return PTTS_OK;
 }
 
