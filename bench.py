@@ -65,6 +65,17 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
 
 
+def load_ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel classes captured
+    with `ncu --set full`; profiles/ncu_traffic_r01.json records the command and the launches averaged."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        d = json.load(f)
+    return {k: v for k, v in d.get("classes", {}).items()}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -271,27 +282,35 @@ def main():
         kc = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share_of_profiled": round(v["ms"] / tot_ms, 4),
                   "tflops": round(v["flops"] / (v["ms"] * 1e9), 3) if v["ms"] else 0.0,
                   "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] else 0.0} for k, v in classes}
-        top, tv = classes[0]
         ridge = peaks["tf_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)  # FLOP per byte
-        intensity = tv["flops"] / max(tv["bytes"], 1.0)
-        common = {"kernel": top, "per_launch_us": 1e3 * tv["ms"] / tv["launches"], "launches": tv["launches"],
-                  "share_of_profiled_gpu_time": tv["ms"] / tot_ms, "arithmetic_intensity_flop_per_byte": intensity,
-                  "traffic": None,
-                  "measured_over": "one timed step with a CUDA-event pair around every launch on the engine "
-                                   "stream (CUDA graphs off); algorithmic flops/bytes per launch summed",
-                  "profiled_step_ms": ms3}
-        if intensity < ridge:
-            ach = tv["bytes"] / (tv["ms"] * 1e6)
-            roofline = dict(common, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
+        ncu_traffic = load_ncu_traffic()
+
+        def roofline_of(name, tv):
+            """Roofline entry of one kernel class: algorithmic bytes (or flops) / event-timed duration."""
+            intensity = tv["flops"] / max(tv["bytes"], 1.0)
+            common = {"kernel": name, "per_launch_us": 1e3 * tv["ms"] / max(tv["launches"], 1),
+                      "launches": tv["launches"], "share_of_profiled_gpu_time": tv["ms"] / tot_ms,
+                      "arithmetic_intensity_flop_per_byte": intensity,
+                      "traffic": ncu_traffic.get(name)}
+            if intensity < ridge:
+                ach = tv["bytes"] / (tv["ms"] * 1e6)
+                return dict(common, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
                             frac=ach / peaks["hbm_gbs"], peak_source=peaks["source"],
                             also_tflops=tv["flops"] / (tv["ms"] * 1e9))
-        else:
             ach = tv["flops"] / (tv["ms"] * 1e9)
-            roofline = dict(common, bound="tensor", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                            frac=ach / peaks["tf_sustained"],
-                            peak_source=peaks["source"] + " (sustained bf16; kernel timed inside a long step)",
-                            note="split-bf16 operands: 3 tensor-core products per useful fp32-accurate product, "
-                                 "so the useful ceiling is peak/3")
+            return dict(common, bound="tensor", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                        frac=ach / peaks["tf_sustained"], issued_tflops=3.0 * ach,
+                        frac_issued=3.0 * ach / peaks["tf_sustained"],
+                        peak_source=peaks["source"] + " (sustained bf16; kernel timed inside a long step)",
+                        note="split-bf16 operands: 3 tensor-core products per useful fp32-accurate product "
+                             "(issued = 3 x achieved), so the useful ceiling is peak/3")
+
+        top, tv = classes[0]
+        roofline = dict(roofline_of(top, tv),
+                        measured_over="one timed step with a CUDA-event pair around every launch on the engine "
+                                      "stream (CUDA graphs off); algorithmic flops/bytes per launch summed",
+                        profiled_step_ms=ms3)
+        roofline_by_class = {k: roofline_of(k, v) for k, v in classes if v["ms"] > 0 and (v["flops"] or v["bytes"])}
         alg_flops = 2.0 * (info.macs_ar_frame + info.macs_mimi_frame) * frames
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -301,7 +320,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
                     "d2h_bytes_per_step": int(samples2 * 4 / max(args.steps, 1))},
             "gpu_launches": int(st["kernel_launches"]),
-            "roofline": roofline,
+            "roofline": roofline, "roofline_by_class": roofline_by_class,
             "kernel_classes": kc, "gemm_shapes": shapes,
             "stage_ms_rank0": {k: round(st[k], 2) for k in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")},
             "mean_batch_occupancy": st["step_rows"] / max(st["steps"], 1),

@@ -16,6 +16,7 @@
 // phase 1 and 3 read whole 128-byte lines.
 #include "kernels.cuh"
 #include "split.cuh"
+#include "launch.cuh"
 #include <math.h>
 
 namespace ptts {
@@ -132,6 +133,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_kernel(const float *qkv, long ldq, float *out, long ldo,
                            const int32_t *row_slot, const int32_t *row_pos,
                            KvGeom kv, int layer, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   extern __shared__ float smem[];
   __shared__ float red[ATT_THREADS / 32];
   __shared__ float4 pv[8 * 16];
@@ -358,8 +361,7 @@ int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
     return 0;
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
-  attention_paged_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, row_slot,
-                                                        row_pos, kv, layer, sp);
+  launch_k(attention_paged_kernel, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv, layer, sp);
   return 1;
 }
 
@@ -389,6 +391,8 @@ __global__ void __launch_bounds__(256)
     rope_kv_append_kernel(float *qkv, const int32_t *row_slot,
                           const int32_t *row_pos, const float *cosT,
                           const float *sinT, KvGeom kv, int layer) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   const int r = blockIdx.x;
   const int slot = row_slot[r], pos = row_pos[r];
   if (pos < 0)
@@ -429,7 +433,7 @@ int rope_kv_append(float *qkv, int rows, const int32_t *row_slot,
                    const KvGeom &kv, int layer, cudaStream_t st) {
   if (rows <= 0)
     return 0;
-  rope_kv_append_kernel<<<rows, 256, 0, st>>>(qkv, row_slot, row_pos, cosT, sinT, kv, layer);
+  launch_k(rope_kv_append_kernel, dim3(rows), dim3(256), 0, st, qkv, row_slot, row_pos, cosT, sinT, kv, layer);
   return 1;
 }
 

@@ -1,9 +1,14 @@
 // elementwise.cu — row-wise and gather/scatter kernels of the hot path.
 #include "kernels.cuh"
 #include "split.cuh"
+#include "launch.cuh"
 #include <math.h>
 
 namespace ptts {
+
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void pdl_set(bool on) { g_pdl = on; }
 
 // LayerNorm (+ optional adaLN modulate).  One warp per row, two-pass fp32
 // statistics about the mean (reference: fp64 mean / biased variance,
@@ -12,6 +17,8 @@ __global__ void __launch_bounds__(256)
     layernorm_kernel(const float *x, long ldx, float *out, long ldo, int rows,
                      int D, const float *w, const float *b, float eps,
                      const float *scale, const float *shift, long ldmod, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows)
@@ -66,8 +73,7 @@ int layernorm(const float *x, long ldx, float *out, long ldo, int rows, int D,
   if (rows <= 0)
     return 0;
   int ctas = (rows + 7) / 8;
-  layernorm_kernel<<<ctas, 256, 0, st>>>(x, ldx, out, ldo, rows, D, w, b, eps, scale,
-                                         shift, ldmod, sp);
+  launch_k(layernorm_kernel, dim3(ctas), dim3(256), 0, st, x, ldx, out, ldo, rows, D, w, b, eps, scale, shift, ldmod, sp);
   return 1;
 }
 
@@ -92,6 +98,8 @@ int embed_gather(const int64_t *ids, const float *table, float *out, int rows,
 
 __global__ void nan_to_bos_kernel(const float *frames, const float *bos, float *out,
                                   int n, int ldim, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
@@ -106,12 +114,14 @@ int nan_to_bos(const float *frames, const float *bos, float *out, int rows,
   int n = rows * ldim;
   if (n <= 0)
     return 0;
-  nan_to_bos_kernel<<<(n + 255) / 256, 256, 0, st>>>(frames, bos, out, n, ldim, sp);
+  launch_k(nan_to_bos_kernel, dim3((n + 255) / 256), dim3(256), 0, st, frames, bos, out, n, ldim, sp);
   return 1;
 }
 
 __global__ void add_vec_silu_kernel(const float *a, const float *tvec, float *out,
                                     int n, int C, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
@@ -126,11 +136,13 @@ int add_vec_silu(const float *a, const float *tvec, float *out, int rows, int C,
   int n = rows * C;
   if (n <= 0)
     return 0;
-  add_vec_silu_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, tvec, out, n, C, sp);
+  launch_k(add_vec_silu_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a, tvec, out, n, C, sp);
   return 1;
 }
 
 __global__ void copy_rows_kernel(const float *src, float *dst, int n, int width, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
@@ -143,12 +155,14 @@ int copy_rows(const float *src, float *dst, int rows, int width, cudaStream_t st
   int n = rows * width;
   if (n <= 0)
     return 0;
-  copy_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, width, sp);
+  launch_k(copy_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, src, dst, n, width, sp);
   return 1;
 }
 
 __global__ void gather_rows_kernel(const float *src, const int64_t *off, float *dst,
                                    int rows, int width, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * width)
     return;
@@ -163,11 +177,13 @@ int gather_rows(const float *src, const int64_t *src_off, float *dst, int rows,
   int n = rows * width;
   if (n <= 0)
     return 0;
-  gather_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, src_off, dst, rows, width, sp);
+  launch_k(gather_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, src, src_off, dst, rows, width, sp);
   return 1;
 }
 __global__ void scatter_rows_kernel(const float *src, float *dst, const int64_t *off,
                                     int rows, int width) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * width)
     return;
@@ -179,7 +195,7 @@ int scatter_rows(const float *src, float *dst, const int64_t *dst_off, int rows,
   int n = rows * width;
   if (n <= 0)
     return 0;
-  scatter_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, dst_off, rows, width);
+  launch_k(scatter_rows_kernel, dim3((n + 255) / 256), dim3(256), 0, st, src, dst, dst_off, rows, width);
   return 1;
 }
 

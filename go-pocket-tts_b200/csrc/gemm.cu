@@ -13,6 +13,7 @@
 //               path replaces this for the batched regime; see DESIGN.md.)
 #include "kernels.cuh"
 #include "gemm_epi.cuh"
+#include "launch.cuh"
 #include <math.h>
 
 namespace ptts {
@@ -33,6 +34,8 @@ __device__ __forceinline__ float4 ldg_stream(const float *p) {
 // memory system idle (B=1 ran at 0.7 TB/s that way).  K <= 128*KU is a single trip.
 template <int MR, int NC, int KU>
 __global__ void __launch_bounds__(256) gemv_kernel(GemmArgs g) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -335,17 +338,17 @@ static void launch_gemv(const GemmArgs &g, cudaStream_t st) {
     int ctas = (g.N / 2 + warps_per_cta - 1) / warps_per_cta;
     if (ctas > 148 * 8)
       ctas = 148 * 8;
-    gemv_kernel<MR, 2, 4><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+    launch_k(gemv_kernel<MR, 2, 4>, dim3(ctas), dim3(warps_per_cta * 32), 0, st, g);
   } else {
     int ctas = (g.N + warps_per_cta - 1) / warps_per_cta;
     if (ctas > 148 * 8)
       ctas = 148 * 8;
     if (g.K <= 512)
-      gemv_kernel<MR, 1, 4><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+      launch_k(gemv_kernel<MR, 1, 4>, dim3(ctas), dim3(warps_per_cta * 32), 0, st, g);
     else if (g.K <= 1024 || MR > 2)
-      gemv_kernel<MR, 1, 8><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+      launch_k(gemv_kernel<MR, 1, 8>, dim3(ctas), dim3(warps_per_cta * 32), 0, st, g);
     else
-      gemv_kernel<MR, 1, 16><<<ctas, warps_per_cta * 32, 0, st>>>(g);
+      launch_k(gemv_kernel<MR, 1, 16>, dim3(ctas), dim3(warps_per_cta * 32), 0, st, g);
   }
 }
 
@@ -411,6 +414,8 @@ int gemm(const GemmArgs &g, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
     rowdot_kernel(const float *A, long lda, const float *w, float bias0, int M,
                   int K, float *out) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= M)
@@ -437,7 +442,7 @@ int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
   if (M <= 0)
     return 0;
   int ctas = (M + 7) / 8;
-  rowdot_kernel<<<ctas, 256, 0, st>>>(A, lda, w, bias0, M, K, out);
+  launch_k(rowdot_kernel, dim3(ctas), dim3(256), 0, st, A, lda, w, bias0, M, K, out);
   return 1;
 }
 

@@ -1,0 +1,39 @@
+// launch.cuh — programmatic dependent launch (PDL) for the AR-step kernel chain.
+//
+// One AR frame is ~79 dependent launches of short kernels; with plain stream order every
+// kernel pays the launch latency and its own prologue after the previous grid has fully
+// drained.  Kernels on that path start with PDL_TRIGGER (lets the next grid be scheduled
+// as SMs free up) and PDL_WAIT (blocks until the previous grid has completed and its
+// writes are visible) before they touch any global memory another kernel produces or
+// reads; the tcgen05 GEMM runs its prologue and prefetches its (constant) weight tiles
+// in front of PDL_WAIT.  Both instructions are no-ops in a launch without the attribute.
+#pragma once
+#include <cuda_runtime.h>
+#include <utility>
+
+namespace ptts {
+
+#define PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+// Set by the engine around the AR step (graph capture keeps the programmatic edges).
+bool pdl_enabled();
+void pdl_set(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+} // namespace ptts

@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "gemm_epi.cuh"
 #include "split.cuh"
+#include "launch.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
   int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
+  PDL_TRIGGER(); // the next grid may be scheduled; it blocks in its own PDL_WAIT until this one is done
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.M, N = g.N, K = g.K;
   const int S = items.S;
@@ -361,36 +363,64 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     TC_STAMP(1);
 
   if (warp == 0) {
-    // ===== TMA producer: W hi + lo tiles of every k-block of every item =====
+    // ===== TMA producer: W (and, ATMA, A) hi + lo tiles of every k-block of every item.
+    // The weight tiles of the first ring pass do not depend on the previous kernel, so
+    // they are requested before PDL_WAIT; their A tiles follow once it returns. =====
     if (lane == 0) {
-      long it = 0;
-      for (long i = blockIdx.x; i < items.total; i += gridDim.x) {
+      uint32_t it = 0;
+      bool waited = false;
+      int npend = 0;
+      int pend_s[STAGES], pend_k0[STAGES], pend_m0[STAGES];
+      auto load_a = [&](int s, int k0, int m0) {
+        uint8_t *st = smem + s * SM::STAGE;
+        if (g.a_cin > 0) { // conv over overlapping rows: k = tap * cin + c
+          const int tap = k0 / g.a_cin, c0 = k0 - tap * g.a_cin;
+          tma_load_3d(st, &amap, &full[s], c0, tap, m0);
+          tma_load_3d(st + SM::A_TILE, &amap, &full[s], c0, tap, g.a_lo_row + m0);
+        } else {
+          tma_load_2d(st, &amap, &full[s], k0, m0);
+          tma_load_2d(st + SM::A_TILE, &amap, &full[s], k0, g.a_lo_row + m0);
+        }
+      };
+      auto dep_wait = [&]() {
+        PDL_WAIT();
+        waited = true;
+        for (int i = 0; i < npend; i++)
+          load_a(pend_s[i], pend_k0[i], pend_m0[i]);
+        npend = 0;
+      };
+      for (int i = blockIdx.x; i < items.total; i += gridDim.x) {
         int m0, n0, kb_begin, nkb, z;
         int tile;
         items.decode(i, m0, n0, kb_begin, nkb, z, tile, BN);
         for (int kb = 0; kb < nkb; kb++, it++) {
           const int s = (int)(it % STAGES);
-          if (it >= STAGES)
+          if (it >= STAGES) {
+            if (!waited)
+              dep_wait();
             mbar_wait(&empty[s], (uint32_t)((it / STAGES) - 1) & 1);
+          }
           uint8_t *st = smem + s * SM::STAGE;
           if (it < 32)
             TC_STAMP(96 + it);
           mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE + (ATMA ? 2 * SM::A_TILE : 0));
           const int k0 = (kb_begin + kb) * TC_BK;
           if (ATMA) {
-            if (g.a_cin > 0) { // conv over overlapping rows: k = tap * cin + c
-              const int tap = k0 / g.a_cin, c0 = k0 - tap * g.a_cin;
-              tma_load_3d(st, &amap, &full[s], c0, tap, m0);
-              tma_load_3d(st + SM::A_TILE, &amap, &full[s], c0, tap, g.a_lo_row + m0);
-            } else {
-              tma_load_2d(st, &amap, &full[s], k0, m0);
-              tma_load_2d(st + SM::A_TILE, &amap, &full[s], k0, g.a_lo_row + m0);
+            if (waited)
+              load_a(s, k0, m0);
+            else {
+              pend_s[npend] = s;
+              pend_k0[npend] = k0;
+              pend_m0[npend] = m0;
+              npend++;
             }
           }
           tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], k0, n0);
           tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], k0, n_rows_hi + n0);
         }
       }
+      if (!waited)
+        dep_wait();
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -435,6 +465,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     }
   } else if (warp >= tc_base_threads(EW) / 32) {
     // ===== A converters: fp32 global -> (hi, lo) bf16 swizzled smem =====
+    PDL_WAIT();
     const int ct = threadIdx.x - tc_base_threads(EW);
     // PF k-blocks of A stay in flight per thread, across item boundaries.
     constexpr int PF = 3;
@@ -521,6 +552,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     }
   } else {
     // ===== epilogue warps: TMEM -> per-warp smem transpose -> coalesced fused epilogue =====
+    PDL_WAIT();
     const GemmEpi &e = g.epi;
     const int q = warp & 3; // TMEM lane quarter this warp may access
     const uint32_t stg_addr = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
@@ -745,7 +777,8 @@ int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   it.epi_kind = epi_kind_of(g.epi);
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
   const CUtensorMap *am = ATMA ? reinterpret_cast<const CUtensorMap *>(g.amap) : map;
-  tc_gemm_kernel<BN, STAGES, ATMA, EW><<<grid, tc_threads(EW, ATMA), SM::BYTES, st>>>(*map, *am, g, w.N, it);
+  launch_k(tc_gemm_kernel<BN, STAGES, ATMA, EW>, dim3(grid), dim3(tc_threads(EW, ATMA)), SM::BYTES, st, *map, *am, g,
+           w.N, it);
   return 1;
 }
 template <int BN, int STAGES>
