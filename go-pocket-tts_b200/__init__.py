@@ -109,7 +109,7 @@ EXPORTS = [
     "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
-    "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force",
+    "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
 ]
 
 _lib = None
@@ -158,6 +158,7 @@ def lib() -> C.CDLL:
     L.ptts_debug_fetch.restype = C.c_int64
     L.ptts_profile_enable.argtypes = [vp, C.c_int32]
     L.ptts_debug_tc_force.argtypes = [C.c_int32, C.c_int32]
+    L.ptts_debug_gemm_tma.argtypes = [vp, fp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, fp, fp]
     L.ptts_debug_gemm_bench.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     L.ptts_debug_gemm.argtypes = [vp, fp, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, C.c_int32, fp]
     L.ptts_profile_report.argtypes = [vp, C.c_char_p, C.c_int32]
@@ -454,6 +455,18 @@ class NativeCudaRuntime:
         _check(self._lib.ptts_debug_gemm(self._h, _fptr(A), A.shape[0], A.shape[1], _fptr(W), W.shape[0],
                                          _fptr(b), act, path, _fptr(out)))
         return out
+
+    def debug_gemm_tma(self, A, W, bias=None, act: int = 0, taps: int = 1, want_split: bool = False):
+        """TMA-fed tcgen05 GEMM (A split into bf16 planes on the device).  taps > 1: causal conv form,
+        W is [N, taps*cin].  Returns C, or (C, split copy of C) when want_split."""
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        out = np.empty((A.shape[0], W.shape[0]), dtype=np.float32)
+        sp = np.empty_like(out) if want_split else None
+        _check(self._lib.ptts_debug_gemm_tma(self._h, _fptr(A), A.shape[0], A.shape[1], taps, _fptr(W), W.shape[0],
+                                             _fptr(b), act, _fptr(out), _fptr(sp)))
+        return (out, sp) if want_split else out
 
     def tc_force(self, bn: int = 0, s: int = 0):
         _check(self._lib.ptts_debug_tc_force(bn, s))

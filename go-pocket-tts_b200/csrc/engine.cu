@@ -351,6 +351,80 @@ int Engine::debug_gemm(const float *A, int M, int K, const float *W, int N, cons
   return rc;
 }
 
+// TMA-fed GEMM unit-test hook: A [M, cin] is split into bf16 planes on the device and
+// fetched by TMA; taps > 1 runs the implicit-GEMM conv form (W is [N, taps*cin], row m
+// sees rows m-taps+1 .. m, rows < 0 are the zero slack).  C (fp32) and, if c_split is
+// not null, the split-plane copy of the same output (hi + lo, reconstructed on the host).
+int Engine::debug_gemm_tma(const float *A, int M, int cin, int taps, const float *W, int N, const float *bias,
+                           int act, float *C, float *c_split) {
+  if (!tc_on)
+    PTTS_FAIL(PTTS_ESTATE, "native-cuda: tensor-core path is disabled");
+  const int K = cin * taps;
+  float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
+  CUDA_TRY(cudaMalloc(&dA, (size_t)M * cin * 4));
+  CUDA_TRY(cudaMalloc(&dW, (size_t)N * K * 4));
+  CUDA_TRY(cudaMalloc(&dC, (size_t)M * N * 4));
+  CUDA_TRY(cudaMemcpy(dA, A, (size_t)M * cin * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dW, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
+  if (bias) {
+    CUDA_TRY(cudaMalloc(&dB, (size_t)N * 4));
+    CUDA_TRY(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+  }
+  ActSplit in, out;
+  int rc = make_act(in, M, cin, 8);
+  if (rc == PTTS_OK)
+    rc = make_act(out, M, N, 0);
+  std::vector<float> hw(W, W + (size_t)N * K);
+  const int saved_min = tc_min_m;
+  tc_min_m = 1;
+  if (rc == PTTS_OK)
+    rc = make_tc(dW, hw, N, K);
+  GemmArgs g;
+  g.W = dW; g.ldw = K; g.M = M; g.N = N; g.K = K; g.lda = cin;
+  g.epi.bias = dB; g.epi.act = act; g.epi.C = dC; g.epi.ldc = N;
+  if (c_split)
+    g.epi.Cs = out.out();
+  if (rc == PTTS_OK) {
+    copy_rows(dA, dA, M, cin, st, in.out());
+    if (taps > 1) {
+      void *cm = nullptr;
+      rc = make_conv_map(in, cin, taps, &cm);
+      g.amap = cm;
+      g.a_lo_row = (int)in.plane_rows;
+      g.a_cin = cin;
+    } else
+      use_act(g, in);
+  }
+  if (rc == PTTS_OK && (!tc_map.count(dW) || !tc_gemm_supported(g))) {
+    set_error("native-cuda: debug_gemm_tma: shape [%d,%d]x[%d] not supported by the tcgen05 path", M, K, N);
+    rc = PTTS_EINVAL;
+  }
+  if (rc == PTTS_OK) {
+    times.kernel_launches += pgemm(g);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+      e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("cuda: debug_gemm_tma failed: %s", cudaGetErrorString(e));
+      rc = PTTS_ECUDA;
+    } else {
+      cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+      if (c_split) {
+        std::vector<uint16_t> hi((size_t)M * N), lo((size_t)M * N);
+        cudaMemcpy(hi.data(), out.p, hi.size() * 2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(lo.data(), out.p + out.plane_rows * (long)N, lo.size() * 2, cudaMemcpyDeviceToHost);
+        for (size_t i2 = 0; i2 < hi.size(); i2++)
+          c_split[i2] = bf16_to_f32(hi[i2]) + bf16_to_f32(lo[i2]);
+      }
+    }
+  }
+  tc_min_m = saved_min;
+  tc_map.erase(dW);
+  cudaFree(dA); cudaFree(dW); cudaFree(dC);
+  if (dB) cudaFree(dB);
+  return rc;
+}
+
 // Times one GEMM shape on device-resident data (CUDA events around `reps`
 // back-to-back launches).  lda < K exercises the overlapping-row conv form.
 int Engine::debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us) {

@@ -135,6 +135,8 @@ struct Engine {
   int debug_gemm(const float *A, int M, int K, const float *W, int N, const float *bias, int act,
                  int path, float *C);
   int debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us);
+  int debug_gemm_tma(const float *A, int M, int cin, int taps, const float *W, int N, const float *bias, int act,
+                     float *C, float *c_split);
 
   // split activation planes (A operands of the tcgen05 GEMMs)
   ActSplit s_nrm, s_att, s_ff, s_in, s_last, s_sy, s_cur, s_h, s_h2;

@@ -714,6 +714,15 @@ int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const 
   return e->impl.debug_gemm(A, M, K, W, N, bias, act, path, C);
 }
 
+int ptts_debug_gemm_tma(ptts_engine *e, const float *A, int32_t M, int32_t cin, int32_t taps, const float *W, int32_t N,
+                        const float *bias, int32_t act, float *C, float *c_split) {
+  if (!e || !A || !W || !C || M <= 0 || N <= 0 || cin <= 0 || taps <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: debug_gemm_tma: bad arguments");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  cudaSetDevice(e->impl.device);
+  return e->impl.debug_gemm_tma(A, M, cin, taps, W, N, bias, act, C, c_split);
+}
+
 int ptts_debug_tc_force(int32_t bn, int32_t s) {
   ptts::tc_force_tile(bn, s);
   return PTTS_OK;

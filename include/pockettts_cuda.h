@@ -232,6 +232,11 @@ int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const 
                     const float *bias, int32_t act, int32_t path, float *C);
 /* Times one GEMM shape on device data: average microseconds over `reps`
  * launches (CUDA events on the engine stream).  lda < K = overlapping rows. */
+/* Unit-test hook of the TMA-fed GEMM: A [M,cin] is split into bf16 planes on the device;
+ * taps > 1 = implicit-GEMM causal conv (W [N, taps*cin], row m sees rows m-taps+1..m, rows < 0 zero).
+ * c_split (optional) receives the split-plane copy of the output (hi + lo). */
+int ptts_debug_gemm_tma(ptts_engine *e, const float *A, int32_t M, int32_t cin, int32_t taps, const float *W,
+                        int32_t N, const float *bias, int32_t act, float *C, float *c_split);
 /* Sweep hook: force tile width / split-K of the tcgen05 GEMM (bn <= 0 restores the heuristic). */
 int ptts_debug_tc_force(int32_t bn, int32_t s);
 int ptts_debug_gemm_bench(ptts_engine *e, int32_t M, int32_t K, int32_t N, int32_t lda, int32_t path,

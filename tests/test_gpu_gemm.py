@@ -67,3 +67,29 @@ def test_split_k_is_deterministic(small_rt):
     x = small_rt.debug_gemm(A, W, b, path=1)
     y = small_rt.debug_gemm(A, W, b, path=1)
     np.testing.assert_array_equal(x, y)
+
+
+# ---- TMA-fed A operand (bf16 hi/lo planes written by the producer, both operands by TMA) ----
+@pytest.mark.parametrize("M,K,N", [(16, 32, 1024), (300, 1024, 3072), (464, 4096, 1024), (25000, 512, 1536),
+                                   (40000, 32, 64), (9, 512, 32), (2000, 2048, 512)])
+def test_tma_fed_dense(small_rt, M, K, N):
+    A, W, b = _case(M, K, N, M + N + 2)
+    got, sp = small_rt.debug_gemm_tma(A, W, b, want_split=True)
+    _check(got, A, W, b, 0, 4e-5)
+    # the split copy carries ~16 mantissa bits of the fp32 output
+    assert np.abs(sp - got).max() <= 2.0 ** -15 * max(1.0, np.abs(got).max())
+
+
+@pytest.mark.parametrize("M,cin,taps,N", [(5000, 64, 3, 32), (3000, 128, 3, 64), (4097, 128, 2, 256),
+                                          (700, 512, 7, 512), (1500, 256, 2, 640), (20000, 32, 1, 64)])
+def test_tma_fed_causal_conv_form(small_rt, M, cin, taps, N):
+    """Implicit-GEMM conv over overlapping rows through the 3-D TMA map {cin, taps, rows}:
+    out[m] = sum_t W[:, t*cin:(t+1)*cin] @ x[m - (taps-1) + t], rows before 0 are zero."""
+    rng = np.random.default_rng(M + N)
+    x = rng.standard_normal((M, cin)).astype(np.float32)
+    W = (rng.standard_normal((N, taps * cin)) / np.sqrt(taps * cin)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32) * 0.1
+    xp = np.concatenate([np.zeros((taps - 1, cin), np.float32), x])
+    im2col = np.concatenate([xp[t:t + M] for t in range(taps)], axis=1)  # [M, taps*cin]
+    got = small_rt.debug_gemm_tma(x, W, b, act=3, taps=taps)
+    _check(got, im2col, W, b, 3, 4e-5)
