@@ -18,6 +18,7 @@
 #include "split.cuh"
 #include "launch.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ptts {
 
@@ -370,6 +371,12 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      cudaStream_t st, SplitOut sp) {
   if (rows <= 0)
     return 0;
+  static const bool no_mma = getenv("PTTS_ATTN_NO_MMA") != nullptr;
+  if (!no_mma && ctx > 0) {
+    const int n = attention_window_mma(qkv, ldq, out, ldo, rows, D, n_heads, row_pos, ctx, st, sp);
+    if (n > 0)
+      return n;
+  }
   if (ctx > 0 && ctx <= 1024) {
     dim3 grid((rows + MQ - 1) / MQ, n_heads);
     size_t sm = sizeof(float) * (size_t)MQ * (ctx + MQ);

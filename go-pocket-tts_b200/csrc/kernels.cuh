@@ -145,6 +145,12 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      int D, int n_heads, const int32_t *row_pos, int ctx,
                      cudaStream_t st, SplitOut sp = SplitOut());
 
+// Tensor-core version (attention_mma.cu: flash-style, split-bf16 mma.sync, head_dim 64);
+// returns 0 without launching when the shape is not supported.
+int attention_window_mma(const float *qkv, long ldq, float *out, long ldo, int rows, int D,
+                         int n_heads, const int32_t *row_pos, int ctx, cudaStream_t st,
+                         SplitOut sp = SplitOut());
+
 // x_in[r,:] = isnan(frames[r,i]) ? bos[i] : frames[r,i]  (tensor_util.go:242-271)
 int nan_to_bos(const float *frames, const float *bos, float *out, int rows,
                int ldim, cudaStream_t st, SplitOut sp = SplitOut());
