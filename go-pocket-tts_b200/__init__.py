@@ -386,7 +386,7 @@ class NativeCudaRuntime:
                 n = self._lib.ptts_ticket_latents(self._h, p.ticket, _fptr(lat), _fptr(eos), res.n_frames)
                 if n < 0:
                     _check(n)
-            pcm = p.pcm[: res.n_samples].copy() if p.pcm is not None else np.empty(0, np.float32)
+            pcm = p.pcm[: res.n_samples] if p.pcm is not None else np.empty(0, np.float32)  # view: no extra host copy
             return GenerateResult(pcm, res.n_frames, res.queue_ms, res.first_frame_ms, res.total_ms, lat, eos)
         finally:
             self._lib.ptts_ticket_release(self._h, p.ticket)

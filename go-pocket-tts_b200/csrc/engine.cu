@@ -69,8 +69,9 @@ Engine::~Engine() {
     fin_stop = true;
   }
   fin_cv.notify_all();
-  if (finisher.joinable())
-    finisher.join();
+  for (auto &t : finishers)
+    if (t.joinable())
+      t.join();
   if (st) {
     cudaSetDevice(device);
     cudaStreamSynchronize(st);

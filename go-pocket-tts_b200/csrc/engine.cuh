@@ -202,10 +202,11 @@ struct Engine {
   // ---- asynchronous PCM return (scheduler path): a decode's PCM goes device ->
   //      pinned ring on a copy stream while the next AR steps run; a finisher thread
   //      copies it into the callers' buffers and completes the requests ----
-  static constexpr int NPCM = 3;
+  static constexpr int NPCM = 4;
+  static constexpr int NFIN = 3; // finisher threads (first-touch page faults of caller buffers dominate the host copy)
   cudaStream_t st_copy = nullptr;
-  float *m_pcm_ring[NPCM] = {nullptr, nullptr, nullptr};
-  float *h_pcm_ring[NPCM] = {nullptr, nullptr, nullptr}, *h_lat_ring[NPCM] = {nullptr, nullptr, nullptr};
+  float *m_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
+  float *h_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_lat_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_dec0[NPCM]{}, ev_pcm_ready[NPCM]{}, ev_copied[NPCM]{};
   struct PcmJob {
     int buf = 0, rc = 0;
@@ -221,8 +222,8 @@ struct Engine {
   std::mutex fin_mu;
   std::condition_variable fin_cv;
   std::deque<PcmJob> fin_q;
-  bool buf_busy[NPCM] = {false, false, false};
-  std::thread finisher;
+  bool buf_busy[NPCM] = {false, false, false, false};
+  std::vector<std::thread> finishers;
   bool fin_running = false, fin_stop = false;
   int pcm_next = 0;
   double fin_mimi_ms = 0, fin_d2h_ms = 0;

@@ -51,7 +51,8 @@ void Engine::ensure_finisher() {
   std::unique_lock<std::mutex> lk(fin_mu);
   if (!fin_running) {
     fin_running = true;
-    finisher = std::thread([this] { finisher_loop(); });
+    for (int i = 0; i < NFIN; i++)
+      finishers.emplace_back([this] { finisher_loop(); });
   }
 }
 
