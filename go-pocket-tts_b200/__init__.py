@@ -28,6 +28,7 @@ CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "attention_mma.cu", "elementwise
 
 PTTS_OK, PTTS_EINVAL, PTTS_ECUDA, PTTS_ENOMEM, PTTS_ESTATE, PTTS_ECANCELED = 0, -1, -2, -3, -4, -5
 PTTS_REQ_NO_PCM_D2H = 1
+PTTS_REQ_PCM16 = 2
 LATENT_DIM = 32
 SAMPLES_PER_FRAME = 1920
 SAMPLE_RATE = 24000
@@ -223,6 +224,7 @@ class RuntimeGenerateConfig:
     seed: int = 0
     force_eos_step: int = -1
     no_pcm_d2h: bool = False
+    pcm16: bool = False  # PCM16 samples quantised on the device (wav_stream.go:44-54); GenerateResult.pcm is int16
 
 
 def estimate_max_frames(n_tokens: int, frame_rate: float = 12.5) -> int:
@@ -364,13 +366,17 @@ class NativeCudaRuntime:
         keep: list = [toks, noise]
         vemb, vframes, vkv = self._voice_args(cfg, keep)
         flags = PTTS_REQ_NO_PCM_D2H if cfg.no_pcm_d2h else 0
+        if getattr(cfg, "pcm16", False):
+            flags |= PTTS_REQ_PCM16
         g = PttsGenCfg(temperature=cfg.temperature, eos_threshold=cfg.eos_threshold, max_steps=cfg.max_steps,
                        estimated_max_steps=cfg.estimated_max_steps, lsd_decode_steps=cfg.lsd_decode_steps,
                        frames_after_eos=cfg.frames_after_eos, force_eos_step=cfg.force_eos_step, flags=flags)
-        pcm = None if cfg.no_pcm_d2h else np.empty(ms * SAMPLES_PER_FRAME, dtype=np.float32)
+        pcm = None if cfg.no_pcm_d2h else np.empty(ms * SAMPLES_PER_FRAME,
+                                                    dtype=np.int16 if getattr(cfg, "pcm16", False) else np.float32)
         ticket = C.c_int64()
         _check(self._lib.ptts_submit(self._h, toks.ctypes.data_as(C.POINTER(C.c_int64)), toks.size, vemb, vframes,
-                                     vkv, C.byref(g), _fptr(noise), noise.shape[0], _fptr(pcm),
+                                     vkv, C.byref(g), _fptr(noise), noise.shape[0],
+                                     None if pcm is None else pcm.ctypes.data_as(C.POINTER(C.c_float)),
                                      0 if pcm is None else pcm.size, C.byref(ticket)))
         return _Pending(ticket.value, keep, pcm, ms)
 

@@ -1,0 +1,119 @@
+// attend.cuh — one (query row, head) of masked attention with 128 threads: scores,
+// max / exp / sum, P.V (see attention.cu for the reference semantics).  Shared by the
+// stand-alone attention kernels and the fused B=1 frame kernel (step_fused.cu).
+#pragma once
+#include "kernels.cuh"
+#include "split.cuh"
+#include <math.h>
+
+namespace ptts {
+
+constexpr int HD = 64;       // head_dim (FlowLM 1024/16, Mimi 512/8)
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ float block_reduce_max(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < ATT_THREADS / 32; i++)
+    r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ATT_THREADS / 32; i++)
+    r += red[i];
+  __syncthreads();
+  return r;
+}
+
+// KeyFn(j) -> pointer to the 64 floats of key j; ValFn(j) likewise for values.
+template <class KeyFn, class ValFn>
+__device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp,
+                                           ValFn valp, float *out, float *scores,
+                                           float *red, float4 *pv, const SplitOut &sp, long sp_row,
+                                           int sp_col) {
+  const int tid = threadIdx.x;
+  const float scale = 0.125f; // 1/sqrt(64)
+  // phase 1
+  const int part = tid & 7, kslot = tid >> 3; // 16 keys per pass
+  const float4 q0 = *reinterpret_cast<const float4 *>(q + part * 4);
+  const float4 q1 = *reinterpret_cast<const float4 *>(q + 32 + part * 4);
+  float lmax = -INFINITY;
+  for (int j0 = 0; j0 < nkeys; j0 += 16) {
+    const int j = j0 + kslot;
+    float s = 0.0f;
+    if (j < nkeys) {
+      const float *kp = keyp(j);
+      float4 a = *reinterpret_cast<const float4 *>(kp + part * 4);
+      float4 b = *reinterpret_cast<const float4 *>(kp + 32 + part * 4);
+      s = q0.x * a.x;
+      s = fmaf(q0.y, a.y, s);
+      s = fmaf(q0.z, a.z, s);
+      s = fmaf(q0.w, a.w, s);
+      s = fmaf(q1.x, b.x, s);
+      s = fmaf(q1.y, b.y, s);
+      s = fmaf(q1.z, b.z, s);
+      s = fmaf(q1.w, b.w, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (j < nkeys) {
+      s *= scale;
+      if (part == 0)
+        scores[j] = s;
+      lmax = fmaxf(lmax, s);
+    }
+  }
+  const float gmax = block_reduce_max(lmax, red); // includes __syncthreads
+  // phase 2
+  float lsum = 0.0f;
+  for (int j = tid; j < nkeys; j += ATT_THREADS) {
+    float e = expf(scores[j] - gmax);
+    scores[j] = e;
+    lsum += e;
+  }
+  const float gsum = block_reduce_sum(lsum, red);
+  const float inv = 1.0f / gsum;
+  // phase 3
+  const int c4 = tid & 15, grp = tid >> 4; // 8 key groups
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = grp; j < nkeys; j += 8) {
+    const float w = scores[j] * inv;
+    const float4 v = *reinterpret_cast<const float4 *>(valp(j) + c4 * 4);
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
+  pv[grp * 16 + c4] = acc;
+  __syncthreads();
+  if (tid < 16) {
+    float4 r = pv[tid];
+#pragma unroll
+    for (int g2 = 1; g2 < 8; g2++) {
+      float4 t = pv[g2 * 16 + tid];
+      r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+    }
+    if (out)
+      *reinterpret_cast<float4 *>(out + tid * 4) = r;
+    if (sp.hi)
+      split_store4(sp, sp_row, sp_col + tid * 4, r);
+  }
+}
+
+} // namespace ptts

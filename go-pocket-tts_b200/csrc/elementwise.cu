@@ -334,6 +334,27 @@ int final_conv(const float *x, int rows, int Cin, int k, const float *w, float b
   return 1;
 }
 
+// float PCM -> PCM16 exactly as the reference's streaming WAV writer: the product is formed
+// in fp64 (exact for a 24-bit by 15-bit product) and truncated toward zero.
+__global__ void pcm_to_s16_kernel(const float *in, int16_t *out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double v = (double)in[i];
+    v = v != v ? 0.0 : fmax(-1.0, fmin(1.0, v));
+    out[i] = (int16_t)(int)(v * 32767.0);
+  }
+}
+int pcm_to_s16(const float *in, int16_t *out, size_t n, cudaStream_t st) {
+  if (n == 0)
+    return 0;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16)
+    blocks = 148 * 16;
+  pcm_to_s16_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n);
+  return 1;
+}
+
 __global__ void fill_zero_kernel(float4 *p, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

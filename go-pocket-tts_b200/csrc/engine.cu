@@ -94,6 +94,7 @@ Engine::~Engine() {
   for (int i = 0; i < NPCM; i++) {
     fh(h_pcm_ring[i]);
     fh(h_lat_ring[i]);
+    fh(h_s16_ring[i]);
     for (cudaEvent_t e2 : {ev_dec0[i], ev_pcm_ready[i], ev_copied[i]})
       if (e2)
         cudaEventDestroy(e2);
@@ -1135,6 +1136,8 @@ int Engine::finalize() {
   for (int i = 0; i < NPCM; i++) {
     if ((rc = slack_alloc(&m_pcm_ring[i], rows, 1))) return rc;
     CUDA_TRY(cudaMallocHost((void **)&h_pcm_ring[i], rows * sizeof(float)));
+    if ((rc = dmalloc((void **)&m_s16_ring[i], rows * sizeof(int16_t)))) return rc;
+    CUDA_TRY(cudaMallocHost((void **)&h_s16_ring[i], rows * sizeof(int16_t)));
     CUDA_TRY(cudaMallocHost((void **)&h_lat_ring[i], (size_t)mimi_frames_cap * ldim * sizeof(float)));
     CUDA_TRY(cudaEventCreate(&ev_dec0[i]));
     CUDA_TRY(cudaEventCreate(&ev_pcm_ready[i]));
@@ -1812,10 +1815,15 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
     // asynchronous return: the copy stream takes over once the PCM is final; the
     // finisher thread waits on ev_copied, fills the callers' buffers and completes them
     const int k = job->buf;
+    if (job->copy_s16)
+      nl += pcm_to_s16(pcm, m_s16_ring[k], (size_t)rows, st);
     cudaEventRecord(ev_pcm_ready[k], st);
     CUDA_TRY(cudaStreamWaitEvent(st_copy, ev_pcm_ready[k], 0));
     if (job->copy)
       CUDA_TRY(cudaMemcpyAsync(h_pcm_ring[k], pcm, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, st_copy));
+    if (job->copy_s16)
+      CUDA_TRY(cudaMemcpyAsync(h_s16_ring[k], m_s16_ring[k], (size_t)rows * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                               st_copy));
     cudaEventRecord(ev_copied[k], st_copy);
     for (size_t i = 0; i < segs.size(); i++)
       job->segs[i].pcm_off = (size_t)(segs[i].row0 + P) * spb;
@@ -1887,8 +1895,12 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
       js.lat_off = (size_t)tf * ldim;
       js.n_frames = n;
       job.segs.push_back(js);
-      if (!(r->cfg.flags & PTTS_REQ_NO_PCM_D2H) && r->pcm_out)
-        job.copy = true;
+      if (!(r->cfg.flags & PTTS_REQ_NO_PCM_D2H) && r->pcm_out) {
+        if (r->cfg.flags & PTTS_REQ_PCM16)
+          job.copy_s16 = true;
+        else
+          job.copy = true;
+      }
       tf += n;
       segs.push_back(sg);
       i++;

@@ -207,10 +207,11 @@ struct Engine {
   cudaStream_t st_copy = nullptr;
   float *m_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   float *h_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_lat_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
+  int16_t *m_s16_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_s16_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_dec0[NPCM]{}, ev_pcm_ready[NPCM]{}, ev_copied[NPCM]{};
   struct PcmJob {
     int buf = 0, rc = 0;
-    bool copy = false;
+    bool copy = false, copy_s16 = false; // some request wants float / PCM16 samples on the host
     std::string msg;
     struct Seg {
       std::shared_ptr<Request> r;

@@ -179,5 +179,7 @@ int final_conv(const float *x, int rows, int Cin, int k, const float *w,
                float bias, const uint8_t *rowmask, int mask_div, float *pcm,
                cudaStream_t st);
 int fill_zero(float *p, size_t n, cudaStream_t st);
+// out[i] = int16(clamp(in[i], -1, 1) * 32767) truncated toward zero (wav_stream.go:44-54)
+int pcm_to_s16(const float *in, int16_t *out, size_t n, cudaStream_t st);
 
 } // namespace ptts

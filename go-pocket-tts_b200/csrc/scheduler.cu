@@ -86,8 +86,12 @@ void Engine::finisher_loop() {
       Request &r = *sg.r;
       if (job.rc == PTTS_OK) {
         r.latents.assign(h_lat_ring[k] + sg.lat_off, h_lat_ring[k] + sg.lat_off + (size_t)sg.n_frames * ldim);
-        if (!(r.cfg.flags & PTTS_REQ_NO_PCM_D2H) && r.pcm_out)
-          memcpy(r.pcm_out, h_pcm_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(float));
+        if (!(r.cfg.flags & PTTS_REQ_NO_PCM_D2H) && r.pcm_out) {
+          if (r.cfg.flags & PTTS_REQ_PCM16)
+            memcpy(r.pcm_out, h_s16_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(int16_t));
+          else
+            memcpy(r.pcm_out, h_pcm_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(float));
+        }
       }
       complete(sg.r, job.rc, job.rc ? job.msg.c_str() : nullptr);
     }

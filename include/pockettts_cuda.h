@@ -77,6 +77,8 @@ typedef struct {
 } ptts_gen_cfg;
 
 #define PTTS_REQ_NO_PCM_D2H 1 /* leave PCM on the device (bench "value" leg) */
+#define PTTS_REQ_PCM16 2      /* pcm_out is int16_t[pcm_cap]: clamp(v,-1,1)*32767 truncated on the device
+                                 (internal/audio/wav_stream.go:44-54), half the D2H bytes */
 
 /* Upstream voice model state for one transformer layer: the
  * `transformer.layers.{i}.self_attn/cache` tensor, layout [2,1,T,H,Dh] fp32

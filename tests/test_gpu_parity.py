@@ -373,3 +373,18 @@ def test_safetensors_file_loader_roundtrip(pkg, ck, small_tensors, small_rt, tmp
     finally:
         rt_file.close()
         rt_keys.close()
+
+
+def test_pcm16_output_matches_reference_quantiser(small_rt):
+    """On-device PCM16 == int16(clamp(v, -1, 1) * 32767) truncated (internal/audio/wav_stream.go:44-54)
+    of the float PCM of the same request."""
+    pkg = small_rt.__class__.__module__ and __import__("sys").modules[small_rt.__class__.__module__]
+    tokens = [5, 9, 2, 7, 1, 3]
+    noise = pkg.make_noise(8, 0.7, 3)
+    base = dict(max_steps=8, eos_threshold=1e30, force_eos_step=3, frames_after_eos=2, noise=noise)
+    f = small_rt.generate(tokens, pkg.RuntimeGenerateConfig(**base))
+    q = small_rt.generate(tokens, pkg.RuntimeGenerateConfig(pcm16=True, **base))
+    assert q.pcm.dtype == np.int16 and q.pcm.shape == f.pcm.shape and f.n_frames == q.n_frames == 6
+    # scale up so the clamp is exercised too: the quantiser is applied to what the device computed
+    want = np.trunc(np.clip(f.pcm.astype(np.float64), -1.0, 1.0) * 32767.0).astype(np.int16)
+    np.testing.assert_array_equal(q.pcm, want)
