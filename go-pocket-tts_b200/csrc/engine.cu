@@ -90,6 +90,7 @@ Engine::~Engine() {
       cudaFreeHost(p);
   };
   fh(h_row_slot); fh(h_row_pos); fh(h_ids); fh(h_off_a); fh(h_off_b); fh(h_off_c);
+  fh(h_fused_err);
   fh(h_eos); fh(h_lat); fh(h_stage); fh(h_mrow_pos); fh(h_mrow_frame0); fh(h_mmask); fh(h_moff);
   for (int i = 0; i < NPCM; i++) {
     fh(h_pcm_ring[i]);
@@ -1175,6 +1176,7 @@ int Engine::finalize() {
   CUDA_TRY(cudaMallocHost((void **)&h_mmask, Rb));
   CUDA_TRY(cudaMallocHost((void **)&h_moff, (size_t)mimi_frames_cap * 8));
 
+  if ((rc = setup_fused())) return rc;
   host.clear(); // device copies are authoritative from here on
   finalized = true;
   return PTTS_OK;
@@ -1290,6 +1292,69 @@ void Engine::seq_free(Seq *s) {
   free_slots.push_back(s->slot);
   s->slot = -1;
   s->pages.clear();
+}
+
+// Parameter block + launch geometry of the single-kernel B=1 frame.
+int Engine::setup_fused() {
+  fused_on = false;
+  if (getenv("PTTS_NO_FUSED_STEP") || L > FUSED_MAX_LAYERS || depth > FUSED_MAX_LAYERS || Dh != 64 || D % 4 || C % 4 ||
+      ldim > 128 || ldim % 4)
+    return PTTS_OK;
+  FusedParams hp{};
+  hp.D = D; hp.H = H; hp.F = F; hp.L = L; hp.C = C; hp.hid = rb[0].mlp0.out; hp.depth = depth; hp.ldim = ldim;
+  hp.ada_n = ada_n;
+  for (int l = 0; l < L; l++) {
+    const DTLayer &t = fl[l];
+    hp.layer[l] = FusedLayer{t.n1.w, t.n1.b, t.in_proj.w, t.out_proj.w, t.n2.w, t.n2.b, t.l1.w, t.l2.w, t.n1.eps, t.n2.eps};
+  }
+  hp.bos = bos; hp.in_w = input_linear.w; hp.in_b = input_linear.b;
+  hp.on_w = out_norm.w; hp.on_b = out_norm.b; hp.on_eps = out_norm.eps;
+  hp.eos_w = out_eos_lin.w; hp.eos_b = out_eos_bias;
+  hp.ce_w = cond_embed.w; hp.ce_b = cond_embed.b;
+  hp.ada_w = ada_all.w; hp.ada_b = ada_all.b;
+  hp.ip_w = input_proj.w; hp.ip_b = input_proj.b;
+  for (int b = 0; b < depth; b++) {
+    if (rb[b].mlp0.out != hp.hid || rb[b].mlp2.in != hp.hid)
+      return PTTS_OK;
+    hp.rb[b] = FusedRes{rb[b].in_ln.w, rb[b].in_ln.b, rb[b].mlp0.w, rb[b].mlp0.b, rb[b].mlp2.w, rb[b].mlp2.b, rb[b].in_ln.eps};
+  }
+  hp.fin_w = final_linear.w; hp.fin_b = final_linear.b;
+  hp.rope_cos = rope_cos; hp.rope_sin = rope_sin;
+  hp.kv = kvg;
+  hp.x = x; hp.qkv = qkv; hp.att = att; hp.ff = ff; hp.fh_in = fh_in; hp.fh_last = fh_last; hp.fh_eos = fh_eos;
+  hp.fh_cproj = fh_cproj; hp.fh_ada = fh_ada; hp.fh_x = fh_x; hp.fh_h2 = fh_h2; hp.fh_cur = fh_cur;
+  hp.fh_frames = fh_frames; hp.fh_noise = fh_noise;
+  hp.hist = d_hist; hp.noise_pool = d_noise; hp.hist_w = d_hist;
+  int rc;
+  if ((rc = dmalloc((void **)&d_fused_bar, STEP_FUSED_BARRIER_BYTES))) return rc;
+  if ((rc = dmalloc((void **)&d_fused_err, 256))) return rc;
+  CUDA_TRY(cudaMemset(d_fused_bar, 0, STEP_FUSED_BARRIER_BYTES));
+  CUDA_TRY(cudaMemset(d_fused_err, 0, 256));
+  CUDA_TRY(cudaMallocHost((void **)&h_fused_err, sizeof(int)));
+  *h_fused_err = 0;
+  hp.barrier = d_fused_bar;
+  hp.error = d_fused_err;
+  hp.dbg = nullptr;
+  if (getenv("PTTS_FUSED_TIMELINE")) {
+    if ((rc = dmalloc((void **)&fused_dbg, 512 * sizeof(unsigned long long)))) return rc;
+    CUDA_TRY(cudaMemset(fused_dbg, 0, 512 * sizeof(unsigned long long)));
+    hp.dbg = fused_dbg;
+  }
+  int hidmax = hp.hid > F ? hp.hid : F;
+  FusedParams sized = hp;
+  sized.F = hidmax;
+  fused_smem = step_fused_smem(sized, cfg.max_seq_tokens);
+  fused_grid = step_fused_grid(fused_smem);
+  if (fused_grid <= 0)
+    return PTTS_OK; // cannot be resident: keep the multi-kernel path
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  if (!coop)
+    return PTTS_OK;
+  if ((rc = dmalloc((void **)&d_fused, sizeof(FusedParams)))) return rc;
+  CUDA_TRY(cudaMemcpy(d_fused, &hp, sizeof(FusedParams), cudaMemcpyHostToDevice));
+  fused_on = true;
+  return PTTS_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -1518,6 +1583,21 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     ~PdlScope() { pdl_set(false); }
   } pdl_scope(!no_pdl && !prof_on && Bp <= 256); // measured: -3..9 % per frame up to B=256, +2 % at 512
   int64_t &nl = times.kernel_launches;
+  if (Bp == 1 && fused_on && !prof_on) {
+    // the batch-1 latency path: the whole frame is one persistent cooperative kernel
+    float *tv = nullptr;
+    int rc = get_tvec(lsd_steps, &tv);
+    if (rc)
+      return rc;
+    const int n = step_fused_launch(d_fused, fused_grid, fused_smem, d_row_slot, d_row_pos, d_off_a, d_off_b, d_off_c,
+                                    gather_frames ? 1 : 0, gather_noise ? 1 : 0, tv, lsd_steps, d_fused_bar, st);
+    if (n < 0) {
+      cudaGetLastError();
+      PTTS_FAIL(PTTS_ECUDA, "cuda: cooperative launch of the fused frame kernel failed");
+    }
+    nl += n;
+    return PTTS_OK;
+  }
   if (gather_frames)
     PK("gather_scatter", 0, 0, gather_rows(d_hist, d_off_a, fh_frames, Bp, ldim, st));
   if (gather_noise)
@@ -1646,11 +1726,29 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
       return rc;
   }
   cudaEventRecord(ev[4], st);
+  const bool used_fused = Bp == 1 && fused_on && !prof_on;
+  if (used_fused) {
+    timed = false; // no flow-head split inside the single kernel
+    CUDA_TRY(cudaMemcpyAsync(h_fused_err, d_fused_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(cudaMemcpyAsync(h_eos, fh_eos, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (lat_out_host)
     CUDA_TRY(cudaMemcpyAsync(h_lat, fh_cur, (size_t)B * ldim * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
+  if (used_fused && fused_dbg && times.steps == 20) { // one frame's timeline of CTA 0 (tools)
+    unsigned long long hd[512];
+    cudaMemcpy(hd, fused_dbg, sizeof hd, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "fused frame timeline (ns after entry, CTA 0):");
+    for (int i = 1; i < 512 && hd[i]; i++)
+      fprintf(stderr, " %lld", (long long)(hd[i] - hd[0]));
+    fprintf(stderr, "\n");
+  }
+  if (used_fused && *h_fused_err) {
+    fused_on = false; // fall back to the multi-kernel path from here on
+    cudaMemset(d_fused_err, 0, sizeof(int));
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda: fused frame kernel: grid barrier timed out");
+  }
   if (eos_out_host)
     memcpy(eos_out_host, h_eos, (size_t)B * 4);
   if (lat_out_host)

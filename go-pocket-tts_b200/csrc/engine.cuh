@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/pockettts_cuda.h"
 #include "kernels.cuh"
+#include "step_fused.cuh"
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -151,6 +152,16 @@ struct Engine {
       g.a_lo_row = (int)a.plane_rows;
     }
   }
+
+  // ---- single-kernel batch-1 frame (step_fused.cu) ----
+  FusedParams *d_fused = nullptr;
+  unsigned *d_fused_bar = nullptr;
+  int *d_fused_err = nullptr, *h_fused_err = nullptr;
+  unsigned long long *fused_dbg = nullptr;
+  int fused_grid = 0;
+  size_t fused_smem = 0;
+  bool fused_on = false;
+  int setup_fused();
 
   // ---- split-K scratch for skinny GEMMs ----
   float *gemm_ws = nullptr;

@@ -1,0 +1,462 @@
+// step_fused.cu — one AR frame of ONE sequence (the batch-1 latency path) as a single
+// persistent cooperative kernel: flow_lm.go:238-299 (NaN->BOS, input_linear, 6 transformer
+// layers with RoPE + paged-KV append + attention, out_norm, EOS logit) and the LSD / flow
+// head of flow_lm.go:311-353 + flow_net.go:314-356, 46 phases separated by grid barriers
+// instead of 79 kernel launches.
+//
+// The frame is memory-bound (341 MB of fp32 weights, read once); what the multi-kernel
+// version loses is the dependent-launch chain (3-5 us per kernel).  Here
+//   * every warp requests the weight row of its first column of the NEXT phase before it
+//     arrives at the barrier, so the HBM latency and part of the transfer overlap the
+//     barrier and the staging of the next phase's activation vector;
+//   * each CTA stages the (LayerNorm'd / modulated / activated) input vector of a phase in
+//     shared memory once, then its warps stream weight rows against it;
+//   * activations cross phases through L2 (`ld.global.cg`: L1 is not coherent across SMs).
+// Grid = 2 CTAs of 128 threads per SM, launched cooperatively (co-residency is what makes
+// the barrier legal); a spin that exceeds ~1 s raises an error flag instead of hanging.
+#include "step_fused.cuh"
+#include "attend.cuh"
+#include "gemm_epi.cuh"
+
+namespace ptts {
+
+namespace {
+
+constexpr int FT = 128; // threads per CTA (= ATT_THREADS of attend_row)
+
+__device__ __forceinline__ float4 ldg_w(const float *p) { // weights: read once, keep out of L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldcg1(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FSTAMP()                                                               \
+  do {                                                                         \
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0 && nstamp < 500)          \
+      P.dbg[nstamp++] = gtime();                                               \
+  } while (0)
+// Pull constant data (LayerNorm weights, KV rows of earlier tokens) into this SM's L1 ahead of
+// the phase that reads it; costs no registers.
+__device__ __forceinline__ void l1_prefetch(const void *p, size_t bytes) {
+  if (!p)
+    return;
+  const char *c = reinterpret_cast<const char *>(p);
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)FT * 128)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c + off));
+}
+__device__ __forceinline__ float bias_at(const float *b, int n) { return b ? __ldg(b + n) : 0.0f; }
+
+// Grid barrier on 16 striped counters (one 128-byte line each).  Same-address atomics
+// serialise in L2 (~27 cycles each): one counter costs ~4 us for 296 CTAs, a two-level tree
+// two dependent round trips, per-CTA flags polled by everybody flood L2.  Here CTA b adds to
+// counter b % 16 with a no-return reduction (~18 arrivals per counter, in parallel) and
+// lanes 0..15 of warp 0 poll one counter each.  Counters are monotonic within a launch (the
+// host zeroes them before it).
+constexpr int GB_NCTR = 16;
+constexpr int GB_STRIDE = 32; // words between counters
+struct GridBar {
+  unsigned *ctr;
+  int *err;
+  unsigned phase, mine; // arrivals per phase on the counter this lane polls
+  bool dead;
+};
+__device__ __forceinline__ GridBar make_bar(unsigned *ctr, int *err) {
+  GridBar b;
+  b.ctr = ctr;
+  b.err = err;
+  b.phase = 0;
+  b.dead = false;
+  const unsigned c = threadIdx.x & (GB_NCTR - 1);
+  b.mine = (gridDim.x + GB_NCTR - 1 - c) / GB_NCTR; // CTAs with blockIdx % 16 == c
+  return b;
+}
+// Arrive: publish this CTA's writes and count it in.  Must come BEFORE the weight prefetch of
+// the next phase: the gpu-scope fence waits for the issuing thread's outstanding loads.
+__device__ __forceinline__ void grid_arrive(GridBar &b) {
+  b.phase++;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(b.ctr + GB_STRIDE * (blockIdx.x & (GB_NCTR - 1)))
+                 : "memory");
+  }
+}
+// Wait: acquire loads only (no fence: the prefetch loads stay in flight); the CTA barrier
+// joins the pollers' acquires.
+__device__ __forceinline__ void grid_wait(GridBar &b) {
+  if (threadIdx.x < GB_NCTR && !b.dead) {
+    const unsigned target = b.phase * b.mine;
+    const unsigned *p = b.ctr + GB_STRIDE * threadIdx.x;
+    long spins = 0;
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+      if (v >= target)
+        break;
+      if (++spins > 8000000L || ((spins & 255) == 0 && *reinterpret_cast<volatile int *>(b.err) != 0)) {
+        atomicExch(b.err, 1); // somebody is missing: give up instead of hanging the GPU
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (!b.dead && *reinterpret_cast<volatile int *>(b.err) != 0)
+    b.dead = true;
+}
+
+// ---- weight streaming ----
+// A warp's share of a phase is a list of segments: (column n, 1024-wide k chunk c), columns
+// n = gw, gw + nw, ...  Segments are processed in batches of 4 (32 float4 = 8 KB per warp
+// in flight); the first two segments are requested before the grid barrier, the rest of
+// the first batch right after it, so they land while the CTA stages its activation vector.
+constexpr int SEG_K = 1024;
+struct Pref {
+  float4 w[2][8];
+};
+__device__ __forceinline__ void seg_load(float4 (&w)[8], const float *W, int N, int K, int kc, int gw, int nw, int seg,
+                                         int lane) {
+  const int n = gw + (seg / kc) * nw;
+  const int k0 = (seg % kc) * SEG_K;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    const int k = k0 + lane * 4 + 128 * u;
+    w[u] = (n < N && k < K) ? ldg_w(W + (long)n * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void prefetch_w(Pref &p, const float *W, int N, int K, int gw, int nw, int lane) {
+  const int kc = (K + SEG_K - 1) / SEG_K;
+  seg_load(p.w[0], W, N, K, kc, gw, nw, 0, lane);
+  seg_load(p.w[1], W, N, K, kc, gw, nw, 1, lane);
+}
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &w, float acc) {
+  acc = fmaf(a.x, w.x, acc);
+  acc = fmaf(a.y, w.y, acc);
+  acc = fmaf(a.z, w.z, acc);
+  acc = fmaf(a.w, w.w, acc);
+  return acc;
+}
+__device__ __forceinline__ float seg_dot(const float4 (&w)[8], const float *sA, int K, int k0, int lane) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    const int k = k0 + lane * 4 + 128 * u;
+    if (k < K)
+      acc = dot4(*reinterpret_cast<const float4 *>(sA + k), w[u], acc);
+  }
+  return acc;
+}
+// Second half of the first batch: called right after the barrier, before the staging.
+struct Pref2 {
+  float4 w[2][8];
+};
+__device__ __forceinline__ void prefetch_w2(Pref2 &p, const float *W, int N, int K, int gw, int nw, int lane) {
+  const int kc = (K + SEG_K - 1) / SEG_K;
+  seg_load(p.w[0], W, N, K, kc, gw, nw, 2, lane);
+  seg_load(p.w[1], W, N, K, kc, gw, nw, 3, lane);
+}
+// y[n] = W[n,:K] . a for this warp's columns; a is in shared memory; epi(n, y) runs on lane 0.
+template <class Epi>
+__device__ __forceinline__ void gemv_cols(const Pref &p, const Pref2 &p2, const float *W, int N, int K, const float *sA,
+                                          int gw, int nw, int lane, Epi epi) {
+  const int kc = (K + SEG_K - 1) / SEG_K;
+  const int ncols = gw < N ? (N - gw + nw - 1) / nw : 0;
+  const int nseg = ncols * kc;
+  float colacc = 0.0f;
+  auto finish = [&](int seg, float part) { // partial of segment `seg`; emit the column at its last chunk
+    colacc += part;
+    if ((seg % kc) == kc - 1) {
+      float v = colacc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0)
+        epi(gw + (seg / kc) * nw, v);
+      colacc = 0.0f;
+    }
+  };
+  // first batch from the prefetched registers
+  if (nseg > 0) finish(0, seg_dot(p.w[0], sA, K, 0, lane));
+  if (nseg > 1) finish(1, seg_dot(p.w[1], sA, K, (1 % kc) * SEG_K, lane));
+  if (nseg > 2) finish(2, seg_dot(p2.w[0], sA, K, (2 % kc) * SEG_K, lane));
+  if (nseg > 3) finish(3, seg_dot(p2.w[1], sA, K, (3 % kc) * SEG_K, lane));
+  for (int s0 = 4; s0 < nseg; s0 += 4) {
+    float4 w[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      seg_load(w[j], W, N, K, kc, gw, nw, s0 + j, lane); // beyond nseg: n >= N -> zeros, no loads
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (s0 + j < nseg)
+        finish(s0 + j, seg_dot(w[j], sA, K, ((s0 + j) % kc) * SEG_K, lane));
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+// sA[0:K] = src (through L2)
+__device__ __forceinline__ void stage_plain(float *sA, const float *src, int K) {
+  for (int i = threadIdx.x; i < K; i += FT)
+    sA[i] = ldcg1(src + i);
+  __syncthreads();
+}
+// sA = (LN(src) * w + b) [* (1 + scale) + shift]  (linear.go:265-329, tensor_util.go:175-193)
+__device__ __forceinline__ void stage_ln(float *sA, float *red, const float *src, int K, const float *w, const float *b,
+                                         float eps, const float *scale, const float *shift) {
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < K; i += FT) {
+    const float v = ldcg1(src + i);
+    sA[i] = v;
+    s += v;
+  }
+  const float mean = block_sum(s, red) / (float)K;
+  float q = 0.0f;
+  for (int i = threadIdx.x; i < K; i += FT) {
+    const float d = sA[i] - mean;
+    q += d * d;
+  }
+  const float inv = 1.0f / sqrtf(block_sum(q, red) / (float)K + eps);
+  for (int i = threadIdx.x; i < K; i += FT) {
+    float t = (sA[i] - mean) * inv;
+    if (w)
+      t *= __ldg(w + i);
+    if (b)
+      t += __ldg(b + i);
+    if (scale)
+      t = t * (ldcg1(scale + i) + 1.0f) + ldcg1(shift + i);
+    sA[i] = t;
+  }
+  __syncthreads();
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(FT, 2)
+    step_fused_kernel(const FusedParams *__restrict__ Pp, const int32_t *row_slot, const int32_t *row_pos,
+                      const int64_t *off_a, const int64_t *off_b, const int64_t *off_c, int gather_frames,
+                      int gather_noise, const float *tvec, int lsd_steps) {
+  extern __shared__ float dsm[]; // [max(F, max_keys)] activation vector / attention scores
+  __shared__ float red[FT / 32];
+  __shared__ float4 pv[8 * 16];
+  __shared__ __align__(16) float q_s[HD];
+  const FusedParams &P = *Pp;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * FT + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * FT) >> 5;
+  GridBar bar = make_bar(P.barrier, P.error);
+  float *sA = dsm;
+  const int D = P.D, F = P.F, C = P.C, ldim = P.ldim;
+  const int slot = row_slot[0], pos = row_pos[0];
+  Pref pf;
+  Pref2 pf2;
+  int nstamp = 0;
+  FSTAMP();
+// publish the previous phase, request the first weight segments of the next one, wait for
+// everybody, request the rest of the first batch (they land while the vector is staged)
+#define PHASE_BEGIN(W, N, K) PHASE_BEGIN_LN(W, N, K, nullptr, nullptr, 0)
+#define PHASE_BEGIN_LN(W, N, K, LW, LB, KLN)                                   \
+  do {                                                                         \
+    grid_arrive(bar);                                                          \
+    prefetch_w(pf, W, N, K, gw, nw, lane);                                     \
+    l1_prefetch(LW, (size_t)(KLN) * 4);                                        \
+    l1_prefetch(LB, (size_t)(KLN) * 4);                                        \
+    grid_wait(bar);                                                            \
+    prefetch_w2(pf2, W, N, K, gw, nw, lane);                                   \
+    FSTAMP();                                                                  \
+  } while (0)
+  auto gemv_now = [&](const float *W, int N, int K, const float *a, int gw2, auto epi) {
+    Pref q;
+    Pref2 q2;
+    prefetch_w(q, W, N, K, gw2, nw, lane);
+    prefetch_w2(q2, W, N, K, gw2, nw, lane);
+    gemv_cols(q, q2, W, N, K, a, gw2, nw, lane, epi);
+  };
+
+  // ---- phase 0: x = input_linear(nan_to_bos(frame)) ----
+  {
+    const float *frame = gather_frames ? P.hist + off_a[0] : P.fh_frames;
+    if (threadIdx.x < ldim) {
+      const float v = ldcg1(frame + threadIdx.x);
+      const float u = isnan(v) ? __ldg(P.bos + threadIdx.x) : v;
+      sA[threadIdx.x] = u;
+      if (blockIdx.x == 0)
+        P.fh_in[threadIdx.x] = u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < ldim) { // the flow head starts from the noise
+      const float *nz = gather_noise ? P.noise_pool + off_c[0] : P.fh_noise;
+      P.fh_cur[threadIdx.x] = ldcg1(nz + threadIdx.x);
+    }
+    __syncthreads();
+    gemv_now(P.in_w, D, ldim, sA, gw, [&](int n, float v) { P.x[n] = v + bias_at(P.in_b, n); });
+  }
+  for (int l = 0; l < P.L; l++) {
+    const FusedLayer &ly = P.layer[l];
+    // ---- qkv = in_proj(LN1(x)) ----
+    PHASE_BEGIN_LN(ly.in_proj, 3 * D, D, ly.n1w, ly.n1b, D);
+    stage_ln(sA, red, P.x, D, ly.n1w, ly.n1b, ly.eps1, nullptr, nullptr);
+    FSTAMP();
+    gemv_cols(pf, pf2, ly.in_proj, 3 * D, D, sA, gw, nw, lane, [&](int n, float v) { P.qkv[n] = v; });
+    // ---- RoPE, KV append, attention: one CTA per head; the others already hold the first
+    //      out_proj segments when they reach the next barrier ----
+    grid_arrive(bar);
+    prefetch_w(pf, ly.out_proj, D, D, gw, nw, lane);
+    grid_wait(bar);
+    FSTAMP();
+    if ((int)blockIdx.x < P.H) {
+      const int h = blockIdx.x, half = HD / 2;
+      const KvGeom &kv = P.kv;
+      const int PT = kv.page_tokens;
+      const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
+      const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
+      float *page = kv.pool + (long)pt[pos / PT] * page_stride;
+      const int tok = pos % PT;
+      const long koff = ((long)(l * 2 + 0) * kv.n_heads + h) * PT * HD;
+      const long voff = ((long)(l * 2 + 1) * kv.n_heads + h) * PT * HD;
+      if (threadIdx.x < half) { // interleaved pairs (rope.go:81-105)
+        const int j = threadIdx.x;
+        const float c = __ldg(P.rope_cos + (long)pos * half + j), s = __ldg(P.rope_sin + (long)pos * half + j);
+        const float qa = ldcg1(P.qkv + h * HD + 2 * j), qb = ldcg1(P.qkv + h * HD + 2 * j + 1);
+        q_s[2 * j] = qa * c - qb * s;
+        q_s[2 * j + 1] = qa * s + qb * c;
+        const float ka = ldcg1(P.qkv + D + h * HD + 2 * j), kb = ldcg1(P.qkv + D + h * HD + 2 * j + 1);
+        float *dst = page + koff + (long)tok * HD + 2 * j;
+        dst[0] = ka * c - kb * s;
+        dst[1] = ka * s + kb * c;
+      } else if (threadIdx.x < half + HD) {
+        const int d = threadIdx.x - half;
+        page[voff + (long)tok * HD + d] = ldcg1(P.qkv + 2 * D + h * HD + d);
+      }
+      __syncthreads();
+      const float *pool = kv.pool;
+      auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
+      auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
+      attend_row(q_s, pos + 1, keyp, valp, P.att + h * HD, dsm, red, pv, SplitOut(), 0, 0);
+    }
+    // ---- x += out_proj(att) ----
+    grid_arrive(bar);
+    grid_wait(bar);
+    prefetch_w2(pf2, ly.out_proj, D, D, gw, nw, lane);
+    FSTAMP();
+    stage_plain(sA, P.att, D);
+    FSTAMP();
+    gemv_cols(pf, pf2, ly.out_proj, D, D, sA, gw, nw, lane, [&](int n, float v) { P.x[n] = ldcg1(P.x + n) + v; });
+    // ---- ff = gelu(linear1(LN2(x))) ----
+    PHASE_BEGIN_LN(ly.l1, F, D, ly.n2w, ly.n2b, D);
+    stage_ln(sA, red, P.x, D, ly.n2w, ly.n2b, ly.eps2, nullptr, nullptr);
+    FSTAMP();
+    gemv_cols(pf, pf2, ly.l1, F, D, sA, gw, nw, lane, [&](int n, float v) { P.ff[n] = act_apply(v, ACT_GELU); });
+    // ---- x += linear2(ff) ----
+    PHASE_BEGIN(ly.l2, D, F);
+    stage_plain(sA, P.ff, F);
+    FSTAMP();
+    gemv_cols(pf, pf2, ly.l2, D, F, sA, gw, nw, lane, [&](int n, float v) { P.x[n] = ldcg1(P.x + n) + v; });
+  }
+  // ---- last = out_norm(x); eos = last . w_eos + b; cproj = cond_embed(last) ----
+  PHASE_BEGIN_LN(P.ce_w, C, D, P.on_w, P.on_b, D);
+  stage_ln(sA, red, P.x, D, P.on_w, P.on_b, P.on_eps, nullptr, nullptr);
+  FSTAMP();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < D; i += FT)
+      P.fh_last[i] = sA[i];
+  gemv_cols(pf, pf2, P.ce_w, C, D, sA, gw, nw, lane, [&](int n, float v) { P.fh_cproj[n] = v + bias_at(P.ce_b, n); });
+  if (gw == nw - 1) // the EOS logit is one more column, on the last warp
+    gemv_now(P.eos_w, 1, D, sA, 0, [&](int, float v) { P.fh_eos[0] = v + P.eos_b; });
+  const float inv_steps = 1.0f / (float)lsd_steps;
+  for (int it = 0; it < lsd_steps; it++) {
+    // ---- ada = adaLN_all(silu(cproj + t_emb)); fx = input_proj(cur) ----
+    PHASE_BEGIN(P.ada_w, P.ada_n, C);
+    for (int i = threadIdx.x; i < C; i += FT) {
+      const float y = ldcg1(P.fh_cproj + i) + __ldg(tvec + (long)it * C + i);
+      sA[i] = y / (1.0f + expf(-y));
+    }
+    for (int i = threadIdx.x; i < ldim; i += FT)
+      sA[C + i] = ldcg1(P.fh_cur + i);
+    __syncthreads();
+    FSTAMP();
+    gemv_cols(pf, pf2, P.ada_w, P.ada_n, C, sA, gw, nw, lane,
+              [&](int n, float v) { P.fh_ada[n] = v + bias_at(P.ada_b, n); });
+    gemv_now(P.ip_w, C, ldim, sA + C, gw, [&](int n, float v) { P.fh_x[n] = v + bias_at(P.ip_b, n); });
+    for (int b = 0; b < P.depth; b++) {
+      const FusedRes &rb = P.rb[b];
+      const float *shift = P.fh_ada + (long)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
+      // ---- h2 = silu(mlp0(modulate(LN(fx)))) ----
+      PHASE_BEGIN_LN(rb.mlp0w, P.hid, C, rb.lnw, rb.lnb, C);
+      stage_ln(sA, red, P.fh_x, C, rb.lnw, rb.lnb, rb.eps, scale, shift);
+      FSTAMP();
+      gemv_cols(pf, pf2, rb.mlp0w, P.hid, C, sA, gw, nw, lane,
+                [&](int n, float v) { P.fh_h2[n] = act_apply(v + bias_at(rb.mlp0b, n), ACT_SILU); });
+      // ---- fx += gate * mlp2(h2) ----
+      PHASE_BEGIN(rb.mlp2w, C, P.hid);
+      stage_plain(sA, P.fh_h2, P.hid);
+      FSTAMP();
+      gemv_cols(pf, pf2, rb.mlp2w, C, P.hid, sA, gw, nw, lane, [&](int n, float v) {
+        P.fh_x[n] = (v + bias_at(rb.mlp2b, n)) * ldcg1(gate + n) + ldcg1(P.fh_x + n);
+      });
+    }
+    // ---- cur += final(modulate(LN(fx))) / steps ----
+    const float *fshift = P.fh_ada + (long)P.depth * 3 * C, *fscale = fshift + C;
+    PHASE_BEGIN(P.fin_w, ldim, C);
+    stage_ln(sA, red, P.fh_x, C, nullptr, nullptr, 1e-6f, fscale, fshift);
+    FSTAMP();
+    const bool last_it = it == lsd_steps - 1;
+    gemv_cols(pf, pf2, P.fin_w, ldim, C, sA, gw, nw, lane, [&](int n, float v) {
+      const float c = (v + bias_at(P.fin_b, n)) * inv_steps + ldcg1(P.fh_cur + n);
+      P.fh_cur[n] = c;
+      if (last_it)
+        P.hist_w[off_b[0] + n] = c; // the new latent frame of this sequence
+    });
+  }
+  FSTAMP();
+#undef PHASE_BEGIN
+#undef PHASE_BEGIN_LN
+}
+
+size_t step_fused_smem(const FusedParams &hp, int max_keys) {
+  int n = hp.F;
+  if (max_keys > n)
+    n = max_keys;
+  if (hp.C + hp.ldim > n)
+    n = hp.C + hp.ldim;
+  return (size_t)((n + 15) / 16 * 16) * sizeof(float);
+}
+
+int step_fused_grid(size_t smem) {
+  int dev = 0, sms = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaFuncSetAttribute(step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_fused_kernel, FT, smem) != cudaSuccess || occ < 1)
+    return 0;
+  if (occ > 2)
+    occ = 2;
+  return occ * sms;
+}
+
+int step_fused_launch(const FusedParams *dp, int grid, size_t smem, const int32_t *row_slot, const int32_t *row_pos,
+                      const int64_t *off_a, const int64_t *off_b, const int64_t *off_c, int gather_frames,
+                      int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier, cudaStream_t st) {
+  if (cudaMemsetAsync(barrier, 0, STEP_FUSED_BARRIER_BYTES, st) != cudaSuccess)
+    return -1;
+  void *args[] = {(void *)&dp,       (void *)&row_slot,      (void *)&row_pos,      (void *)&off_a, (void *)&off_b,
+                  (void *)&off_c,    (void *)&gather_frames, (void *)&gather_noise, (void *)&tvec,  (void *)&lsd_steps};
+  if (cudaLaunchCooperativeKernel((void *)step_fused_kernel, dim3(grid), dim3(FT), args, smem, st) != cudaSuccess)
+    return -1;
+  return 2; // memset + kernel
+}
+
+} // namespace ptts
