@@ -110,7 +110,7 @@ EXPORTS = [
     "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
-    "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
+    "ptts_voice_cache_stats", "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
 ]
 
 _lib = None
@@ -159,6 +159,7 @@ def lib() -> C.CDLL:
     L.ptts_debug_fetch.restype = C.c_int64
     L.ptts_profile_enable.argtypes = [vp, C.c_int32]
     L.ptts_debug_tc_force.argtypes = [C.c_int32, C.c_int32]
+    L.ptts_voice_cache_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.ptts_debug_gemm_tma.argtypes = [vp, fp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, fp, fp]
     L.ptts_debug_gemm_bench.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     L.ptts_debug_gemm.argtypes = [vp, fp, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, C.c_int32, fp]
@@ -473,6 +474,12 @@ class NativeCudaRuntime:
         _check(self._lib.ptts_debug_gemm_tma(self._h, _fptr(A), A.shape[0], A.shape[1], taps, _fptr(W), W.shape[0],
                                              _fptr(b), act, _fptr(out), _fptr(sp)))
         return (out, sp) if want_split else out
+
+    def voice_cache_stats(self) -> dict:
+        """Shared voice-prefix cache: sequences admitted on shared KV pages, prefill positions saved, entries."""
+        h, t, n = C.c_int64(), C.c_int64(), C.c_int32()
+        _check(self._lib.ptts_voice_cache_stats(self._h, C.byref(h), C.byref(t), C.byref(n)))
+        return {"hits": h.value, "shared_tokens": t.value, "entries": n.value}
 
     def tc_force(self, bn: int = 0, s: int = 0):
         _check(self._lib.ptts_debug_tc_force(bn, s))

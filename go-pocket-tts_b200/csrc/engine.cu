@@ -1284,11 +1284,122 @@ int Engine::sync_pagetab(Seq *s) {
   return PTTS_OK;
 }
 
+// ---------------------------------------------------------------------------
+// voice prefix cache
+// ---------------------------------------------------------------------------
+static uint64_t fnv1a(const void *p, size_t n) {
+  const unsigned char *c = static_cast<const unsigned char *>(p);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++) {
+    h ^= c[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+VoiceEntry *Engine::voice_lookup(const float *emb, int frames, bool create) {
+  if (!voice_share_on || !emb || frames < page_tokens)
+    return nullptr;
+  const size_t n = (size_t)frames * D;
+  const uint64_t h = fnv1a(emb, n * sizeof(float));
+  for (auto &v : voice_cache)
+    if (v->hash == h && v->frames == frames && memcmp(v->data.data(), emb, n * sizeof(float)) == 0) {
+      v->last_use = ++voice_clock;
+      return v.get();
+    }
+  if (!create)
+    return nullptr;
+  while ((int)voice_cache.size() >= voice_cache_max)
+    if (!voice_evict_one())
+      return nullptr;
+  auto v = std::make_unique<VoiceEntry>();
+  v->hash = h;
+  v->frames = frames;
+  v->data.assign(emb, emb + n);
+  v->last_use = ++voice_clock;
+  voice_cache.push_back(std::move(v));
+  return voice_cache.back().get();
+}
+
+// Drops the least recently used entry that no live sequence maps; its pages return to the pool.
+bool Engine::voice_evict_one() {
+  int best = -1;
+  for (size_t i = 0; i < voice_cache.size(); i++)
+    if (voice_cache[i]->refs == 0 && (best < 0 || voice_cache[i]->last_use < voice_cache[best]->last_use))
+      best = (int)i;
+  if (best < 0)
+    return false;
+  for (int p : voice_cache[best]->pages)
+    free_pages.push_back(p);
+  voice_cache.erase(voice_cache.begin() + best);
+  return true;
+}
+
+// A sequence whose first pages are the entry's shared pages (read-only) followed by its own.
+int Engine::seq_alloc_shared(int tokens_needed, VoiceEntry *v, Seq **out) {
+  if (tokens_needed > cfg.max_seq_tokens)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: sequence needs %d KV tokens, max_seq_tokens is %d", tokens_needed,
+              cfg.max_seq_tokens);
+  const int ns = (int)v->pages.size();
+  int np = (tokens_needed + page_tokens - 1) / page_tokens - ns;
+  if (np < 0)
+    np = 0;
+  if (free_slots.empty())
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: no free sequence slot (max_batch %d)", max_batch);
+  if ((int)free_pages.size() < np)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: KV pool exhausted (%d pages wanted, %zu free)", np, free_pages.size());
+  ptts_seq *ps = new ptts_seq();
+  Seq *s = &ps->impl;
+  s->e = this;
+  s->slot = free_slots.back();
+  free_slots.pop_back();
+  s->voice = v;
+  s->n_shared = ns;
+  v->refs++;
+  s->pages = v->pages;
+  for (int i = 0; i < np; i++) {
+    s->pages.push_back(free_pages.back());
+    free_pages.pop_back();
+  }
+  s->kv_cap = (int)s->pages.size() * page_tokens;
+  s->kv_len = ns * page_tokens; // the shared positions are already in the cache
+  for (size_t i = 0; i < s->pages.size(); i++)
+    h_pagetab[(size_t)s->slot * max_pages + i] = s->pages[i];
+  *out = s;
+  voice_hits++;
+  voice_shared_tokens += s->kv_len;
+  return sync_pagetab(s);
+}
+
+// The first sequence of a voice hands its full voice pages to the cache entry once its
+// prefill has been issued (later users are ordered after it on the stream).
+void Engine::voice_donate(Seq *s, VoiceEntry *v) {
+  if (!s || !v || v->ready || s->voice)
+    return;
+  const int ns = v->frames / page_tokens;
+  if (ns <= 0 || (int)s->pages.size() < ns)
+    return;
+  v->pages.assign(s->pages.begin(), s->pages.begin() + ns);
+  v->ready = true;
+  v->refs++;
+  s->voice = v;
+  s->n_shared = ns;
+}
+
 void Engine::seq_free(Seq *s) {
   if (!s || s->slot < 0)
     return;
-  for (int p : s->pages)
-    free_pages.push_back(p);
+  if (s->voice) {
+    s->voice->refs--;
+    s->voice = nullptr;
+  }
+  for (size_t i = (size_t)s->n_shared; i < s->pages.size(); i++)
+    free_pages.push_back(s->pages[i]);
+  s->n_shared = 0;
+  free_slots.push_back(s->slot);
+  s->slot = -1;
+  s->pages.clear();
+  return;
   free_slots.push_back(s->slot);
   s->slot = -1;
   s->pages.clear();

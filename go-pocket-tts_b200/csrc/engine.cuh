@@ -80,6 +80,20 @@ struct ActSplit {
   }
 };
 
+// Shared voice prefix: the K/V of an `audio_prompt` embedding's first
+// floor(T/16)*16 positions depend only on the embedding, so they are prefilled once, kept in
+// whole KV pages and mapped read-only into the page table of every later sequence with the
+// same voice; each sequence prefills only the remaining voice rows and its text.
+struct VoiceEntry {
+  uint64_t hash = 0;
+  int frames = 0;
+  std::vector<float> data; // exact copy of the embedding (hash collisions are compared away)
+  std::vector<int> pages;  // shared pages, page_tokens positions each
+  int refs = 0;            // live sequences mapping the pages
+  uint64_t last_use = 0;
+  bool ready = false;      // K/V present (the first sequence's prefill has been issued)
+};
+
 struct Seq; // ptts_seq
 struct Request;
 
@@ -289,7 +303,17 @@ struct Engine {
   int upload(const std::vector<float> &v, float **out);
   int upload_key(const std::string &key, float **out, std::vector<int64_t> *shape);
 
+  // voice prefix cache (scheduler path)
+  std::vector<std::unique_ptr<VoiceEntry>> voice_cache;
+  uint64_t voice_clock = 0;
+  int voice_cache_max = 16;
+  bool voice_share_on = true;
+  int64_t voice_hits = 0, voice_shared_tokens = 0;
+  VoiceEntry *voice_lookup(const float *emb, int frames, bool create);
+  bool voice_evict_one();
   // sequence resources
+  int seq_alloc_shared(int tokens_needed, VoiceEntry *v, Seq **out);
+  void voice_donate(Seq *s, VoiceEntry *v);
   int seq_alloc(int tokens_needed, Seq **out);
   void seq_free(Seq *s);
   int sync_pagetab(Seq *s);
@@ -331,6 +355,8 @@ struct Engine {
 struct Seq {
   Engine *e = nullptr;
   int slot = -1;
+  VoiceEntry *voice = nullptr; // shared prefix mapped into the first n_shared pages
+  int n_shared = 0;
   std::vector<int> pages;
   int kv_len = 0;   // tokens in cache
   int kv_cap = 0;   // tokens reserved
@@ -350,6 +376,7 @@ struct Request {
   int64_t pcm_cap = 0;
   int max_steps = 0, lsd_steps = 1;
   // state
+  VoiceEntry *voice_entry = nullptr; // cache entry of this request's voice embedding, if any
   Seq *seq = nullptr;
   bool have_cd = false;
   int countdown = 0;

@@ -160,7 +160,34 @@ void Engine::sched_loop() {
         continue;
       }
       Seq *s = nullptr;
-      int rc = seq_alloc(need, &s);
+      // shared voice prefix: map the cached pages, or (first use) become their donor; a
+      // request whose voice is being prefilled by an earlier one of this batch waits a turn
+      VoiceEntry *ve = r->voice_kv ? nullptr : voice_lookup(r->voice_emb, r->voice_frames, true);
+      if (ve && !ve->ready && ve->refs < 0) {
+        leftover.push_back(r);
+        continue;
+      }
+      int rc;
+      if (ve)
+        ve->refs++; // pin: the evictions below must not take this entry
+      if (ve && ve->ready) {
+        rc = seq_alloc_shared(need, ve, &s);
+        while (rc == PTTS_ENOMEM && voice_evict_one())
+          rc = seq_alloc_shared(need, ve, &s);
+        ve->refs--;
+        if (rc == PTTS_OK)
+          prompt -= s->kv_len; // only the unshared voice rows and the text are prefilled
+      } else {
+        rc = seq_alloc(need, &s);
+        while (rc == PTTS_ENOMEM && voice_evict_one())
+          rc = seq_alloc(need, &s);
+        if (ve) {
+          ve->refs--;
+          if (rc == PTTS_OK)
+            ve->refs = -1; // donor chosen: marks "prefill in flight" until voice_donate()
+        }
+      }
+      r->voice_entry = ve;
       if (rc == PTTS_ENOMEM && (!active.empty() || !pending.empty() || !admitted.empty()) &&
           need <= cfg.max_seq_tokens) {
         leftover.push_back(r); // back-pressure: wait for pages / slots
@@ -195,11 +222,19 @@ void Engine::sched_loop() {
         seqs.push_back(r->seq);
         tok.push_back(r->tokens.data());
         ntok.push_back((int)r->tokens.size());
-        voice.push_back(r->voice_kv ? nullptr : r->voice_emb);
-        nvoice.push_back(r->voice_kv ? 0 : r->voice_frames);
+        // a sequence on shared pages starts at kv_len = shared positions: skip those rows
+        const int skip = r->seq->voice ? r->seq->kv_len : 0;
+        voice.push_back(r->voice_kv || !r->voice_emb ? nullptr : r->voice_emb + (size_t)skip * D);
+        nvoice.push_back(r->voice_kv ? 0 : r->voice_frames - skip);
       }
       if (rc == PTTS_OK)
         rc = prefill(seqs, tok, ntok, voice, nvoice);
+      for (auto &r : admitted)
+        if (r->voice_entry && !r->voice_entry->ready) {
+          r->voice_entry->refs = 0;
+          if (rc == PTTS_OK)
+            voice_donate(r->seq, r->voice_entry);
+        }
       if (rc) {
         std::string msg = last_error();
         for (auto &r : admitted) {
@@ -726,6 +761,19 @@ int ptts_debug_gemm_tma(ptts_engine *e, const float *A, int32_t M, int32_t cin, 
   std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
   cudaSetDevice(e->impl.device);
   return e->impl.debug_gemm_tma(A, M, cin, taps, W, N, bias, act, C, c_split);
+}
+
+int ptts_voice_cache_stats(ptts_engine *e, int64_t *hits, int64_t *shared_tokens, int32_t *entries) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  std::unique_lock<std::mutex> gl(e->impl.gpu_mu);
+  if (hits)
+    *hits = e->impl.voice_hits;
+  if (shared_tokens)
+    *shared_tokens = e->impl.voice_shared_tokens;
+  if (entries)
+    *entries = (int32_t)e->impl.voice_cache.size();
+  return PTTS_OK;
 }
 
 int ptts_debug_tc_force(int32_t bn, int32_t s) {

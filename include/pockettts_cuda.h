@@ -234,6 +234,10 @@ int ptts_debug_gemm(ptts_engine *e, const float *A, int32_t M, int32_t K, const 
                     const float *bias, int32_t act, int32_t path, float *C);
 /* Times one GEMM shape on device data: average microseconds over `reps`
  * launches (CUDA events on the engine stream).  lda < K = overlapping rows. */
+/* Voice prefix cache: requests that carry the same `audio_prompt` embedding share the
+ * KV pages of its first floor(T/16)*16 positions; hits = sequences admitted on shared pages,
+ * shared_tokens = prefill positions they did not recompute, entries = voices currently cached. */
+int ptts_voice_cache_stats(ptts_engine *e, int64_t *hits, int64_t *shared_tokens, int32_t *entries);
 /* Unit-test hook of the TMA-fed GEMM: A [M,cin] is split into bf16 planes on the device;
  * taps > 1 = implicit-GEMM causal conv (W [N, taps*cin], row m sees rows m-taps+1..m, rows < 0 zero).
  * c_split (optional) receives the split-plane copy of the output (hi + lo). */

@@ -388,3 +388,31 @@ def test_pcm16_output_matches_reference_quantiser(small_rt):
     # scale up so the clamp is exercised too: the quantiser is applied to what the device computed
     want = np.trunc(np.clip(f.pcm.astype(np.float64), -1.0, 1.0) * 32767.0).astype(np.int16)
     np.testing.assert_array_equal(q.pcm, want)
+
+
+def test_voice_prefix_is_shared_across_requests(small_rt, small_oracle, pkg):
+    """requests that carry the same audio_prompt embedding map the KV pages of its first
+    floor(T/16)*16 positions instead of prefilling them again; results stay at oracle parity."""
+    tv = 37  # two full 16-token pages shared, 5 voice rows + the text prefilled per request
+    voice = np.sin(0.01 * np.arange(tv * 1024, dtype=np.float64)).astype(np.float32).reshape(1, tv, 1024)
+    ve = pkg.VoiceEmbedding(voice)
+    before = small_rt.voice_cache_stats()
+    toks_a, toks_b = _tokens(6, 31), _tokens(9, 32)
+    a1, pcm_a, lat_a, _ = _gen_both(small_rt, small_oracle, pkg, toks_a, 6, 3, 1, 41, voice_embedding=ve)   # donor
+    a2, _, _, _ = _gen_both(small_rt, small_oracle, pkg, toks_a, 6, 3, 1, 41, voice_embedding=ve)           # shared
+    b, pcm_b, lat_b, _ = _gen_both(small_rt, small_oracle, pkg, toks_b, 7, 4, 1, 42, voice_embedding=ve)    # shared, other text
+    after = small_rt.voice_cache_stats()
+    assert after["hits"] - before["hits"] == 2 and after["shared_tokens"] - before["shared_tokens"] == 2 * 32
+    for got, lat, pcm in ((a1, lat_a, pcm_a), (a2, lat_a, pcm_a), (b, lat_b, pcm_b)):
+        assert got.n_frames == lat.shape[0]
+        assert allclose_ref(got.latents, lat, ABS, REL), np.abs(got.latents - lat).max()
+        assert snr_db(pcm, got.pcm) >= 40.0
+    # concurrent requests with one voice: the first becomes the donor, the rest wait one turn and share
+    noise = pkg.make_noise(6, 0.7, 43)
+    cfg = pkg.RuntimeGenerateConfig(max_steps=6, eos_threshold=1e30, force_eos_step=3, frames_after_eos=1, noise=noise,
+                                    voice_embedding=pkg.VoiceEmbedding(voice * 0.5))
+    pend = [small_rt.submit(toks_a, cfg) for _ in range(5)]
+    outs = [small_rt.wait(p, want_latents=True) for p in pend]
+    for o in outs[1:]:
+        assert np.abs(o.latents - outs[0].latents).max() <= 2e-4 + 1e-3 * np.abs(outs[0].latents).max()
+    assert small_rt.voice_cache_stats()["hits"] - after["hits"] == 4
