@@ -1297,13 +1297,25 @@ static uint64_t fnv1a(const void *p, size_t n) {
   return h;
 }
 
+// Lookup cost matters: it runs on the scheduler thread for every request.  The key is a
+// hash of ~2048 strided samples; a candidate is confirmed by a full compare unless the caller
+// passes the very buffer that was confirmed before (the usual server case: one loaded voice
+// file serving many requests).
 VoiceEntry *Engine::voice_lookup(const float *emb, int frames, bool create) {
   if (!voice_share_on || !emb || frames < page_tokens)
     return nullptr;
   const size_t n = (size_t)frames * D;
-  const uint64_t h = fnv1a(emb, n * sizeof(float));
+  const size_t stride = n / 2048 > 0 ? n / 2048 : 1;
+  uint64_t h = 1469598103934665603ull ^ (uint64_t)n;
+  for (size_t i = 0; i < n; i += stride) {
+    uint32_t u;
+    memcpy(&u, emb + i, 4);
+    h = (h ^ u) * 1099511628211ull;
+  }
   for (auto &v : voice_cache)
-    if (v->hash == h && v->frames == frames && memcmp(v->data.data(), emb, n * sizeof(float)) == 0) {
+    if (v->hash == h && v->frames == frames &&
+        (v->src == emb || memcmp(v->data.data(), emb, n * sizeof(float)) == 0)) {
+      v->src = emb;
       v->last_use = ++voice_clock;
       return v.get();
     }
@@ -1315,6 +1327,7 @@ VoiceEntry *Engine::voice_lookup(const float *emb, int frames, bool create) {
   auto v = std::make_unique<VoiceEntry>();
   v->hash = h;
   v->frames = frames;
+  v->src = emb;
   v->data.assign(emb, emb + n);
   v->last_use = ++voice_clock;
   voice_cache.push_back(std::move(v));
@@ -1408,6 +1421,7 @@ void Engine::seq_free(Seq *s) {
 // Parameter block + launch geometry of the single-kernel B=1 frame.
 int Engine::setup_fused() {
   fused_on = false;
+  voice_share_on = getenv("PTTS_NO_VOICE_SHARING") == nullptr;
   if (getenv("PTTS_NO_FUSED_STEP") || L > FUSED_MAX_LAYERS || depth > FUSED_MAX_LAYERS || Dh != 64 || D % 4 || C % 4 ||
       ldim > 128 || ldim % 4)
     return PTTS_OK;

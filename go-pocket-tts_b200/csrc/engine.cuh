@@ -88,6 +88,7 @@ struct VoiceEntry {
   uint64_t hash = 0;
   int frames = 0;
   std::vector<float> data; // exact copy of the embedding (hash collisions are compared away)
+  const float *src = nullptr; // host buffer last confirmed equal to `data`
   std::vector<int> pages;  // shared pages, page_tokens positions each
   int refs = 0;            // live sequences mapping the pages
   uint64_t last_use = 0;
