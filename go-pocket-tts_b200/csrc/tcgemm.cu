@@ -295,6 +295,7 @@ struct TcItems {
   int total;
   int ntn, S, kb_per, nkb_all;
   int epi_kind; // epi_code() of a compiled epilogue, or -1: generic
+  int cluster;  // 1: the S splits of a tile are one thread-block cluster and reduce through DSMEM
   __device__ __forceinline__ void decode(int i, int &m0, int &n0, int &kb_begin, int &nkb, int &z, int &tile,
                                          int bn) const {
     z = (int)(i % S);
@@ -585,6 +586,8 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (et == 0 && li == 0)
         TC_STAMP(41);
+      if (items.cluster)
+        break; // one item per CTA; the accumulator is reduced across the cluster below
 #pragma unroll 1
       for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
         const int n = n0 + c0 + cf;
@@ -721,6 +724,118 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
       }
     }
   }
+  if (items.cluster) {
+    // ===== split-K across a cluster: every CTA's partial accumulator goes from TMEM straight
+    // into the leader's shared memory (its operand ring is idle by then) through DSMEM; the
+    // leader sums the S partials in split order (deterministic) and runs the epilogue.  No
+    // partials through L2, no atomics, no second kernel. =====
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    int m0, n0, kb_begin, nkb, z, tile;
+    items.decode((int)blockIdx.x, m0, n0, kb_begin, nkb, z, tile, BN);
+    const bool epi_warp = warp >= 2 && warp < 2 + EW;
+    const int q = warp & 3;
+    const int c_first = EW == 8 ? ((warp - 2) >> 2) * 32 : 0;
+    constexpr int C_STEP = EW == 8 ? 64 : 32;
+    if (epi_warp) {
+      uint32_t leader_base;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_base) : "r"(smem_u32(smem)), "r"(0));
+      const uint32_t slot = leader_base + (uint32_t)z * (uint32_t)(TC_BM * BN * 4);
+      const uint32_t stg_addr_c = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
+#pragma unroll 1
+      for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+            "%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // transpose through the warp's staging buffer so that every remote store instruction
+        // covers 4 rows x 128 contiguous bytes (a row-per-lane store is 32 separate 16-byte
+        // DSMEM transactions and ran at ~4 GB/s)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          sts128(stg_addr_c + (uint32_t)(lane * SM::STG_LD + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int row = j * 4 + (lane >> 3);
+          const float4 a = lds128(stg_addr_c + (uint32_t)(row * SM::STG_LD + (lane & 7) * 4) * 4);
+          const uint32_t dst = slot + (uint32_t)(((q * 32 + row) * BN + c0 + (lane & 7) * 4) * 4);
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                       : "memory");
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (epi_warp && z == 0) {
+      const GemmEpi &e = g.epi;
+      const uint32_t stg_addr = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
+      const int rsub = lane >> 3, cf = (lane & 7) * 4;
+      uint32_t rows = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int m = m0 + q * 32 + j * 4 + rsub;
+        if (m < M) {
+          rows |= 1u << j;
+          if (!e.rowmask || e.rowmask[m / e.mask_div])
+            rows |= 0x100u << j;
+        }
+      }
+      const bool full = __all_sync(0xffffffffu, (rows & 0xFFu) == 0xFFu);
+      const uint32_t slots = smem_u32(smem);
+#pragma unroll 1
+      for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
+        const int n = n0 + c0 + cf;
+        const bool nok = n < N;
+        float4 res[8];
+        const bool have_res = e.residual != nullptr;
+        if (have_res) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int m = m0 + q * 32 + j * 4 + rsub;
+            res[j] = (nok && ((rows >> j) & 1)) ? *reinterpret_cast<const float4 *>(e.residual + (long)m * e.ldr + n)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (nok) {
+          if (e.bias)
+            bias4 = __ldg(reinterpret_cast<const float4 *>(e.bias + n));
+          if (e.colscale)
+            cs4 = __ldg(reinterpret_cast<const float4 *>(e.colscale + n));
+        }
+        // sum the S partials of this lane's 8 x 4 outputs in split order into the warp's staging
+        // buffer (each lane reads back only what it wrote)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int row = q * 32 + j * 4 + rsub;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int sp = 0; sp < S; sp++) {
+            const float4 u = lds128(slots + (uint32_t)sp * (uint32_t)(TC_BM * BN * 4) + (uint32_t)((row * BN + c0 + cf) * 4));
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+          }
+          sts128(stg_addr + (uint32_t)((j * 4 + rsub) * SM::STG_LD + cf) * 4, __float_as_uint(a.x), __float_as_uint(a.y),
+                 __float_as_uint(a.z), __float_as_uint(a.w));
+        }
+        if (nok) {
+          const uint32_t rd_addr = stg_addr + (uint32_t)(rsub * SM::STG_LD + cf) * 4;
+          const long m_first = m0 + q * 32 + rsub;
+          epi_rows_dispatch(items.epi_kind, e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res,
+                            full);
+        }
+      }
+    }
+  }
   if (threadIdx.x == 64)
     TC_STAMP(43);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -775,10 +890,16 @@ int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   it.S = S;
   it.total = (int)(tiles * S);
   it.epi_kind = epi_kind_of(g.epi);
+  // split-K through a cluster (DSMEM) when the S partial tiles fit the leader's operand ring
+  static const bool no_cluster = getenv("PTTS_TC_NO_CLUSTER") != nullptr;
+  it.cluster = (ATMA && !no_cluster && S > 1 && S <= 8 && it.total <= tc_num_sms() &&
+                (long)S * TC_BM * BN * 4 <= (long)STAGES * SM::STAGE)
+                   ? 1
+                   : 0;
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
   const CUtensorMap *am = ATMA ? reinterpret_cast<const CUtensorMap *>(g.amap) : map;
-  launch_k(tc_gemm_kernel<BN, STAGES, ATMA, EW>, dim3(grid), dim3(tc_threads(EW, ATMA)), SM::BYTES, st, *map, *am, g,
-           w.N, it);
+  launch_kc(tc_gemm_kernel<BN, STAGES, ATMA, EW>, dim3(grid), dim3(tc_threads(EW, ATMA)), SM::BYTES, st,
+            it.cluster ? S : 1, *map, *am, g, w.N, it);
   return 1;
 }
 template <int BN, int STAGES>
@@ -854,8 +975,13 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
       const double l2_floor = (double)items * kb_per * kb_bytes / 8.0e6;
       if (l2_floor > t)
         t = l2_floor;
-      if (s > 1)
-        t += 5.0 + (b / 64.0) * (2.5 + 1.0 * s);
+      if (s > 1) {
+        // through a cluster (DSMEM) when the partial tiles fit the leader's operand ring
+        // (stages x stage bytes: 160 KB for b = 32, 192 KB otherwise), else through L2
+        const long ring = b == 32 ? 4L * 40960 : 196608L;
+        const bool cl = atma && s <= 8 && items <= sms && (long)s * 128 * b * 4 <= ring;
+        t += cl ? 3.5 + (b / 64.0) * (1.0 + 0.5 * s) : 5.0 + (b / 64.0) * (2.5 + 1.0 * s); // measured
+      }
       if (t < best) {
         best = t;
         bn = b;
