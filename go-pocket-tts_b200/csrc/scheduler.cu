@@ -616,12 +616,19 @@ int ptts_decode(ptts_engine *e, ptts_seq *seq, int32_t first_frame, int32_t n_fr
   const int spf = E.info.samples_per_frame;
   if (first_frame == 0)
     return E.decode_seqs({&seq->impl}, {0}, {n_frames}, {pcm_out}, true);
-  // causal stack: decode the prefix and hand back the requested tail
-  std::vector<float> tmp((size_t)(first_frame + n_frames) * spf);
-  int rc = E.decode_seqs({&seq->impl}, {0}, {first_frame + n_frames}, {tmp.data()}, true);
+  // Frame-level streaming in bounded work per emitted frame: the decoder is
+  // causal with a finite receptive field — ML transformer layers of window Mctx rows (RoPE
+  // is relative, LayerNorm per row), then convolutions reaching back a few rows — so the
+  // samples of frame f depend only on the latent frames f - ctx .. f.  Decode that window
+  // and hand back the requested tail.
+  const int ctx = (E.ML * (E.Mctx > 0 ? E.Mctx - 1 : 8192) + 8 + E.up_stride - 1) / E.up_stride + 1;
+  const int start = first_frame > ctx ? first_frame - ctx : 0;
+  const int span = first_frame + n_frames - start;
+  std::vector<float> tmp((size_t)span * spf);
+  int rc = E.decode_seqs({&seq->impl}, {start}, {span}, {tmp.data()}, true);
   if (rc)
     return rc;
-  memcpy(pcm_out, tmp.data() + (size_t)first_frame * spf, (size_t)n_frames * spf * 4);
+  memcpy(pcm_out, tmp.data() + (size_t)(first_frame - start) * spf, (size_t)n_frames * spf * 4);
   return PTTS_OK;
 }
 

@@ -416,3 +416,21 @@ def test_voice_prefix_is_shared_across_requests(small_rt, small_oracle, pkg):
     for o in outs[1:]:
         assert np.abs(o.latents - outs[0].latents).max() <= 2e-4 + 1e-3 * np.abs(outs[0].latents).max()
     assert small_rt.voice_cache_stats()["hits"] - after["hits"] == 4
+
+
+def test_streaming_decode_uses_a_bounded_window(small_rt, pkg):
+    """ptts_decode(seq, first, n) re-decodes only the receptive field of the requested
+    frames (1 transformer layer x window 250 rows + conv context = 18 frames in the small model),
+    and the samples match the whole-chunk decode."""
+    toks = _tokens(9, 51)
+    s = small_rt.seq_open(toks, reserve_frames=64)
+    noise = pkg.make_noise(48, 0.7, 52)
+    for i in range(48):
+        small_rt.step([s], noise[i])
+    whole = s.decode(0, 48)
+    for first, n in ((0, 1), (17, 2), (30, 1), (47, 1), (40, 8)):
+        part = s.decode(first, n)
+        ref = whole[first * 1920:(first + n) * 1920]
+        assert snr_db(ref, part) >= 60.0, (first, n, snr_db(ref, part))
+        np.testing.assert_allclose(part, ref, atol=2e-3, rtol=1e-3)
+    s.close()
