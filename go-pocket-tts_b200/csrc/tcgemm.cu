@@ -562,6 +562,115 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     const int c_first = EW == 8 ? ((warp - 2) >> 2) * 32 : 0;
     constexpr int C_STEP = EW == 8 ? 64 : 32;
     const int rsub = lane >> 3, cf = (lane & 7) * 4;     // coalesced phase: 4 rows x 32 columns per instruction
+    if (S == 1 && !items.cluster) {
+      // ---- software-pipelined epilogue (the common case).  A unit is one 32-column chunk
+      // of one item.  The TMEM load of unit u+1 (and its residual rows) is issued right
+      // after unit u's accumulator chunk has been parked in the staging buffer, so it is in
+      // flight while unit u's rows are processed and stored: the short-K shapes are bound
+      // by this warp's latency chain, not by its instruction count. ----
+      struct UnitCtx {
+        int m0, n0, c0, b;
+        uint32_t rows;
+        bool full, nok, last_chunk, have_res;
+        float4 bias4, cs4;
+        float4 res[8];
+      };
+      const int nch = (BN - c_first + C_STEP - 1) / C_STEP; // chunks of an item this warp owns
+      const int my_items = ((int)items.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int nunits = c_first < BN ? my_items * nch : 0;
+      uint32_t v[32];
+      uint32_t rows_item = 0;
+      bool full_item = false;
+      int im0 = 0, in0 = 0;
+      auto issue = [&](int u, UnitCtx &c) {
+        const int li2 = u / nch, j = u - li2 * nch;
+        c.b = li2 & 1;
+        c.c0 = c_first + j * C_STEP;
+        c.last_chunk = j == nch - 1;
+        if (j == 0) {
+          int kb_begin, nkb, z, tile;
+          items.decode((int)blockIdx.x + li2 * (int)gridDim.x, im0, in0, kb_begin, nkb, z, tile, BN);
+          rows_item = 0;
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) {
+            const int m = im0 + q * 32 + jj * 4 + rsub;
+            if (m < M) {
+              rows_item |= 1u << jj;
+              if (!e.rowmask || e.rowmask[m / e.mask_div])
+                rows_item |= 0x100u << jj;
+            }
+          }
+          full_item = __all_sync(0xffffffffu, (rows_item & 0xFFu) == 0xFFu);
+          mbar_wait(&acc_full[c.b], (uint32_t)(li2 >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        c.m0 = im0;
+        c.n0 = in0;
+        c.rows = rows_item;
+        c.full = full_item;
+        const int n = in0 + c.c0 + cf;
+        c.nok = n < N;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c.b * BN + c.c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+            "%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        c.have_res = e.residual != nullptr;
+        if (c.have_res) {
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) {
+            const int m = im0 + q * 32 + jj * 4 + rsub;
+            c.res[jj] = (c.nok && ((rows_item >> jj) & 1))
+                            ? *reinterpret_cast<const float4 *>(e.residual + (long)m * e.ldr + n)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        c.bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        c.cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (c.nok) {
+          if (e.bias)
+            c.bias4 = __ldg(reinterpret_cast<const float4 *>(e.bias + n));
+          if (e.colscale)
+            c.cs4 = __ldg(reinterpret_cast<const float4 *>(e.colscale + n));
+        }
+      };
+      UnitCtx cur, nxt;
+      if (nunits > 0)
+        issue(0, nxt);
+      for (int u = 0; u < nunits; u++) {
+        cur = nxt;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          sts128(stg_addr + (uint32_t)(lane * SM::STG_LD + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        if (cur.last_chunk) { // this warp has read all of its share of the accumulator
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&acc_empty[cur.b]);
+        }
+        if (u + 1 < nunits)
+          issue(u + 1, nxt);
+        if (cur.nok) {
+          const uint32_t rd_addr = stg_addr + (uint32_t)(rsub * SM::STG_LD + cf) * 4;
+          const long m_first = cur.m0 + q * 32 + rsub;
+          epi_rows_dispatch(items.epi_kind, e, rd_addr, SM::STG_LD * 4, m_first, cur.n0 + cur.c0 + cf, cur.rows, cur.bias4,
+                            cur.cs4, cur.res, cur.have_res, cur.full);
+        }
+        __syncwarp(); // staging is rewritten by the next unit
+      }
+      if (c_first >= BN) { // a warp without columns (EW = 8, BN = 32) still releases the accumulators
+        for (int k = 0; k < my_items; k++) {
+          mbar_wait(&acc_full[k & 1], (uint32_t)(k >> 1) & 1);
+          mbar_arrive(&acc_empty[k & 1]);
+        }
+      }
+    } else {
     uint32_t li = 0;
     for (int i = blockIdx.x; i < items.total; i += gridDim.x, li++) {
       int m0, n0, kb_begin, nkb, z;
@@ -723,6 +832,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
         }
       }
     }
+    } // S > 1 / cluster path
   }
   if (items.cluster) {
     // ===== split-K across a cluster: every CTA's partial accumulator goes from TMEM straight
