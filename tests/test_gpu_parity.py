@@ -434,3 +434,49 @@ def test_streaming_decode_uses_a_bounded_window(small_rt, pkg):
         assert snr_db(ref, part) >= 60.0, (first, n, snr_db(ref, part))
         np.testing.assert_allclose(part, ref, atol=2e-3, rtol=1e-3)
     s.close()
+
+
+def test_scheduler_stress_mixed_requests(pkg, small_tensors):
+    """Mixed traffic on one engine under slot / KV-page pressure: plain, voice-conditioned (two voices sharing
+    the prefix cache, which must evict under pressure), PCM16 and cancelled requests.  Every request ends
+    with OK or 'context canceled'; survivors equal the same request generated alone."""
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=6, max_seq_tokens=192, max_frames=24,
+                               mimi_group_frames=48, kv_pages=40)
+    try:
+        voices = [pkg.VoiceEmbedding(np.sin(0.01 * (k + 1) * np.arange(35 * 1024)).astype(np.float32).reshape(1, 35, 1024))
+                  for k in range(2)]
+        specs = []
+        for i in range(36):
+            ms = 5 + i % 7
+            kw = dict(max_steps=ms, eos_threshold=1e30, force_eos_step=ms - 3, frames_after_eos=1,
+                      noise=pkg.make_noise(ms, 0.7, 900 + i))
+            if i % 3 == 1:
+                kw["voice_embedding"] = voices[(i // 3) % 2]
+            if i % 5 == 2:
+                kw["pcm16"] = True
+            specs.append((_tokens(4 + i % 9, 800 + i), kw))
+        pend = [rt.submit(t, pkg.RuntimeGenerateConfig(**kw)) for t, kw in specs]
+        cancelled = set(range(3, 36, 6))
+        for i in cancelled:
+            rt.cancel(pend[i])
+        outs = {}
+        for i, p in enumerate(pend):
+            try:
+                outs[i] = rt.wait(p, want_latents=True)
+            except pkg.NativeCudaError as e:
+                assert i in cancelled and "canceled" in str(e), (i, str(e))
+        assert len(outs) >= 36 - len(cancelled)
+        assert rt.voice_cache_stats()["hits"] > 0
+        for i in (0, 1, 2, 7, 16, 22, 34):
+            if i not in outs:
+                continue
+            t, kw = specs[i]
+            solo = rt.generate(t, pkg.RuntimeGenerateConfig(**kw), want_latents=True)
+            assert solo.n_frames == outs[i].n_frames
+            assert np.all(np.abs(solo.latents - outs[i].latents) <= 2e-4 + 1e-3 * np.abs(solo.latents)), i
+            if kw.get("pcm16"):
+                assert outs[i].pcm.dtype == np.int16 and np.abs(outs[i].pcm.astype(np.int32) - solo.pcm).max() <= 8
+            else:
+                assert snr_db(solo.pcm, outs[i].pcm) >= 40.0, i
+    finally:
+        rt.close()
