@@ -1165,6 +1165,10 @@ int Engine::finalize() {
       if ((rc = make_conv_map(sm_ye[s], res1[s].cin, res1[s].taps, &res1[s].amap))) return rc;
       if (res2[s].taps != 1)
         if ((rc = make_conv_map(sm_he[s], res2[s].cin, res2[s].taps, &res2[s].amap))) return rc;
+      if (s == 1 && up[s].cout == 128) { // the fused block of this stage writes here; up[s+1] reads it
+        if ((rc = make_act(sm_yf[s], r2, up[s].cout, lead))) return rc;
+        if ((rc = make_conv_map(sm_yf[s], up[s + 1].cin, up[s + 1].taps, &up_alt_amap[s + 1]))) return rc;
+      }
     }
   }
   if ((rc = dmalloc((void **)&d_mrow_pos, Rb * 4))) return rc;
@@ -2017,18 +2021,52 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
   conv_gemm(init_conv, m_x, sm_x, Rb, 1, nullptr, f32(m_y0e), &sm_y0e, nullptr);
   const float *cur = m_y0e;
   const ActSplit *curs = &sm_y0e;
+  bool cur_alt = false; // the previous stage's fused block wrote sm_yf instead of sm_ye
   int rows = Rb, div = 1;
   for (int s = 0; s < 3; s++) {
-    conv_gemm(up[s], cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr); // rows*stride outputs
+    if (cur_alt) {
+      DConvG u = up[s];
+      u.amap = up_alt_amap[s];
+      conv_gemm(u, cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr);
+    } else
+      conv_gemm(up[s], cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr); // rows*stride outputs
+    cur_alt = false;
     rows *= up[s].stride;
     div *= up[s].stride;
-    conv_gemm(res1[s], m_ye[s], sm_ye[s], rows, div, nullptr, f32(m_he[s]), &sm_he[s], nullptr);
-    // elu(x + conv2(..)); the last stage feeds the fp32 final conv
+    // elu(x + conv2(elu(conv1(elu(x))))); the last stage feeds the fp32 final conv
     const bool last = s == 2;
-    conv_gemm(res2[s], m_he[s], sm_he[s], rows, div, nullptr, (last || !sp_on) ? m_ye[s] : nullptr,
-              last ? nullptr : &sm_ye[s], m_y[s]);
+    bool fused = false;
+    static const bool no_rb = getenv("PTTS_NO_FUSED_RESBLOCK") != nullptr;
+    if (sp_on && !no_rb && res1[s].amap && res2[s].taps == 1 && (last || (sm_yf[s].p && up_alt_amap[s + 1]))) {
+      auto w1 = tc_map.find(res1[s].w), w2 = tc_map.find(res2[s].w);
+      if (w1 != tc_map.end() && w2 != tc_map.end()) {
+        cudaEvent_t pa, pb;
+        if (prof_on)
+          prof_begin(&pa, &pb);
+        const int n = resblock_fused(*w1->second, *w2->second, res1[s].amap, (int)sm_ye[s].plane_rows, rows, res1[s].cin,
+                                     res1[s].cout, res1[s].taps, res1[s].b, res2[s].b, m_y[s], d_mmask, div,
+                                     last ? m_ye[s] : nullptr, last ? SplitOut() : sm_yf[s].out(), st);
+        if (prof_on) {
+          const double c = res1[s].cin, h = res1[s].cout;
+          prof_end(pa, pb, n ? "resblock_fused" : "none", 2.0 * rows * (3 * c * h + h * c), 4.0 * rows * 3 * c,
+                   s == 2 ? "shape/resblock3" : "shape/resblock2");
+        }
+        nl += n;
+        fused = n > 0;
+      }
+    }
+    const ActSplit *next_src = &sm_ye[s];
+    if (fused && !last) {
+      next_src = &sm_yf[s];
+      cur_alt = true;
+    }
+    if (!fused) {
+      conv_gemm(res1[s], m_ye[s], sm_ye[s], rows, div, nullptr, f32(m_he[s]), &sm_he[s], nullptr);
+      conv_gemm(res2[s], m_he[s], sm_he[s], rows, div, nullptr, (last || !sp_on) ? m_ye[s] : nullptr,
+                last ? nullptr : &sm_ye[s], m_y[s]);
+    }
     cur = m_ye[s];
-    curs = &sm_ye[s];
+    curs = next_src;
   }
   PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, pcm, st));
   const int spb = div; // samples per base row

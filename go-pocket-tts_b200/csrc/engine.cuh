@@ -157,6 +157,10 @@ struct Engine {
   // split activation planes (A operands of the tcgen05 GEMMs)
   ActSplit s_nrm, s_att, s_ff, s_in, s_last, s_sy, s_cur, s_h, s_h2;
   ActSplit sm_latin, sm_nrm, sm_att, sm_ff, sm_x, sm_y0e, sm_ye[3], sm_he[3];
+  // output of a fused residual block (its input planes are still being read as halo rows by
+  // neighbouring tiles, so it cannot be written in place) + the next up-conv's map over it
+  ActSplit sm_yf[3];
+  void *up_alt_amap[3] = {nullptr, nullptr, nullptr};
   std::vector<void *> host_maps;
   int make_act(ActSplit &a, long rows_cap, int K, int lead);
   // conv form of an activation's map: {cin, taps, rows} over the same planes

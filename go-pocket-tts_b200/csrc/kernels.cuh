@@ -92,6 +92,14 @@ void tc_force_tile(int bn, int s);
 // Same contract as gemm(); W is taken from `w` (g.W is ignored).
 int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant);
 
+// One SEANet residual block (mimi.go:146-164) as a single kernel (resblock.cu):
+//   out = elu(y + b2 + W2 . elu(b1 + W1 . [e(r-2), e(r-1), e(r)])),  e = elu(y) as split planes
+// behind `amap` ({C, 3, rows} conv map).  C in {64, 128}, H = C/2.  Returns the number of
+// launches, 0 when the shape is not supported (nothing launched).
+int resblock_fused(const TcWeight &w1, const TcWeight &w2, const void *amap, int a_lo_row, int M, int C, int H, int taps,
+                   const float *b1, const float *b2, const float *y, const uint8_t *rowmask, int mask_div, float *out,
+                   SplitOut outs, cudaStream_t st);
+
 // out[m] = dot(A[m,:K], w) + bias0   (N == 1 linear: out_eos)
 int rowdot(const float *A, long lda, const float *w, float bias0, int M, int K,
            float *out, cudaStream_t st);
