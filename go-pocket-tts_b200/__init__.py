@@ -43,24 +43,44 @@ class NativeCudaError(RuntimeError):
 # ---------------------------------------------------------------------------
 # build
 # ---------------------------------------------------------------------------
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-ffp-contract=off"]
+OBJ_DIR = os.path.join(PKG_DIR, "csrc", "_obj")
+
+
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
+    """The one-shot equivalent of what build_library does per file."""
     srcs = [os.path.join(PKG_DIR, "csrc", s) for s in CSRC]
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", out, *srcs]
+    return ["nvcc", *NVCC_FLAGS, "-shared", "-o", out, *srcs]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into the in-tree shared library."""
-    srcs = [os.path.join(PKG_DIR, "csrc", s) for s in os.listdir(os.path.join(PKG_DIR, "csrc"))]
-    srcs.append(os.path.join(REPO_ROOT, "include", "pockettts_cuda.h"))
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(s) for s in srcs)
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
-    cmd = nvcc_command()
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    """Compile every CUDA source for sm_100a into the in-tree shared library: one object per
+    source (rebuilt when the source or any header is newer), compiled in parallel, then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    cdir = os.path.join(PKG_DIR, "csrc")
+    headers = [os.path.join(cdir, h) for h in os.listdir(cdir) if h.endswith((".cuh", ".h", ".hpp"))]
+    headers.append(os.path.join(REPO_ROOT, "include", "pockettts_cuda.h"))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    src_time = max(os.path.getmtime(os.path.join(cdir, n)) for n in CSRC)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(hdr_time, src_time):
+        return LIB_PATH  # e.g. on the GPU box: the built library travels, the objects do not
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs, objs = [], []
+    for name in CSRC:
+        src = os.path.join(cdir, name)
+        obj = os.path.join(OBJ_DIR, name + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            jobs.append(["nvcc", *NVCC_FLAGS, "-c", "-o", obj, src])
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        list(ex.map(run, jobs))
+    run(["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB_PATH, *objs])
     return LIB_PATH
 
 

@@ -45,7 +45,7 @@ template <class KeyFn, class ValFn>
 __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp,
                                            ValFn valp, float *out, float *scores,
                                            float *red, float4 *pv, const SplitOut &sp, long sp_row,
-                                           int sp_col) {
+                                           int sp_col, uint2 *ll_out = nullptr, unsigned ll_tag = 0) {
   const int tid = threadIdx.x;
   const float scale = 0.125f; // 1/sqrt(64)
   // phase 1
@@ -113,6 +113,14 @@ __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp
       *reinterpret_cast<float4 *>(out + tid * 4) = r;
     if (sp.hi)
       split_store4(sp, sp_row, sp_col + tid * 4, r);
+    if (ll_out) { // (value, tag) words for the flag-in-data exchange of step_fused.cu
+      const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(ll_out + tid * 4 + e),
+                     "r"(__float_as_uint(rv[e])), "r"(ll_tag)
+                     : "memory");
+    }
   }
 }
 

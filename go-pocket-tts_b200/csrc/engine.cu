@@ -1427,7 +1427,7 @@ int Engine::setup_fused() {
   fused_on = false;
   voice_share_on = getenv("PTTS_NO_VOICE_SHARING") == nullptr;
   if (getenv("PTTS_NO_FUSED_STEP") || L > FUSED_MAX_LAYERS || depth > FUSED_MAX_LAYERS || Dh != 64 || D % 4 || C % 4 ||
-      ldim > 128 || ldim % 4)
+      ldim > 128 || ldim % 4 || F % 4 || rb[0].mlp0.out % 4 || ada_n % 2)
     return PTTS_OK;
   FusedParams hp{};
   hp.D = D; hp.H = H; hp.F = F; hp.L = L; hp.C = C; hp.hid = rb[0].mlp0.out; hp.depth = depth; hp.ldim = ldim;
@@ -1463,6 +1463,23 @@ int Engine::setup_fused() {
   *h_fused_err = 0;
   hp.barrier = d_fused_bar;
   hp.error = d_fused_err;
+  // which frame kernel: PTTS_FUSED_LL=1 flag-in-data exchange, =0 grid barriers
+  {
+    const char *v = getenv("PTTS_FUSED_LL");
+    fused_ll = v ? atoi(v) != 0 : FUSED_LL_DEFAULT;
+  }
+  {
+    const size_t words = step_fused_ll_words(hp);
+    uint2 *llbuf = nullptr;
+    if ((rc = dmalloc((void **)&llbuf, (words + 2) * sizeof(uint2)))) return rc;
+    CUDA_TRY(cudaMemset(llbuf, 0, (words + 2) * sizeof(uint2)));
+    step_fused_ll_assign(hp, llbuf);
+    hp.epoch = reinterpret_cast<unsigned *>(llbuf + words); // first tag 1: zeroed words never match
+    const unsigned one = 1;
+    CUDA_TRY(cudaMemcpy(hp.epoch, &one, sizeof one, cudaMemcpyHostToDevice));
+    const char *ns = getenv("PTTS_FUSED_POLL_NS");
+    hp.poll_ns = ns ? atoi(ns) : 0;
+  }
   hp.dbg = nullptr;
   if (getenv("PTTS_FUSED_TIMELINE")) {
     if ((rc = dmalloc((void **)&fused_dbg, 512 * sizeof(unsigned long long)))) return rc;
@@ -1473,7 +1490,7 @@ int Engine::setup_fused() {
   FusedParams sized = hp;
   sized.F = hidmax;
   fused_smem = step_fused_smem(sized, cfg.max_seq_tokens);
-  fused_grid = step_fused_grid(fused_smem);
+  fused_grid = step_fused_grid(fused_smem, fused_ll);
   if (fused_grid <= 0)
     return PTTS_OK; // cannot be resident: keep the multi-kernel path
   int coop = 0;
@@ -1719,7 +1736,7 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     if (rc)
       return rc;
     const int n = step_fused_launch(d_fused, fused_grid, fused_smem, d_row_slot, d_row_pos, d_off_a, d_off_b, d_off_c,
-                                    gather_frames ? 1 : 0, gather_noise ? 1 : 0, tv, lsd_steps, d_fused_bar, st);
+                                    gather_frames ? 1 : 0, gather_noise ? 1 : 0, tv, lsd_steps, d_fused_bar, fused_ll, st);
     if (n < 0) {
       cudaGetLastError();
       PTTS_FAIL(PTTS_ECUDA, "cuda: cooperative launch of the fused frame kernel failed");

@@ -179,7 +179,7 @@ struct Engine {
   unsigned long long *fused_dbg = nullptr;
   int fused_grid = 0;
   size_t fused_smem = 0;
-  bool fused_on = false;
+  bool fused_on = false, fused_ll = true;
   int setup_fused();
 
   // ---- split-K scratch for skinny GEMMs ----

@@ -425,22 +425,434 @@ __global__ void __launch_bounds__(FT, 2)
 #undef PHASE_BEGIN_LN
 }
 
+// ===========================================================================================
+// Flag-in-data variant.  The grid barrier above costs three dependent L2 round trips per
+// phase (fence + arrive, poll, staging loads).  Here every activation that crosses CTAs is an
+// 8-byte (value, tag) word written with ONE relaxed 64-bit store by the lane that produced
+// it; consumers poll the data itself until every word carries the tag of the producing phase
+// (8-byte accesses are single-copy atomic, so a word is either old or new, never torn).  No
+// counters, no fences, no arrive: producer store -> L2 -> consumer load is the whole
+// hand-over, and a consumer only waits for the words it reads (an attention CTA for the 192
+// q/k/v columns of its head).  Tags are `epoch + phase index`, unique per phase and launch;
+// `epoch` lives in device memory so the launch can be replayed from a CUDA graph.
+//
+// Why one buffer per tensor is enough (no double buffering).  Writes of phase p happen after
+// the writer staged the outputs of phase p-1 it needs; by induction over the phases every
+// CTA that read anything in a phase q < p has finished those reads (a CTA only reads in a
+// phase in which it owns columns, and it publishes its columns after its reads).  What a
+// phase must not do is write a tensor that the SAME phase stages; the phase list below never
+// does (x is updated in place by out_proj / linear2, which stage att / ff; fx by mlp2, which
+// stages h2; cur by the final layer, which stages fx and ada).
+namespace {
+
+struct Poll {
+  int *err;
+  int sleep_ns;
+  bool dead;
+};
+__device__ __forceinline__ void ll_st(uint2 *buf, int n, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(buf + n), "r"(__float_as_uint(v)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ll_ld2(const uint2 *p) { // two words; each half is atomic on its own
+  uint4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 ll_ld1(const uint2 *p) {
+  uint2 r;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+// After a failed poll: back off, give up after ~seconds (a missing producer must not hang the GPU).
+__device__ __forceinline__ bool poll_fail(Poll &pl, int &spins) {
+  if (pl.sleep_ns)
+    __nanosleep(pl.sleep_ns);
+  if (++spins > 3000000 || ((spins & 1023) == 0 && *reinterpret_cast<volatile int *>(pl.err) != 0)) {
+    atomicExch(pl.err, 1);
+    pl.dead = true;
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ float ll_get1(const uint2 *buf, int n, unsigned tag, Poll &pl) {
+  uint2 r = ll_ld1(buf + n);
+  int spins = 0;
+  while (r.y != tag && !pl.dead) {
+    if (poll_fail(pl, spins))
+      break;
+    r = ll_ld1(buf + n);
+  }
+  return __uint_as_float(r.x);
+}
+__device__ __forceinline__ float2 ll_get2(const uint2 *buf, int n, unsigned tag, Poll &pl) {
+  uint4 r = ll_ld2(buf + n);
+  int spins = 0;
+  while ((r.y != tag || r.w != tag) && !pl.dead) {
+    if (poll_fail(pl, spins))
+      break;
+    r = ll_ld2(buf + n);
+  }
+  return make_float2(__uint_as_float(r.x), __uint_as_float(r.z));
+}
+// sA[0:K] <- values of buf[0:K] once they all carry `tag` (K even).  Thread t owns the pairs
+// 2t + 2*FT*u; up to four 16-byte loads are in flight per thread before the first check.
+__device__ __forceinline__ void ll_stage_raw(float *sA, const uint2 *buf, int K, unsigned tag, Poll &pl) {
+  for (int i0 = 2 * threadIdx.x; i0 < K; i0 += 8 * FT) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + 2 * FT * u;
+      if (i < K)
+        r[u] = ll_ld2(buf + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + 2 * FT * u;
+      if (i < K) {
+        int spins = 0;
+        while ((r[u].y != tag || r[u].w != tag) && !pl.dead) {
+          if (poll_fail(pl, spins))
+            break;
+          r[u] = ll_ld2(buf + i);
+        }
+        *reinterpret_cast<float2 *>(sA + i) = make_float2(__uint_as_float(r[u].x), __uint_as_float(r[u].z));
+      }
+    }
+  }
+}
+__device__ __forceinline__ void ll_stage_plain(float *sA, const uint2 *buf, int K, unsigned tag, Poll &pl) {
+  ll_stage_raw(sA, buf, K, tag, pl);
+  __syncthreads();
+}
+// As stage_ln, from (value, tag) words; the adaLN scale / shift vectors (also tagged) are staged
+// behind the row at sA[K:2K] / sA[2K:3K].  Every pass touches only the thread's own pairs.
+__device__ __forceinline__ void ll_stage_ln(float *sA, float *red, const uint2 *src, int K, unsigned tag, const float *w,
+                                            const float *b, float eps, const uint2 *scale, const uint2 *shift,
+                                            unsigned ada_tag, Poll &pl) {
+  ll_stage_raw(sA, src, K, tag, pl);
+  if (scale) {
+    ll_stage_raw(sA + K, scale, K, ada_tag, pl);
+    ll_stage_raw(sA + 2 * K, shift, K, ada_tag, pl);
+  }
+  float s = 0.0f;
+  for (int i = 2 * threadIdx.x; i < K; i += 2 * FT)
+    s += sA[i] + sA[i + 1];
+  const float mean = block_sum(s, red) / (float)K;
+  float q = 0.0f;
+  for (int i = 2 * threadIdx.x; i < K; i += 2 * FT) {
+    const float d0 = sA[i] - mean, d1 = sA[i + 1] - mean;
+    q += d0 * d0 + d1 * d1;
+  }
+  const float inv = 1.0f / sqrtf(block_sum(q, red) / (float)K + eps);
+  for (int i0 = 2 * threadIdx.x; i0 < K; i0 += 2 * FT) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = i0 + e;
+      float t = (sA[i] - mean) * inv;
+      if (w)
+        t *= __ldg(w + i);
+      if (b)
+        t += __ldg(b + i);
+      if (scale)
+        t = t * (sA[K + i] + 1.0f) + sA[2 * K + i];
+      sA[i] = t;
+    }
+  }
+  __syncthreads();
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(FT, 2)
+    step_fused_ll_kernel(const FusedParams *__restrict__ Pp, const int32_t *row_slot, const int32_t *row_pos,
+                         const int64_t *off_a, const int64_t *off_b, const int64_t *off_c, int gather_frames,
+                         int gather_noise, const float *tvec, int lsd_steps) {
+  extern __shared__ float dsm[]; // activation vector (+ adaLN scale / shift) / attention scores
+  __shared__ float red[FT / 32];
+  __shared__ float4 pv[8 * 16];
+  __shared__ __align__(16) float q_s[HD];
+  const FusedParams &P = *Pp;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * FT + threadIdx.x) >> 5;
+  const int gw0 = (blockIdx.x * FT) >> 5; // first warp of this CTA
+  const int nw = (gridDim.x * FT) >> 5;
+  float *sA = dsm;
+  const int D = P.D, F = P.F, C = P.C, ldim = P.ldim;
+  const int slot = row_slot[0], pos = row_pos[0];
+  Poll pl{P.error, P.poll_ns, false};
+  const unsigned base = __ldcg(P.epoch);
+  unsigned T = base; // tag of the phase being produced
+  Pref pf;
+  Pref2 pf2;
+  int nstamp = 0;
+  FSTAMP();
+  auto gemv_now = [&](const float *W, int N, int K, const float *a, int gw2, auto epi) {
+    Pref q;
+    Pref2 q2;
+    prefetch_w(q, W, N, K, gw2, nw, lane);
+    prefetch_w2(q2, W, N, K, gw2, nw, lane);
+    gemv_cols(q, q2, W, N, K, a, gw2, nw, lane, epi);
+  };
+  // the first weight batch of a phase is requested before anything is polled: it is in
+  // flight while the producers of the previous phase finish
+#define LL_PREFETCH(W, N, K, LW, LB, KLN)                                      \
+  do {                                                                         \
+    T++;                                                                       \
+    prefetch_w(pf, W, N, K, gw, nw, lane);                                     \
+    prefetch_w2(pf2, W, N, K, gw, nw, lane);                                   \
+    l1_prefetch(LW, (size_t)(KLN) * 4);                                        \
+    l1_prefetch(LB, (size_t)(KLN) * 4);                                        \
+    __syncthreads(); /* the previous phase's dots are done with sA */          \
+  } while (0)
+  const float *noise0 = gather_noise ? P.noise_pool + off_c[0] : P.fh_noise;
+
+  // ---- phase 0: x = input_linear(nan_to_bos(frame)) ----
+  if (gw0 < D || blockIdx.x == 0) {
+    const float *frame = gather_frames ? P.hist + off_a[0] : P.fh_frames;
+    if (threadIdx.x < ldim) {
+      const float v = ldcg1(frame + threadIdx.x);
+      const float u = isnan(v) ? __ldg(P.bos + threadIdx.x) : v;
+      sA[threadIdx.x] = u;
+      if (blockIdx.x == 0)
+        P.fh_in[threadIdx.x] = u;
+    }
+    __syncthreads();
+    gemv_now(P.in_w, D, ldim, sA, gw, [&](int n, float v) { ll_st(P.ll_x, n, v + bias_at(P.in_b, n), T); });
+  }
+  unsigned t_x = T;
+  for (int l = 0; l < P.L; l++) {
+    const FusedLayer &ly = P.layer[l];
+    // ---- qkv = in_proj(LN1(x)) ----
+    LL_PREFETCH(ly.in_proj, 3 * D, D, ly.n1w, ly.n1b, D);
+    if (gw0 < 3 * D) {
+      ll_stage_ln(sA, red, P.ll_x, D, t_x, ly.n1w, ly.n1b, ly.eps1, nullptr, nullptr, 0, pl);
+      FSTAMP();
+      gemv_cols(pf, pf2, ly.in_proj, 3 * D, D, sA, gw, nw, lane, [&](int n, float v) { ll_st(P.ll_qkv, n, v, T); });
+    }
+    const unsigned t_qkv = T;
+    // ---- RoPE, KV append, attention: one CTA per head, which waits only for the 192 q/k/v
+    //      words of its head; everybody else goes straight on to poll att ----
+    T++;
+    prefetch_w(pf, ly.out_proj, D, D, gw, nw, lane);
+    __syncthreads(); // the in_proj dots of this CTA are done with sA (= the scores below)
+    if ((int)blockIdx.x < P.H) {
+      const int h = blockIdx.x, half = HD / 2;
+      const KvGeom &kv = P.kv;
+      const int PT = kv.page_tokens;
+      const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
+      const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
+      float *page = kv.pool + (long)pt[pos / PT] * page_stride;
+      const int tok = pos % PT;
+      const long koff = ((long)(l * 2 + 0) * kv.n_heads + h) * PT * HD;
+      const long voff = ((long)(l * 2 + 1) * kv.n_heads + h) * PT * HD;
+      if (threadIdx.x < half) { // interleaved pairs (rope.go:81-105)
+        const int j = threadIdx.x;
+        const float c = __ldg(P.rope_cos + (long)pos * half + j), s = __ldg(P.rope_sin + (long)pos * half + j);
+        const float2 qq = ll_get2(P.ll_qkv, h * HD + 2 * j, t_qkv, pl);
+        const float2 kk = ll_get2(P.ll_qkv, D + h * HD + 2 * j, t_qkv, pl);
+        q_s[2 * j] = qq.x * c - qq.y * s;
+        q_s[2 * j + 1] = qq.x * s + qq.y * c;
+        float *dst = page + koff + (long)tok * HD + 2 * j;
+        dst[0] = kk.x * c - kk.y * s;
+        dst[1] = kk.x * s + kk.y * c;
+      } else if (threadIdx.x < half + HD) {
+        const int d = threadIdx.x - half;
+        page[voff + (long)tok * HD + d] = ll_get1(P.ll_qkv, 2 * D + h * HD + d, t_qkv, pl);
+      }
+      __syncthreads();
+      FSTAMP();
+      const float *pool = kv.pool;
+      auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
+      auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
+      attend_row(q_s, pos + 1, keyp, valp, nullptr, dsm, red, pv, SplitOut(), 0, 0, P.ll_att + h * HD, T);
+      __syncthreads(); // scores (dsm) are restaged as the activation vector below
+    }
+    const unsigned t_att = T;
+    // ---- x += out_proj(att) ----
+    T++;
+    prefetch_w2(pf2, ly.out_proj, D, D, gw, nw, lane);
+    FSTAMP();
+    if (gw0 < D) {
+      ll_stage_plain(sA, P.ll_att, D, t_att, pl);
+      FSTAMP();
+      float pre = 0.0f; // the residual of this warp's first column, in flight during the dot
+      if (lane == 0 && gw < D)
+        pre = ll_get1(P.ll_x, gw, t_x, pl);
+      gemv_cols(pf, pf2, ly.out_proj, D, D, sA, gw, nw, lane, [&](int n, float v) {
+        const float xo = n == gw ? pre : ll_get1(P.ll_x, n, t_x, pl);
+        ll_st(P.ll_x, n, xo + v, T);
+      });
+    }
+    t_x = T;
+    // ---- ff = gelu(linear1(LN2(x))) ----
+    LL_PREFETCH(ly.l1, F, D, ly.n2w, ly.n2b, D);
+    if (gw0 < F) {
+      ll_stage_ln(sA, red, P.ll_x, D, t_x, ly.n2w, ly.n2b, ly.eps2, nullptr, nullptr, 0, pl);
+      FSTAMP();
+      gemv_cols(pf, pf2, ly.l1, F, D, sA, gw, nw, lane,
+                [&](int n, float v) { ll_st(P.ll_ff, n, act_apply(v, ACT_GELU), T); });
+    }
+    const unsigned t_ff = T;
+    // ---- x += linear2(ff) ----
+    LL_PREFETCH(ly.l2, D, F, nullptr, nullptr, 0);
+    if (gw0 < D) {
+      ll_stage_plain(sA, P.ll_ff, F, t_ff, pl);
+      FSTAMP();
+      float pre = 0.0f;
+      if (lane == 0 && gw < D)
+        pre = ll_get1(P.ll_x, gw, t_x, pl);
+      gemv_cols(pf, pf2, ly.l2, D, F, sA, gw, nw, lane, [&](int n, float v) {
+        const float xo = n == gw ? pre : ll_get1(P.ll_x, n, t_x, pl);
+        ll_st(P.ll_x, n, xo + v, T);
+      });
+    }
+    t_x = T;
+  }
+  // ---- last = out_norm(x); eos = last . w_eos + b; cproj = cond_embed(last) ----
+  LL_PREFETCH(P.ce_w, C, D, P.on_w, P.on_b, D);
+  if (gw0 < C) { // CTA 0 always owns column 0
+    ll_stage_ln(sA, red, P.ll_x, D, t_x, P.on_w, P.on_b, P.on_eps, nullptr, nullptr, 0, pl);
+    FSTAMP();
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < D; i += FT)
+        P.fh_last[i] = sA[i];
+    gemv_cols(pf, pf2, P.ce_w, C, D, sA, gw, nw, lane,
+              [&](int n, float v) { ll_st(P.ll_cproj, n, v + bias_at(P.ce_b, n), T); });
+    if (gw == 0) // the EOS logit is one more column
+      gemv_now(P.eos_w, 1, D, sA, 0, [&](int, float v) { P.fh_eos[0] = v + P.eos_b; });
+  }
+  const unsigned t_cproj = T;
+  unsigned t_cur = 0;
+  const float inv_steps = 1.0f / (float)lsd_steps;
+  for (int it = 0; it < lsd_steps; it++) {
+    // ---- ada = adaLN_all(silu(cproj + t_emb)); fx = input_proj(cur) ----
+    LL_PREFETCH(P.ada_w, P.ada_n, C, nullptr, nullptr, 0);
+    if (gw0 < P.ada_n || gw0 < C) {
+      ll_stage_raw(sA, P.ll_cproj, C, t_cproj, pl);
+      if (it == 0) { // the flow starts from the noise (an input of the launch)
+        for (int i = threadIdx.x; i < ldim; i += FT)
+          sA[C + i] = ldcg1(noise0 + i);
+      } else {
+        ll_stage_raw(sA + C, P.ll_cur, ldim, t_cur, pl);
+      }
+      for (int i0 = 2 * threadIdx.x; i0 < C; i0 += 2 * FT) { // own pairs of ll_stage_raw
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const float y = sA[i0 + e] + __ldg(tvec + (long)it * C + i0 + e);
+          sA[i0 + e] = y / (1.0f + expf(-y));
+        }
+      }
+      __syncthreads();
+      FSTAMP();
+      gemv_cols(pf, pf2, P.ada_w, P.ada_n, C, sA, gw, nw, lane,
+                [&](int n, float v) { ll_st(P.ll_ada, n, v + bias_at(P.ada_b, n), T); });
+      gemv_now(P.ip_w, C, ldim, sA + C, gw, [&](int n, float v) { ll_st(P.ll_fx, n, v + bias_at(P.ip_b, n), T); });
+    }
+    const unsigned t_ada = T;
+    unsigned t_fx = T;
+    for (int b = 0; b < P.depth; b++) {
+      const FusedRes &rb = P.rb[b];
+      const uint2 *shift = P.ll_ada + (long)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
+      // ---- h2 = silu(mlp0(modulate(LN(fx)))) ----
+      LL_PREFETCH(rb.mlp0w, P.hid, C, rb.lnw, rb.lnb, C);
+      if (gw0 < P.hid) {
+          ll_stage_ln(sA, red, P.ll_fx, C, t_fx, rb.lnw, rb.lnb, rb.eps, scale, shift, t_ada, pl);
+        FSTAMP();
+        gemv_cols(pf, pf2, rb.mlp0w, P.hid, C, sA, gw, nw, lane, [&](int n, float v) {
+          ll_st(P.ll_h2, n, act_apply(v + bias_at(rb.mlp0b, n), ACT_SILU), T);
+        });
+      }
+      const unsigned t_h2 = T;
+      // ---- fx += gate * mlp2(h2) ----
+      LL_PREFETCH(rb.mlp2w, C, P.hid, nullptr, nullptr, 0);
+      if (gw0 < C) {
+          ll_stage_plain(sA, P.ll_h2, P.hid, t_h2, pl);
+        FSTAMP();
+        float pre_g = 0.0f, pre_x = 0.0f;
+        if (lane == 0 && gw < C) {
+          pre_g = ll_get1(gate, gw, t_ada, pl);
+          pre_x = ll_get1(P.ll_fx, gw, t_fx, pl);
+        }
+        gemv_cols(pf, pf2, rb.mlp2w, C, P.hid, sA, gw, nw, lane, [&](int n, float v) {
+          const float g = n == gw ? pre_g : ll_get1(gate, n, t_ada, pl);
+          const float xo = n == gw ? pre_x : ll_get1(P.ll_fx, n, t_fx, pl);
+          ll_st(P.ll_fx, n, (v + bias_at(rb.mlp2b, n)) * g + xo, T);
+        });
+      }
+      t_fx = T;
+    }
+    // ---- cur += final(modulate(LN(fx))) / steps ----
+    const uint2 *fshift = P.ll_ada + (long)P.depth * 3 * C, *fscale = fshift + C;
+    LL_PREFETCH(P.fin_w, ldim, C, nullptr, nullptr, 0);
+    if (gw0 < ldim) {
+      ll_stage_ln(sA, red, P.ll_fx, C, t_fx, nullptr, nullptr, 1e-6f, fscale, fshift, t_ada, pl);
+      FSTAMP();
+      const bool last_it = it == lsd_steps - 1;
+      const bool first_it = it == 0;
+      const unsigned t_prev = t_cur;
+      gemv_cols(pf, pf2, P.fin_w, ldim, C, sA, gw, nw, lane, [&](int n, float v) {
+        const float co = first_it ? ldcg1(noise0 + n) : ll_get1(P.ll_cur, n, t_prev, pl);
+        const float c = (v + bias_at(P.fin_b, n)) * inv_steps + co;
+        if (!last_it)
+          ll_st(P.ll_cur, n, c, T);
+        else {
+          P.fh_cur[n] = c;
+          P.hist_w[off_b[0] + n] = c; // the new latent frame of this sequence
+        }
+      });
+    }
+    t_cur = T;
+  }
+  FSTAMP();
+  // Everybody that polls has read `epoch` long before CTA 0 gets here (CTA 0 consumed words
+  // that depend on every producing CTA's first phase).
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    *P.epoch = T + 1;
+#undef LL_PREFETCH
+}
+
 size_t step_fused_smem(const FusedParams &hp, int max_keys) {
   int n = hp.F;
   if (max_keys > n)
     n = max_keys;
+  if (3 * hp.C > n) // row + adaLN scale + shift (flag-in-data variant)
+    n = 3 * hp.C;
   if (hp.C + hp.ldim > n)
     n = hp.C + hp.ldim;
   return (size_t)((n + 15) / 16 * 16) * sizeof(float);
 }
 
-int step_fused_grid(size_t smem) {
+namespace {
+inline size_t ev2(size_t n) { return (n + 1) & ~(size_t)1; } // 16-byte aligned sub-buffers
+} // namespace
+size_t step_fused_ll_words(const FusedParams &hp) {
+  return ev2(hp.D) + ev2(3 * (size_t)hp.D) + ev2(hp.D) + ev2(hp.F) + ev2(hp.C) + ev2(hp.ada_n) + ev2(hp.C) +
+         ev2(hp.hid) + ev2(hp.ldim);
+}
+void step_fused_ll_assign(FusedParams &hp, uint2 *p) {
+  hp.ll_x = p;      p += ev2(hp.D);
+  hp.ll_qkv = p;    p += ev2(3 * (size_t)hp.D);
+  hp.ll_att = p;    p += ev2(hp.D);
+  hp.ll_ff = p;     p += ev2(hp.F);
+  hp.ll_cproj = p;  p += ev2(hp.C);
+  hp.ll_ada = p;    p += ev2(hp.ada_n);
+  hp.ll_fx = p;     p += ev2(hp.C);
+  hp.ll_h2 = p;     p += ev2(hp.hid);
+  hp.ll_cur = p;
+}
+
+int step_fused_grid(size_t smem, bool ll) {
   int dev = 0, sms = 0, occ = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaFuncSetAttribute(step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  const void *fn = ll ? (const void *)step_fused_ll_kernel : (const void *)step_fused_kernel;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_fused_kernel, FT, smem) != cudaSuccess || occ < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, FT, smem) != cudaSuccess || occ < 1)
     return 0;
   if (occ > 2)
     occ = 2;
@@ -449,14 +861,16 @@ int step_fused_grid(size_t smem) {
 
 int step_fused_launch(const FusedParams *dp, int grid, size_t smem, const int32_t *row_slot, const int32_t *row_pos,
                       const int64_t *off_a, const int64_t *off_b, const int64_t *off_c, int gather_frames,
-                      int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier, cudaStream_t st) {
-  if (cudaMemsetAsync(barrier, 0, STEP_FUSED_BARRIER_BYTES, st) != cudaSuccess)
+                      int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier, bool ll, cudaStream_t st) {
+  if (!ll && cudaMemsetAsync(barrier, 0, STEP_FUSED_BARRIER_BYTES, st) != cudaSuccess)
     return -1;
   void *args[] = {(void *)&dp,       (void *)&row_slot,      (void *)&row_pos,      (void *)&off_a, (void *)&off_b,
                   (void *)&off_c,    (void *)&gather_frames, (void *)&gather_noise, (void *)&tvec,  (void *)&lsd_steps};
-  if (cudaLaunchCooperativeKernel((void *)step_fused_kernel, dim3(grid), dim3(FT), args, smem, st) != cudaSuccess)
+  // cooperative in both variants: co-residency of all CTAs is what makes the spinning legal
+  void *fn = ll ? (void *)step_fused_ll_kernel : (void *)step_fused_kernel;
+  if (cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FT), args, smem, st) != cudaSuccess)
     return -1;
-  return 2; // memset + kernel
+  return ll ? 1 : 2; // (memset +) kernel
 }
 
 } // namespace ptts

@@ -13,6 +13,8 @@ struct FusedRes {
   float eps;
 };
 constexpr int FUSED_MAX_LAYERS = 8;
+// default frame kernel when PTTS_FUSED_LL is unset (flag-in-data exchange vs grid barriers)
+constexpr bool FUSED_LL_DEFAULT = false;
 constexpr size_t STEP_FUSED_BARRIER_BYTES = 8192; // top + per-group counters, 128 B apart (<= 63 groups)
 
 // Lives in device memory (one copy per engine); every pointer is a device pointer.
@@ -37,16 +39,24 @@ struct FusedParams {
   const float *hist, *noise_pool;
   float *hist_w;
   unsigned *barrier;
+  // flag-in-data exchange (step_fused_ll_kernel): every cross-CTA activation lives as
+  // (value, tag) 8-byte words; `epoch` holds the first tag of the next launch
+  uint2 *ll_x, *ll_qkv, *ll_att, *ll_ff, *ll_cproj, *ll_ada, *ll_fx, *ll_h2, *ll_cur;
+  unsigned *epoch;
+  int poll_ns; // back-off between failed polls (0: none)
   int *error;
   unsigned long long *dbg; // optional timeline of CTA 0 (globaltimer), tools only
 };
 
 size_t step_fused_smem(const FusedParams &hp, int max_keys);
-// CTAs of a cooperative launch (0: the kernel cannot be resident)
-int step_fused_grid(size_t smem);
+// (value, tag) words the flag-in-data variant needs behind FusedParams::ll_*
+size_t step_fused_ll_words(const FusedParams &hp);
+void step_fused_ll_assign(FusedParams &hp, uint2 *base);
+// CTAs of a cooperative launch (0: the kernel cannot be resident); ll selects the kernel
+int step_fused_grid(size_t smem, bool ll);
 // returns the number of stream operations enqueued, < 0 on a launch error
 int step_fused_launch(const FusedParams *dp, int grid, size_t smem, const int32_t *row_slot, const int32_t *row_pos,
                       const int64_t *off_a, const int64_t *off_b, const int64_t *off_c, int gather_frames,
-                      int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier, cudaStream_t st);
+                      int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier, bool ll, cudaStream_t st);
 
 } // namespace ptts

@@ -110,3 +110,32 @@ def test_pcm_is_prefix_stable(full_rt, pkg):
     assert long.n_frames == 30 and short.n_frames == 12
     np.testing.assert_array_equal(long.latents[:12], short.latents)
     assert snr_db(long.pcm[: 12 * 1920], short.pcm) >= 60.0
+
+
+def test_fused_frame_kernel_variants_agree(pkg, full_tensors, monkeypatch):
+    """The batch-1 frame kernel exists twice: flag-in-data exchange (PTTS_FUSED_LL=1) and grid
+    barriers (PTTS_FUSED_LL=0).  Both compute every dot product in the same order; only the LayerNorm
+    partial sums are grouped differently, so 24 fed-back frames (1 and 2 LSD steps) agree far inside
+    the latent tolerance, and the flag-in-data kernel is deterministic across engines."""
+    toks = _tokens(22, 11)
+
+    def run(lsd):
+        rt = pkg.NativeCudaRuntime(tensors=full_tensors, max_batch=4, max_seq_tokens=256, max_frames=64,
+                                   mimi_group_frames=64)
+        try:
+            cfg = _cfg(pkg, 24, 20, 12, lsd_decode_steps=lsd)
+            return rt.generate(toks, cfg, want_latents=True)
+        finally:
+            rt.close()
+
+    for lsd in (1, 2):
+        monkeypatch.setenv("PTTS_FUSED_LL", "1")
+        a = run(lsd)
+        a2 = run(lsd)
+        monkeypatch.setenv("PTTS_FUSED_LL", "0")
+        b = run(lsd)
+        assert a.n_frames == b.n_frames == 23
+        np.testing.assert_array_equal(a.latents, a2.latents)
+        assert np.all(np.abs(a.latents - b.latents) <= 1e-5 + 1e-4 * np.abs(b.latents)), \
+            (lsd, np.abs(a.latents - b.latents).max())
+        assert snr_db(b.pcm, a.pcm) >= 60.0

@@ -5,7 +5,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
-body = rows[h + 1:]
+body = [r for r in rows[h + 1:] if len(r) == len(hdr)]  # two kernels in one report: skip the second header
 ci = {n: i for i, n in enumerate(hdr)}
 S, X = ci["# Samples"], ci["Instructions Executed"]
 stall_cols = [i for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
