@@ -1479,6 +1479,10 @@ int Engine::setup_fused() {
     CUDA_TRY(cudaMemcpy(hp.epoch, &one, sizeof one, cudaMemcpyHostToDevice));
     const char *ns = getenv("PTTS_FUSED_POLL_NS");
     hp.poll_ns = ns ? atoi(ns) : 0;
+    const char *la = getenv("PTTS_FUSED_L2_AHEAD");
+    hp.l2_ahead = la ? atoi(la) : FUSED_L2_AHEAD_DEFAULT;
+    if (hp.l2_ahead < 0 || hp.l2_ahead > 8)
+      hp.l2_ahead = 0;
   }
   hp.dbg = nullptr;
   if (getenv("PTTS_FUSED_TIMELINE")) {

@@ -53,6 +53,58 @@ __device__ __forceinline__ void l1_prefetch(const void *p, size_t bytes) {
 }
 __device__ __forceinline__ float bias_at(const float *b, int n) { return b ? __ldg(b + n) : 0.0f; }
 
+// ---- L2 look-ahead ----
+// The weights do not depend on the activations, so their HBM stream need not stop at the phase
+// boundaries: while phase i computes, the rows this warp will read in phase i + l2_ahead are
+// requested into L2 with bulk prefetches (one instruction per row, no registers, not in the
+// L1tex FIFO).  The register loads of a phase then hit L2, and HBM stays busy across the
+// exchanges between phases.  Weight phases in order: per layer in_proj, out_proj, linear1,
+// linear2; cond_embed; per LSD step adaLN_all, per block mlp0, mlp2, final.
+__device__ __forceinline__ bool phase_weights(const FusedParams &P, int idx, int lsd_steps, const float *&W, int &N,
+                                              int &K) {
+  if (idx < 4 * P.L) {
+    const FusedLayer &ly = P.layer[idx >> 2];
+    switch (idx & 3) {
+    case 0: W = ly.in_proj; N = 3 * P.D; K = P.D; break;
+    case 1: W = ly.out_proj; N = P.D; K = P.D; break;
+    case 2: W = ly.l1; N = P.F; K = P.D; break;
+    default: W = ly.l2; N = P.D; K = P.F; break;
+    }
+    return true;
+  }
+  idx -= 4 * P.L;
+  if (idx == 0) {
+    W = P.ce_w; N = P.C; K = P.D;
+    return true;
+  }
+  idx -= 1;
+  const int per = 2 + 2 * P.depth;
+  if (idx >= lsd_steps * per)
+    return false;
+  const int j = idx % per;
+  if (j == 0) {
+    W = P.ada_w; N = P.ada_n; K = P.C;
+  } else if (j == per - 1) {
+    W = P.fin_w; N = P.ldim; K = P.C;
+  } else {
+    const FusedRes &rb = P.rb[(j - 1) >> 1];
+    if ((j - 1) & 1) {
+      W = rb.mlp2w; N = P.C; K = P.hid;
+    } else {
+      W = rb.mlp0w; N = P.hid; K = P.C;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void l2_prefetch_phase(const FusedParams &P, int idx, int lsd_steps, int gw, int nw, int lane) {
+  const float *W;
+  int N, K;
+  if (!phase_weights(P, idx, lsd_steps, W, N, K))
+    return;
+  for (int n = gw + lane * nw; n < N; n += 32 * nw) // lane i: the warp's i-th column, the whole row
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + (long)n * K), "r"(K * 4) : "memory");
+}
+
 // Grid barrier on 16 striped counters (one 128-byte line each).  Same-address atomics
 // serialise in L2 (~27 cycles each): one counter costs ~4 us for 296 CTAs, a two-level tree
 // two dependent round trips, per-CTA flags polled by everybody flood L2.  Here CTA b adds to
@@ -265,6 +317,15 @@ __global__ void __launch_bounds__(FT, 2)
   Pref2 pf2;
   int nstamp = 0;
   FSTAMP();
+  int wph = 0; // index of the weight phase being started (see phase_weights)
+#define L2_AHEAD()                                                             \
+  do {                                                                         \
+    if (P.l2_ahead > 0)                                                        \
+      l2_prefetch_phase(P, wph + P.l2_ahead, lsd_steps, gw, nw, lane);         \
+    wph++;                                                                     \
+  } while (0)
+  for (int a = 0; a < P.l2_ahead; a++)
+    l2_prefetch_phase(P, a, lsd_steps, gw, nw, lane);
 // publish the previous phase, request the first weight segments of the next one, wait for
 // everybody, request the rest of the first batch (they land while the vector is staged)
 #define PHASE_BEGIN(W, N, K) PHASE_BEGIN_LN(W, N, K, nullptr, nullptr, 0)
@@ -272,6 +333,7 @@ __global__ void __launch_bounds__(FT, 2)
   do {                                                                         \
     grid_arrive(bar);                                                          \
     prefetch_w(pf, W, N, K, gw, nw, lane);                                     \
+    L2_AHEAD();                                                                \
     l1_prefetch(LW, (size_t)(KLN) * 4);                                        \
     l1_prefetch(LB, (size_t)(KLN) * 4);                                        \
     grid_wait(bar);                                                            \
@@ -314,6 +376,7 @@ __global__ void __launch_bounds__(FT, 2)
     //      out_proj segments when they reach the next barrier ----
     grid_arrive(bar);
     prefetch_w(pf, ly.out_proj, D, D, gw, nw, lane);
+    L2_AHEAD();
     grid_wait(bar);
     FSTAMP();
     if ((int)blockIdx.x < P.H) {
@@ -423,6 +486,7 @@ __global__ void __launch_bounds__(FT, 2)
   FSTAMP();
 #undef PHASE_BEGIN
 #undef PHASE_BEGIN_LN
+#undef L2_AHEAD
 }
 
 // ===========================================================================================
@@ -599,16 +663,26 @@ __global__ void __launch_bounds__(FT, 2)
   };
   // the first weight batch of a phase is requested before anything is polled: it is in
   // flight while the producers of the previous phase finish
+#define L2_AHEAD()                                                             \
+  do {                                                                         \
+    if (P.l2_ahead > 0)                                                        \
+      l2_prefetch_phase(P, wph + P.l2_ahead, lsd_steps, gw, nw, lane);         \
+    wph++;                                                                     \
+  } while (0)
 #define LL_PREFETCH(W, N, K, LW, LB, KLN)                                      \
   do {                                                                         \
     T++;                                                                       \
     prefetch_w(pf, W, N, K, gw, nw, lane);                                     \
     prefetch_w2(pf2, W, N, K, gw, nw, lane);                                   \
+    L2_AHEAD();                                                                \
     l1_prefetch(LW, (size_t)(KLN) * 4);                                        \
     l1_prefetch(LB, (size_t)(KLN) * 4);                                        \
     __syncthreads(); /* the previous phase's dots are done with sA */          \
   } while (0)
   const float *noise0 = gather_noise ? P.noise_pool + off_c[0] : P.fh_noise;
+  int wph = 0; // index of the weight phase being started (see phase_weights)
+  for (int a = 0; a < P.l2_ahead; a++)
+    l2_prefetch_phase(P, a, lsd_steps, gw, nw, lane);
 
   // ---- phase 0: x = input_linear(nan_to_bos(frame)) ----
   if (gw0 < D || blockIdx.x == 0) {
@@ -638,6 +712,7 @@ __global__ void __launch_bounds__(FT, 2)
     //      words of its head; everybody else goes straight on to poll att ----
     T++;
     prefetch_w(pf, ly.out_proj, D, D, gw, nw, lane);
+    L2_AHEAD();
     __syncthreads(); // the in_proj dots of this CTA are done with sA (= the scores below)
     if ((int)blockIdx.x < P.H) {
       const int h = blockIdx.x, half = HD / 2;
@@ -813,6 +888,7 @@ __global__ void __launch_bounds__(FT, 2)
   if (blockIdx.x == 0 && threadIdx.x == 0)
     *P.epoch = T + 1;
 #undef LL_PREFETCH
+#undef L2_AHEAD
 }
 
 size_t step_fused_smem(const FusedParams &hp, int max_keys) {

@@ -15,6 +15,7 @@ struct FusedRes {
 constexpr int FUSED_MAX_LAYERS = 8;
 // default frame kernel when PTTS_FUSED_LL is unset (flag-in-data exchange vs grid barriers)
 constexpr bool FUSED_LL_DEFAULT = false;
+constexpr int FUSED_L2_AHEAD_DEFAULT = 0; // PTTS_FUSED_L2_AHEAD: weight phases prefetched into L2 ahead of use
 constexpr size_t STEP_FUSED_BARRIER_BYTES = 8192; // top + per-group counters, 128 B apart (<= 63 groups)
 
 // Lives in device memory (one copy per engine); every pointer is a device pointer.
@@ -44,6 +45,7 @@ struct FusedParams {
   uint2 *ll_x, *ll_qkv, *ll_att, *ll_ff, *ll_cproj, *ll_ada, *ll_fx, *ll_h2, *ll_cur;
   unsigned *epoch;
   int poll_ns; // back-off between failed polls (0: none)
+  int l2_ahead; // weight phases whose rows are bulk-prefetched into L2 ahead of their use (0: off)
   int *error;
   unsigned long long *dbg; // optional timeline of CTA 0 (globaltimer), tools only
 };
