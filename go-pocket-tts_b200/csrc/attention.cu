@@ -304,6 +304,44 @@ __global__ void __launch_bounds__(256)
   const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
   float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
   const int tok = pos % PT;
+  if (D <= 4 * (int)blockDim.x) {
+    // Same arithmetic with every load of the thread issued before the first store: qkv and the
+    // page may alias as far as the compiler knows, so the loops below run one dependent memory
+    // round trip per iteration (11 us per launch, once per layer per frame).
+    float a[4], b[4], cj[4], sj[4], vv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p = threadIdx.x + k * blockDim.x;
+      if (p < D) {
+        const int isk = p >= D / 2;
+        const int pp = isk ? p - D / 2 : p;
+        const int h = pp / half, j = pp % half;
+        const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
+        a[k] = src[0];
+        b[k] = src[1];
+        cj[k] = c[j];
+        sj[k] = s[j];
+        vv[k] = row[2 * D + p];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p = threadIdx.x + k * blockDim.x;
+      if (p < D) {
+        const int isk = p >= D / 2;
+        const int pp = isk ? p - D / 2 : p;
+        const int h = pp / half, j = pp % half;
+        const float o0 = a[k] * cj[k] - b[k] * sj[k];
+        const float o1 = a[k] * sj[k] + b[k] * cj[k];
+        float *dst = isk ? page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + 2 * j
+                         : row + h * HD + 2 * j;
+        dst[0] = o0;
+        dst[1] = o1;
+        page[((long)(layer * 2 + 1) * H + p / HD) * PT * HD + (long)tok * HD + p % HD] = vv[k];
+      }
+    }
+    return;
+  }
   // q and k pairs
   for (int p = threadIdx.x; p < D; p += blockDim.x) { // D/2 pairs each for q,k
     const int isk = p >= D / 2;
