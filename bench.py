@@ -30,9 +30,17 @@ import tempfile
 import threading
 import time
 
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's
+# back (NCCL prints its version banner there at every debug level above NONE), so fd 1 is pointed
+# at stderr for the whole process and the JSON line goes to a private duplicate of the real stdout.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str) -> None:
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -190,7 +198,7 @@ def main():
         v = tot_a / tot_t
         sample = (f"{cores} chunks (first of the workload) capped at {args.cpu_sample_frames} frames each, "
                   f"one chunk per host thread")
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -394,7 +402,7 @@ def main():
                       f"frames each ({nfr} frames), one chunk per host thread, {t:.1f} s of wall time",
             "note": "C restatement of the reference path (oracle/); the Go reference cannot be built here"}
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     rt.close()
     if world > 1:
         dist.destroy_process_group()
