@@ -140,3 +140,19 @@ def test_workload_follows_reference_chunking_rules():
     # determinism of the shard: same seed, same chunks
     again = wl.make_workload(200, 5, 60, seed=7)
     assert all(np.array_equal(a.tokens, b.tokens) for a, b in zip(chunks, again))
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line whatever the libraries print (NCCL's banner
+    goes to fd 1); checked on the CPU-only reference arm with a tiny sample."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--arch", "small", "--cpu-sample-frames", "2"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
