@@ -14,6 +14,14 @@
 //   * activations cross phases through L2 (`ld.global.cg`: L1 is not coherent across SMs).
 // Grid = 2 CTAs of 128 threads per SM, launched cooperatively (co-residency is what makes
 // the barrier legal); a spin that exceeds ~1 s raises an error flag instead of hanging.
+//
+// Two kernels share the weight streaming and staging code and differ in how a phase hands its
+// output vector to the next one: step_fused_kernel (grid barrier, default) and
+// step_fused_ll_kernel (flag-in-data words polled by the consumers, PTTS_FUSED_LL=1); both can
+// bulk-prefetch the weight rows of later phases into L2 (PTTS_FUSED_L2_AHEAD).  Measured on
+// B200: 266 / 277 us per frame, look-ahead slower in both (profiles/fused_matrix_r01e.txt) —
+// the frame is bound by bytes / ~3 TB/s + ~3 us per phase whichever exchange is used; see
+// DESIGN.md section 4 for the analysis and the planned TMA-fed shared-memory weight ring.
 #include "step_fused.cuh"
 #include "attend.cuh"
 #include "gemm_epi.cuh"
