@@ -258,6 +258,51 @@ __device__ __forceinline__ void gemv_cols(const Pref &p, const Pref2 &p2, const 
   }
 }
 
+// K == SEG_K / 2 (the adaLN projection, 10240 x 512): a 1024-wide register segment would be
+// half empty and a warp's eight or nine columns would take three dependent batches.  Two
+// consecutive rows are contiguous in memory, so the matrix is read as [N/2, 2K]: one segment =
+// one row pair, the activation vector is staged twice back to back (sA2[k] == sA2[k + K]) and the
+// two halves of the lane's partial sums go to the two rows.  Per-lane summation order and the
+// shuffles are those of gemv_cols, so the results are bit-identical.
+template <class Epi>
+__device__ __forceinline__ void gemv_pairs(const Pref &p, const Pref2 &p2, const float *W, int NP, const float *sA2,
+                                           int gw, int nw, int lane, Epi epi) {
+  const int ncols = gw < NP ? (NP - gw + nw - 1) / nw : 0; // row pairs of this warp
+  auto finish = [&](int seg, const float4 (&w)[8]) {
+    float lo = 0.0f, hi = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      lo = dot4(*reinterpret_cast<const float4 *>(sA2 + lane * 4 + 128 * u), w[u], lo);
+#pragma unroll
+    for (int u = 4; u < 8; u++)
+      hi = dot4(*reinterpret_cast<const float4 *>(sA2 + lane * 4 + 128 * u), w[u], hi);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo += __shfl_xor_sync(0xffffffffu, lo, o);
+      hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    if (lane == 0) {
+      const int m = gw + seg * nw;
+      epi(2 * m, lo);
+      epi(2 * m + 1, hi);
+    }
+  };
+  if (ncols > 0) finish(0, p.w[0]);
+  if (ncols > 1) finish(1, p.w[1]);
+  if (ncols > 2) finish(2, p2.w[0]);
+  if (ncols > 3) finish(3, p2.w[1]);
+  for (int s0 = 4; s0 < ncols; s0 += 4) {
+    float4 w[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      seg_load(w[j], W, NP, SEG_K, 1, gw, nw, s0 + j, lane); // beyond ncols: n >= NP -> zeros, no loads
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (s0 + j < ncols)
+        finish(s0 + j, w[j]);
+  }
+}
+
 __device__ __forceinline__ float block_sum(float v, float *red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -449,18 +494,30 @@ __global__ void __launch_bounds__(FT, 2)
   const float inv_steps = 1.0f / (float)lsd_steps;
   for (int it = 0; it < lsd_steps; it++) {
     // ---- ada = adaLN_all(silu(cproj + t_emb)); fx = input_proj(cur) ----
-    PHASE_BEGIN(P.ada_w, P.ada_n, C);
+    const bool pair_ada = 2 * C == SEG_K && (P.ada_n & 1) == 0; // see gemv_pairs
+    float *sCur = sA + (pair_ada ? 2 * C : C);
+    if (pair_ada)
+      PHASE_BEGIN(P.ada_w, P.ada_n / 2, 2 * C);
+    else
+      PHASE_BEGIN(P.ada_w, P.ada_n, C);
     for (int i = threadIdx.x; i < C; i += FT) {
-      const float y = ldcg1(P.fh_cproj + i) + __ldg(tvec + (long)it * C + i);
-      sA[i] = y / (1.0f + expf(-y));
+      float y = ldcg1(P.fh_cproj + i) + __ldg(tvec + (long)it * C + i);
+      y = y / (1.0f + expf(-y));
+      sA[i] = y;
+      if (pair_ada)
+        sA[C + i] = y;
     }
     for (int i = threadIdx.x; i < ldim; i += FT)
-      sA[C + i] = ldcg1(P.fh_cur + i);
+      sCur[i] = ldcg1(P.fh_cur + i);
     __syncthreads();
     FSTAMP();
-    gemv_cols(pf, pf2, P.ada_w, P.ada_n, C, sA, gw, nw, lane,
-              [&](int n, float v) { P.fh_ada[n] = v + bias_at(P.ada_b, n); });
-    gemv_now(P.ip_w, C, ldim, sA + C, gw, [&](int n, float v) { P.fh_x[n] = v + bias_at(P.ip_b, n); });
+    if (pair_ada)
+      gemv_pairs(pf, pf2, P.ada_w, P.ada_n / 2, sA, gw, nw, lane,
+                 [&](int n, float v) { P.fh_ada[n] = v + bias_at(P.ada_b, n); });
+    else
+      gemv_cols(pf, pf2, P.ada_w, P.ada_n, C, sA, gw, nw, lane,
+                [&](int n, float v) { P.fh_ada[n] = v + bias_at(P.ada_b, n); });
+    gemv_now(P.ip_w, C, ldim, sCur, gw, [&](int n, float v) { P.fh_x[n] = v + bias_at(P.ip_b, n); });
     for (int b = 0; b < P.depth; b++) {
       const FusedRes &rb = P.rb[b];
       const float *shift = P.fh_ada + (long)b * 3 * C, *scale = shift + C, *gate = shift + 2 * C;
@@ -905,8 +962,8 @@ size_t step_fused_smem(const FusedParams &hp, int max_keys) {
     n = max_keys;
   if (3 * hp.C > n) // row + adaLN scale + shift (flag-in-data variant)
     n = 3 * hp.C;
-  if (hp.C + hp.ldim > n)
-    n = hp.C + hp.ldim;
+  if (2 * hp.C + hp.ldim > n) // activation staged twice for the row-pair GEMV + the latent
+    n = 2 * hp.C + hp.ldim;
   return (size_t)((n + 15) / 16 * 16) * sizeof(float);
 }
 
