@@ -127,7 +127,7 @@ class PttsResult(C.Structure):
 EXPORTS = [
     "ptts_last_error", "ptts_version", "ptts_device_count", "ptts_create", "ptts_destroy", "ptts_load_tensor",
     "ptts_load_safetensors", "ptts_finalize_weights", "ptts_model_info_get", "ptts_generate_audio",
-    "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_release", "ptts_seq_open",
+    "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_error", "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
     "ptts_voice_cache_stats", "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
@@ -164,6 +164,7 @@ def lib() -> C.CDLL:
     L.ptts_wait.argtypes = [vp, C.c_int64, C.POINTER(PttsResult)]
     L.ptts_cancel.argtypes = [vp, C.c_int64]
     L.ptts_ticket_latents.argtypes = [vp, C.c_int64, fp, fp, C.c_int32]
+    L.ptts_ticket_error.argtypes = [vp, C.c_int64, C.c_char_p, C.c_int32]
     L.ptts_ticket_release.argtypes = [vp, C.c_int64]
     L.ptts_seq_open.argtypes = [vp, i64p, C.c_int32, fp, C.c_int32, C.POINTER(PttsVoiceKV), C.c_int32,
                                 C.POINTER(vp)]
@@ -319,10 +320,17 @@ class NativeCudaRuntime:
             raise
 
     # -- weights ----------------------------------------------------------
-    def load_tensor(self, key: str, a: np.ndarray):
+    def load_tensor(self, key: str, a: np.ndarray, dtype: str = "f32"):
+        """One safetensors key.  dtype "f16" / "bf16" hands the engine the half-precision payload
+        (PTTS_DTYPE_F16 / _BF16), widened on the C side as store.go:339-395 does."""
         a = np.ascontiguousarray(a, dtype=np.float32)
         shape = (C.c_int64 * a.ndim)(*a.shape)
-        _check(self._lib.ptts_load_tensor(self._h, key.encode(), shape, a.ndim, 0, a.ctypes.data_as(C.c_void_p)))
+        code = {"f32": 0, "f16": 1, "bf16": 2}[dtype]
+        if code == 1:
+            a = np.ascontiguousarray(a.astype(np.float16))
+        elif code == 2:
+            a = np.ascontiguousarray((a.view(np.uint32) >> 16).astype(np.uint16))  # exact for bf16-representable values
+        _check(self._lib.ptts_load_tensor(self._h, key.encode(), shape, a.ndim, code, a.ctypes.data_as(C.c_void_p)))
 
     def finalize(self):
         _check(self._lib.ptts_finalize_weights(self._h))
@@ -405,7 +413,12 @@ class NativeCudaRuntime:
         res = PttsResult()
         rc = self._lib.ptts_wait(self._h, p.ticket, C.byref(res))
         try:
-            _check(rc)
+            if rc != 0:  # the request's own message (not the calling thread's last error)
+                if self._h is None:  # engine closed under the waiter: ptts_wait left the text on this thread
+                    raise NativeCudaError(rc, self._lib.ptts_last_error().decode("utf-8", "replace"))
+                buf = C.create_string_buffer(512)
+                self._lib.ptts_ticket_error(self._h, p.ticket, buf, len(buf))
+                raise NativeCudaError(rc, buf.value.decode("utf-8", "replace"))
             lat = eos = None
             if want_latents:
                 lat = np.empty((res.n_frames, LATENT_DIM), dtype=np.float32)

@@ -1103,6 +1103,8 @@ int Engine::finalize() {
 
   // ---- Mimi workspaces (front slack rows stay zero: causal left context) ----
   mimi_frames_cap = cfg.mimi_group_frames;
+  if (mimi_frames_cap < max_frames)
+    mimi_frames_cap = max_frames; // one finished chunk must always fit a decode group
   int max_segs = 2 * max_batch + 64;
   if (max_segs > mimi_frames_cap) max_segs = mimi_frames_cap;
   mimi_rows_cap = up_stride * mimi_frames_cap + mimi_pad * max_segs;
@@ -2158,10 +2160,12 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
     while (i < reqs.size() && (int)segs.size() < max_segs) {
       const std::shared_ptr<Request> &r = reqs[i];
       const int n = r->seq->frames;
-      if (n <= 0 || n > mimi_frames_cap) {
-        std::unique_lock<std::mutex> lk(fin_mu);
-        buf_busy[k] = false;
-        PTTS_FAIL(PTTS_ENOMEM, "native-cuda: %d frames exceed mimi_group_frames %d", n, mimi_frames_cap);
+      if (n <= 0 || n > mimi_frames_cap) { // cannot happen (finalize raises the workspace to max_frames): fail it alone
+        char msg[128];
+        snprintf(msg, sizeof msg, "native-cuda: %d frames exceed mimi_group_frames %d", n, mimi_frames_cap);
+        complete_request(r, PTTS_ENOMEM, msg);
+        i++;
+        continue;
       }
       if (tf + n > mimi_frames_cap)
         break;
@@ -2186,6 +2190,11 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
       tf += n;
       segs.push_back(sg);
       i++;
+    }
+    if (segs.empty()) {
+      std::unique_lock<std::mutex> lk(fin_mu);
+      buf_busy[k] = false;
+      continue;
     }
     int rc = PTTS_OK;
     if (cudaMemcpyAsync(d_moff, h_moff, (size_t)tf * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)

@@ -398,6 +398,8 @@ struct Request {
 };
 
 int load_safetensors_file(Engine *e, const char *path);
+// Publishes a request's outcome (status + per-request message) and wakes its waiter.
+void complete_request(const std::shared_ptr<Request> &r, int status, const char *msg);
 
 } // namespace ptts
 

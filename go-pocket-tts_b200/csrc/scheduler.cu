@@ -28,7 +28,7 @@ static int resolve_max_steps(const ptts_gen_cfg &c, int ntok) {
   return ms;
 }
 
-static void complete(const std::shared_ptr<Request> &r, int status, const char *msg) {
+void complete_request(const std::shared_ptr<Request> &r, int status, const char *msg) {
   std::unique_lock<std::mutex> lk(r->mu);
   r->res.status = status;
   if (msg)
@@ -93,7 +93,7 @@ void Engine::finisher_loop() {
             memcpy(r.pcm_out, h_pcm_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(float));
         }
       }
-      complete(sg.r, job.rc, job.rc ? job.msg.c_str() : nullptr);
+      complete_request(sg.r, job.rc, job.rc ? job.msg.c_str() : nullptr);
     }
     {
       std::unique_lock<std::mutex> lk(fin_mu);
@@ -115,9 +115,24 @@ void Engine::sched_loop() {
       if (active.empty() && pending.empty())
         q_cv.wait(lk, [&] { return sched_stop || !queue.empty(); });
       if (sched_stop) {
+        // Close() with requests in flight: every waiter is released (queued, live and
+        // finished-but-undecoded alike); their sequences go back to the pool.
         for (auto &r : queue)
-          complete(r, PTTS_ECANCELED, "native-cuda: engine destroyed");
+          complete_request(r, PTTS_ECANCELED, "native-cuda: engine destroyed");
         queue.clear();
+        lk.unlock();
+        std::unique_lock<std::mutex> gl(gpu_mu);
+        for (auto *v : {&active, &pending})
+          for (auto &r : *v) {
+            if (r->seq) {
+              seq_free(r->seq);
+              delete reinterpret_cast<ptts_seq *>(r->seq);
+              r->seq = nullptr;
+            }
+            complete_request(r, PTTS_ECANCELED, "native-cuda: engine destroyed");
+          }
+        active.clear();
+        pending.clear();
         break;
       }
       // take as many queued requests as there could be room for; resources are
@@ -135,7 +150,7 @@ void Engine::sched_loop() {
         seq_free(active[i]->seq);
         delete reinterpret_cast<ptts_seq *>(active[i]->seq);
         active[i]->seq = nullptr;
-        complete(active[i], PTTS_ECANCELED, "context canceled");
+        complete_request(active[i], PTTS_ECANCELED, "context canceled");
         active.erase(active.begin() + i);
       } else
         i++;
@@ -145,7 +160,7 @@ void Engine::sched_loop() {
     int ptoks = 0;
     for (auto &r : candidates) {
       if (r->cancel) {
-        complete(r, PTTS_ECANCELED, "context canceled");
+        complete_request(r, PTTS_ECANCELED, "context canceled");
         continue;
       }
       if (!leftover.empty()) { // keep FIFO order once one had to wait
@@ -194,7 +209,7 @@ void Engine::sched_loop() {
         continue;
       }
       if (rc) {
-        complete(r, rc, last_error());
+        complete_request(r, rc, last_error());
         continue;
       }
       r->seq = s;
@@ -212,13 +227,28 @@ void Engine::sched_loop() {
       std::vector<int> ntok, nvoice;
       std::vector<const float *> voice;
       int rc = PTTS_OK;
+      // a request whose own inputs are bad fails alone (the reference fails only the offending
+      // call); the rest of the batch is prefilled as usual
+      for (size_t i = 0; i < admitted.size();) {
+        auto &r = admitted[i];
+        int vrc = r->voice_kv ? import_voice_kv(r->seq, r->voice_kv) : PTTS_OK;
+        if (vrc) {
+          std::string msg = last_error();
+          if (r->voice_entry && !r->voice_entry->ready)
+            r->voice_entry->refs = 0;
+          seq_free(r->seq);
+          delete reinterpret_cast<ptts_seq *>(r->seq);
+          r->seq = nullptr;
+          complete_request(r, vrc, msg.c_str());
+          admitted.erase(admitted.begin() + i);
+        } else
+          i++;
+      }
       for (auto &r : admitted) {
         auto now = std::chrono::steady_clock::now();
         r->res.queue_ms = std::chrono::duration<double, std::milli>(now - r->t_submit).count();
         cudaMemcpyAsync(d_noise + (size_t)r->seq->slot * max_frames * ldim, r->noise,
                         (size_t)r->max_steps * ldim * 4, cudaMemcpyHostToDevice, st);
-        if (r->voice_kv && rc == PTTS_OK)
-          rc = import_voice_kv(r->seq, r->voice_kv);
         seqs.push_back(r->seq);
         tok.push_back(r->tokens.data());
         ntok.push_back((int)r->tokens.size());
@@ -227,7 +257,7 @@ void Engine::sched_loop() {
         voice.push_back(r->voice_kv || !r->voice_emb ? nullptr : r->voice_emb + (size_t)skip * D);
         nvoice.push_back(r->voice_kv ? 0 : r->voice_frames - skip);
       }
-      if (rc == PTTS_OK)
+      if (!admitted.empty())
         rc = prefill(seqs, tok, ntok, voice, nvoice);
       for (auto &r : admitted)
         if (r->voice_entry && !r->voice_entry->ready) {
@@ -241,7 +271,7 @@ void Engine::sched_loop() {
           seq_free(r->seq);
           delete reinterpret_cast<ptts_seq *>(r->seq);
           r->seq = nullptr;
-          complete(r, rc, msg.c_str());
+          complete_request(r, rc, msg.c_str());
         }
       } else {
         for (auto &r : admitted)
@@ -305,7 +335,7 @@ void Engine::sched_loop() {
           seq_free(r->seq);
           delete reinterpret_cast<ptts_seq *>(r->seq);
           r->seq = nullptr;
-          complete(r, fail_rc, fail_msg.c_str());
+          complete_request(r, fail_rc, fail_msg.c_str());
         } else if (finished[i]) {
           r->finished_at_iter = (int)iter;
           pending_frames += r->seq->frames;
@@ -330,15 +360,12 @@ void Engine::sched_loop() {
         r->res.n_frames = r->seq->frames;
         r->res.n_samples = (int64_t)r->seq->frames * info.samples_per_frame;
       }
-      int rc = decode_async(pending);
-      std::string msg = rc ? last_error() : "";
+      decode_async(pending); // every request is completed by the finisher (or, on error, inside)
       for (auto &r : pending) {
         // every read of this sequence's state is ordered on the stream already
         seq_free(r->seq);
         delete reinterpret_cast<ptts_seq *>(r->seq);
         r->seq = nullptr;
-        if (rc && !r->done)
-          complete(r, rc, msg.c_str()); // requests of a group that never reached the finisher
       }
       pending.clear();
       pending_frames = 0;
@@ -417,7 +444,31 @@ int ptts_model_info_get(ptts_engine *e, ptts_model_info *out) {
   return PTTS_OK;
 }
 
-static int validate_request(Engine &E, int32_t n_tokens, const float *voice_emb, int32_t voice_frames,
+// flow_transformer.go:451-480,517-631: shape / offset guards of an upstream voice model state,
+// checked at the call that carries it so a bad file fails only its own request.
+static int validate_voice_kv(Engine &E, const ptts_voice_kv *vk) {
+  if (vk->n_layers <= 0 || !vk->layers)
+    PTTS_FAIL(PTTS_EINVAL, "generate: load voice model state: no layers");
+  if (vk->n_layers != E.L)
+    PTTS_FAIL(PTTS_EINVAL, "native: voice model state has %d layers, transformer has %d", vk->n_layers, E.L);
+  for (int l = 0; l < vk->n_layers; l++) {
+    const ptts_voice_layer &vl = vk->layers[l];
+    if (!vl.cache)
+      PTTS_FAIL(PTTS_EINVAL, "native: voice model state module \"transformer.layers.%d.self_attn\" missing cache", l);
+    if (vl.offset < 0)
+      PTTS_FAIL(PTTS_EINVAL, "native: voice model state module has negative offset %d", vl.offset);
+    if (vl.offset > vl.cache_tokens)
+      PTTS_FAIL(PTTS_EINVAL, "native: voice model state offset %d exceeds cache length %d", vl.offset,
+                vl.cache_tokens);
+    if (vl.offset != vk->layers[0].offset)
+      PTTS_FAIL(PTTS_EINVAL, "native-cuda: voice model state offsets differ across layers");
+  }
+  if (vk->layers[0].offset > E.max_rows)
+    PTTS_FAIL(PTTS_ENOMEM, "native-cuda: voice state (%d tokens) exceeds workspace rows", vk->layers[0].offset);
+  return PTTS_OK;
+}
+
+static int validate_request(Engine &E, const int64_t *tokens, int32_t n_tokens, const float *voice_emb, int32_t voice_frames,
                             const ptts_voice_kv *voice_kv, const ptts_gen_cfg *cfg,
                             const float *noise, int32_t noise_rows, float *pcm_out, int64_t pcm_cap,
                             int *max_steps_out) {
@@ -431,8 +482,18 @@ static int validate_request(Engine &E, int32_t n_tokens, const float *voice_emb,
     PTTS_FAIL(PTTS_EINVAL, "generate: voice embedding and voice model state are mutually exclusive");
   if (voice_emb && voice_frames <= 0)
     PTTS_FAIL(PTTS_EINVAL, "generate: build voice tensor: voice_frames must be > 0");
-  if (voice_kv && (voice_kv->n_layers <= 0 || !voice_kv->layers))
-    PTTS_FAIL(PTTS_EINVAL, "generate: load voice model state: no layers");
+  if (voice_kv) {
+    int rc = validate_voice_kv(E, voice_kv);
+    if (rc)
+      return rc;
+  }
+  if (!tokens)
+    PTTS_FAIL(PTTS_EINVAL, "generate: NULL argument");
+  // conditioner.go:31-53 range check, at the call (not inside the batched prefill)
+  for (int j = 0; j < n_tokens; j++)
+    if (tokens[j] < 0 || tokens[j] >= E.nbins)
+      PTTS_FAIL(PTTS_EINVAL, "generate: text embeddings: native: token id %d (%lld) out of range [0,%d)", j,
+                (long long)tokens[j], E.nbins);
   int ms = resolve_max_steps(*cfg, n_tokens);
   if (ms > E.max_frames)
     PTTS_FAIL(PTTS_ENOMEM, "generate: max steps %d exceeds engine max_frames %d", ms, E.max_frames);
@@ -454,11 +515,11 @@ int ptts_submit(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const f
     PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
   Engine &E = e->impl;
   int ms = 0;
-  int rc = validate_request(E, n_tokens, voice_emb, voice_frames, voice_kv, cfg, noise, noise_rows,
+  int rc = validate_request(E, tokens, n_tokens, voice_emb, voice_frames, voice_kv, cfg, noise, noise_rows,
                             pcm_out, pcm_cap, &ms);
   if (rc)
     return rc;
-  if (!tokens || !ticket)
+  if (!ticket)
     PTTS_FAIL(PTTS_EINVAL, "generate: NULL argument");
   auto r = std::make_shared<Request>();
   r->tokens.assign(tokens, tokens + n_tokens);
@@ -476,6 +537,8 @@ int ptts_submit(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const f
   E.ensure_sched();
   {
     std::unique_lock<std::mutex> lk(E.q_mu);
+    if (E.sched_stop)
+      PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable: engine is shutting down");
     r->ticket = E.next_ticket++;
     E.tickets[r->ticket] = r;
     E.queue.push_back(r);
@@ -532,6 +595,19 @@ int ptts_ticket_latents(ptts_engine *e, int64_t ticket, float *latents, float *e
   if (eos_logits)
     memcpy(eos_logits, r->eos.data(), (size_t)n * 4);
   return n;
+}
+
+int ptts_ticket_error(ptts_engine *e, int64_t ticket, char *buf, int32_t cap) {
+  if (!e || !buf || cap <= 0)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: ticket_error: bad arguments");
+  auto r = find_ticket(e->impl, ticket);
+  if (!r)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: unknown ticket %lld", (long long)ticket);
+  std::unique_lock<std::mutex> lk(r->mu);
+  const size_t n = r->err.size() < (size_t)cap - 1 ? r->err.size() : (size_t)cap - 1;
+  memcpy(buf, r->err.data(), n);
+  buf[n] = 0;
+  return (int)n;
 }
 
 int ptts_ticket_release(ptts_engine *e, int64_t ticket) {

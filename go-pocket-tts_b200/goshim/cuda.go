@@ -61,11 +61,25 @@ type Engine struct {
 	h *C.ptts_engine
 }
 
+// lastError reads the calling thread's message.  ptts_last_error() is thread-local on
+// the C side, so every caller brackets the failing call and this read with
+// runtime.LockOSThread (see locked); request errors do not use it at all — Wait reads the
+// message stored on the ticket (ptts_ticket_error).
 func lastError(rc C.int) error {
 	if rc == C.PTTS_ECANCELED {
 		return ErrCanceled
 	}
 	return errors.New(C.GoString(C.ptts_last_error()))
+}
+
+// locked runs one C call and, if it failed, fetches its message on the same OS thread.
+func locked(call func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := call(); rc != 0 {
+		return lastError(rc)
+	}
+	return nil
 }
 
 // Open creates the engine and uploads every tensor of the store, exactly the
@@ -81,8 +95,8 @@ func Open(store *safetensors.Store, cfg Config) (*Engine, error) {
 	cc.max_prefill_tokens = C.int32_t(cfg.MaxPrefillTokens)
 
 	e := &Engine{}
-	if rc := C.ptts_create(&cc, &e.h); rc != 0 {
-		return nil, fmt.Errorf("native-cuda: create engine: %w", lastError(rc))
+	if err := locked(func() C.int { return C.ptts_create(&cc, &e.h) }); err != nil {
+		return nil, fmt.Errorf("native-cuda: create engine: %w", err)
 	}
 
 	for _, name := range store.Names() {
@@ -103,19 +117,21 @@ func Open(store *safetensors.Store, cfg Config) (*Engine, error) {
 		if len(shape) > 0 {
 			sp = &shape[0]
 		}
-		rc := C.ptts_load_tensor(e.h, cname, sp, C.int32_t(len(shape)), C.PTTS_DTYPE_F32,
-			unsafe.Pointer(&t.Data[0]))
+		err = locked(func() C.int {
+			return C.ptts_load_tensor(e.h, cname, sp, C.int32_t(len(shape)), C.PTTS_DTYPE_F32,
+				unsafe.Pointer(&t.Data[0]))
+		})
 		C.free(unsafe.Pointer(cname))
 		runtime.KeepAlive(t)
-		if rc != 0 {
+		if err != nil {
 			e.Close()
-			return nil, fmt.Errorf("native-cuda: upload %q: %w", name, lastError(rc))
+			return nil, fmt.Errorf("native-cuda: upload %q: %w", name, err)
 		}
 	}
 
-	if rc := C.ptts_finalize_weights(e.h); rc != 0 {
+	if err := locked(func() C.int { return C.ptts_finalize_weights(e.h) }); err != nil {
 		e.Close()
-		return nil, fmt.Errorf("native-cuda: finalize weights: %w", lastError(rc))
+		return nil, fmt.Errorf("native-cuda: finalize weights: %w", err)
 	}
 	return e, nil
 }
@@ -134,6 +150,21 @@ type Ticket struct {
 	id   C.int64_t
 	pcm  []float32
 	pins runtime.Pinner
+	// C-allocated voice descriptor (the engine reads it until Wait returns)
+	vkv    *C.ptts_voice_kv
+	layers unsafe.Pointer
+}
+
+func (t *Ticket) release() {
+	t.pins.Unpin()
+	if t.layers != nil {
+		C.free(t.layers)
+		t.layers = nil
+	}
+	if t.vkv != nil {
+		C.free(unsafe.Pointer(t.vkv))
+		t.vkv = nil
+	}
 }
 
 // Submit queues one chunk.  noise is [maxSteps*32], drawn by the caller
@@ -181,15 +212,18 @@ func (e *Engine) Submit(tokens []int64, voiceEmb []float32, voiceFrames int, voi
 		vkv = (*C.ptts_voice_kv)(C.calloc(1, C.sizeof_ptts_voice_kv))
 		vkv.layers = &layers[0]
 		vkv.n_layers = C.int32_t(len(voice))
+		t.vkv, t.layers = vkv, unsafe.Pointer(layers)
 	}
 
-	rc := C.ptts_submit(e.h, (*C.int64_t)(unsafe.Pointer(&tokens[0])), C.int32_t(len(tokens)),
-		vemb, C.int32_t(voiceFrames), vkv, &g,
-		(*C.float)(unsafe.Pointer(&noise[0])), C.int32_t(len(noise)/C.PTTS_LATENT_DIM),
-		(*C.float)(unsafe.Pointer(&t.pcm[0])), C.int64_t(len(t.pcm)), &t.id)
-	if rc != 0 {
-		t.pins.Unpin()
-		return nil, lastError(rc)
+	err := locked(func() C.int {
+		return C.ptts_submit(e.h, (*C.int64_t)(unsafe.Pointer(&tokens[0])), C.int32_t(len(tokens)),
+			vemb, C.int32_t(voiceFrames), vkv, &g,
+			(*C.float)(unsafe.Pointer(&noise[0])), C.int32_t(len(noise)/C.PTTS_LATENT_DIM),
+			(*C.float)(unsafe.Pointer(&t.pcm[0])), C.int64_t(len(t.pcm)), &t.id)
+	})
+	if err != nil {
+		t.release()
+		return nil, err
 	}
 	return t, nil
 }
@@ -199,10 +233,20 @@ func (e *Engine) Submit(tokens []int64, voiceEmb []float32, voiceFrames int, voi
 func (e *Engine) Wait(t *Ticket) ([]float32, int, error) {
 	var res C.ptts_result
 	rc := C.ptts_wait(e.h, t.id, &res)
+	var err error
+	if rc == C.PTTS_ECANCELED {
+		err = ErrCanceled
+	} else if rc != 0 {
+		// the message lives on the ticket, not in thread-local state: the goroutine may have
+		// moved to another OS thread while it was blocked in ptts_wait
+		var buf [512]C.char
+		C.ptts_ticket_error(e.h, t.id, &buf[0], C.int32_t(len(buf)))
+		err = errors.New(C.GoString(&buf[0]))
+	}
 	C.ptts_ticket_release(e.h, t.id)
-	t.pins.Unpin()
-	if rc != 0 {
-		return nil, 0, lastError(rc)
+	t.release()
+	if err != nil {
+		return nil, 0, err
 	}
 	out := append([]float32(nil), t.pcm[:int(res.n_samples)]...)
 	return out, int(res.n_frames), nil

@@ -181,6 +181,11 @@ int ptts_cancel(ptts_engine *e, int64_t ticket);
  * until the ticket is released. */
 int ptts_ticket_latents(ptts_engine *e, int64_t ticket, float *latents,
                         float *eos_logits, int32_t cap_frames);
+/* The request's own error text (empty when it succeeded), copied into buf (NUL-terminated,
+ * truncated to cap); returns its length.  Unlike ptts_last_error() it does not depend on
+ * which OS thread asks: a Go caller reads it after ptts_wait without runtime.LockOSThread
+ * (errors of GenerateAudio, runtime_native_safetensors.go:91,173,214). */
+int ptts_ticket_error(ptts_engine *e, int64_t ticket, char *buf, int32_t cap);
 int ptts_ticket_release(ptts_engine *e, int64_t ticket);
 
 /* ---- stage-level API: mirrors native.Model

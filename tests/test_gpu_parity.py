@@ -480,3 +480,56 @@ def test_scheduler_stress_mixed_requests(pkg, small_tensors):
                 assert snr_db(solo.pcm, outs[i].pcm) >= 40.0, i
     finally:
         rt.close()
+
+
+def test_bad_request_fails_alone(small_rt, small_oracle, pkg):
+    """The reference fails only the offending call: a request with a bad token id or a malformed voice
+    model state is refused with its own message while the requests around it complete normally."""
+    good = [(_tokens(5 + i, 600 + i), pkg.make_noise(4, 0.7, 610 + i)) for i in range(4)]
+    pend = []
+    for i, (t, n) in enumerate(good):
+        pend.append(small_rt.submit(t, pkg.RuntimeGenerateConfig(max_steps=4, eos_threshold=1e30, noise=n)))
+        if i == 1:
+            with pytest.raises(pkg.NativeCudaError, match=r"token id 2 \(4001\) out of range"):
+                small_rt.submit([1, 2, 4001], pkg.RuntimeGenerateConfig(max_steps=4, eos_threshold=1e30))
+        if i == 2:
+            vs = pkg.VoiceModelState([np.zeros((2, 1, 4, 16, 64), np.float32)] * 3, [2, 2, 2])  # 3 layers, model has 2
+            with pytest.raises(pkg.NativeCudaError, match="voice model state has 3 layers, transformer has 2"):
+                small_rt.submit([1, 2], pkg.RuntimeGenerateConfig(max_steps=4, eos_threshold=1e30, voice_model_state=vs))
+            vs = pkg.VoiceModelState([np.zeros((2, 1, 4, 16, 64), np.float32)] * 2, [2, 9])
+            with pytest.raises(pkg.NativeCudaError, match="exceeds cache length"):
+                small_rt.submit([1, 2], pkg.RuntimeGenerateConfig(max_steps=4, eos_threshold=1e30, voice_model_state=vs))
+    for (t, n), p in zip(good, pend):
+        got = small_rt.wait(p, want_latents=True)
+        _, lat, _ = small_oracle.generate_audio(t, noise=n, max_steps=4, eos_threshold=1e30, want_pcm=False)
+        assert got.n_frames == 4 and allclose_ref(got.latents, lat, ABS, REL)
+
+
+def test_close_with_requests_in_flight_releases_waiters(pkg, small_tensors):
+    """Engine.Close() during GenerateAudio must not deadlock the callers (server shutdown): queued, live
+    and finished-but-undecoded requests all return 'engine destroyed' / canceled."""
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=256, max_frames=96,
+                               mimi_group_frames=96)
+    pend = [rt.submit(_tokens(5, 700 + i), pkg.RuntimeGenerateConfig(max_steps=90, eos_threshold=1e30, seed=i))
+            for i in range(5)]  # 2 live, 3 queued
+    outcomes = []
+
+    def waiter(p):
+        try:
+            rt.wait(p)
+            outcomes.append("ok")
+        except pkg.NativeCudaError as e:
+            outcomes.append((e.status, str(e)))
+
+    ths = [threading.Thread(target=waiter, args=(p,)) for p in pend]
+    for t in ths:
+        t.start()
+    import time
+    time.sleep(0.5)  # every waiter is inside ptts_wait by now
+    rt.close()
+    for t in ths:
+        t.join(timeout=60)
+    assert not any(t.is_alive() for t in ths), "a waiter is still blocked after close()"
+    assert len(outcomes) == 5
+    assert all(o == "ok" or o[0] == pkg.PTTS_ECANCELED for o in outcomes), outcomes
+    assert any(o != "ok" for o in outcomes)
