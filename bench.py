@@ -61,7 +61,12 @@ def parse_args():
     ap.add_argument("--utterances", type=int, default=TOTAL_UTTERANCES // MAX_GPUS, help="per GPU")
     ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--arch", default="full", choices=["full", "small"])
-    ap.add_argument("--cpu-sample-frames", type=int, default=24)
+    ap.add_argument("--cpu-sample-frames", type=int, default=0,
+                    help="cap on frames per chunk of the CPU sample (0 = whole chunks, the default: a cap keeps the "
+                         "full prompt prefill and so under-states the CPU path)")
+    ap.add_argument("--queue", type=int, default=0,
+                    help="strong-scaling mode: this many queued utterances in TOTAL (C5 as written: 4096), split "
+                         "over the ranks; default 0 = the driver's weak-scaling contract (--utterances per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     return ap.parse_args()
@@ -143,7 +148,7 @@ def cpu_run(om, chunks, frames_cap, threads):
 
     def one(i):
         c = chunks[i]
-        ms = min(c.max_steps, frames_cap)
+        ms = min(c.max_steps, frames_cap) if frames_cap > 0 else c.max_steps
         force = min(c.force_eos_step, ms - 1 - c.frames_after_eos) if ms > c.frames_after_eos + 1 else 0
         pcm, lat, _ = om.generate_audio(c.tokens, noise=c.noise()[:ms], max_steps=ms, eos_threshold=1e30,
                                         force_eos_step=max(force, 0), frames_after_eos=c.frames_after_eos)
@@ -173,8 +178,17 @@ def main():
     wl = importlib.import_module("pockettts_b200.workload")
     sh = importlib.import_module("pockettts_b200.sharding")
     arch = ck.ArchConfig.full() if args.arch == "full" else ck.ArchConfig.small()
-    workload_name = (f"C5 shard: {args.utterances} utterances/GPU x U{{5..60}} words, <=50-token chunks, "
-                     f"forced-EOS schedule, lsd_steps=1, random-init PocketTTS ({args.arch}), seed 20260118")
+    scaling = "weak"
+    if args.queue > 0:  # C5 as written: one queue of N utterances, whatever the GPU count
+        scaling = "strong"
+        args.utterances = sh.shard_range(rank, world, args.queue)[1] - sh.shard_range(rank, world, args.queue)[0]
+        workload_name = (f"C5: {args.queue} queued utterances in total x U{{5..60}} words split over {world} GPU(s), "
+                         f"<=50-token chunks, forced-EOS schedule, lsd_steps=1, random-init PocketTTS ({args.arch}), "
+                         f"seed 20260118")
+    else:
+        workload_name = (f"C5 shard: {args.utterances} utterances/GPU x U{{5..60}} words, <=50-token chunks, "
+                         f"forced-EOS schedule, lsd_steps=1, random-init PocketTTS ({args.arch}), seed 20260118")
+    DTYPE = "f32 storage/accumulate, split-bf16x3 operands"
     config = {"workload": workload_name, "utterances_per_gpu": args.utterances, "max_batch": args.max_batch,
               "l2": "working set (weights 341 MB + KV + Mimi workspace, several GB) >> 126 MB L2; no flush needed",
               "weights": "fp32 as stored by the reference"}
@@ -196,12 +210,12 @@ def main():
             tot_a += a
             tot_t += t
         v = tot_a / tot_t
-        sample = (f"{cores} chunks (first of the workload) capped at {args.cpu_sample_frames} frames each, "
-                  f"one chunk per host thread")
+        cap_txt = f"capped at {args.cpu_sample_frames} frames each" if args.cpu_sample_frames > 0 else "whole chunks"
+        sample = f"{cores} chunks (first of the workload), {cap_txt}, one chunk per host thread, per step"
         emit(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "C restatement of the reference (Go toolchain unavailable); AVX2+FMA dot"},
@@ -225,7 +239,9 @@ def main():
     tensors = ck.make_checkpoint(arch)
     rt = pkg.NativeCudaRuntime(tensors=tensors, device=local_rank, max_batch=args.max_batch, max_seq_tokens=512,
                                max_frames=256, mimi_group_frames=2048)
-    chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=sh.shard_range(rank, world, args.utterances)[0])
+    first_utt = sh.shard_range(rank, world, args.queue)[0] if args.queue > 0 else \
+        sh.shard_range(rank, world, args.utterances)[0]
+    chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=first_utt)
     noises = [c.noise() for c in chunks]
     h2d = sum(c.tokens.nbytes + n.nbytes for c, n in zip(chunks, noises))
 
@@ -269,7 +285,9 @@ def main():
     ms, frames, _, wall_ms = timed(True, args.steps)
     st = rt.stage_times()
     # (2) e2e: K timed steps through the public call with host buffers
+    rt.stage_times(reset=True)
     ms2, frames2, samples2, _ = timed(False, args.steps)
+    st_e2e = rt.stage_times()
     clocks = sampler.stop() if rank == 0 else {}
     # (3) one more timed step with per-launch CUDA events (roofline accounting;
     #     event pairs around every GEMM/attention launch, CUDA graphs off)
@@ -317,8 +335,20 @@ def main():
                         note="split-bf16 operands: 3 tensor-core products per useful fp32-accurate product "
                              "(issued = 3 x achieved), so the useful ceiling is peak/3")
 
-        top, tv = classes[0]
-        roofline = dict(roofline_of(top, tv),
+        # the dominant kernel is chosen by kernel FUNCTION: every tcgen05_* class (tile width / epilogue-warp
+        # variants) is the one templated tc_gemm_kernel; the per-tile split stays in roofline_by_class
+        def function_of(cls):
+            return "tc_gemm_kernel" if cls.startswith("tcgen05_") else cls
+        by_fn = {}
+        for k, v in classes:
+            acc = by_fn.setdefault(function_of(k), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "classes": []})
+            for f in ("launches", "ms", "flops", "bytes"):
+                acc[f] += v[f]
+            acc["classes"].append(k)
+        top, tv = max(by_fn.items(), key=lambda kv: kv[1]["ms"])
+        roofline = dict(roofline_of(top, tv), classes_merged=tv["classes"],
+                        algorithmic="2*M*N*K flops per GEMM launch, 4*(N*K + M*min(K,lda) + M*N) bytes; attention: "
+                                    "4*keys*D flops, K+V rows read once (DESIGN.md section 4)",
                         measured_over="one timed step with a CUDA-event pair around every launch on the engine "
                                       "stream (CUDA graphs off); algorithmic flops/bytes per launch summed",
                         profiled_step_ms=ms3)
@@ -327,7 +357,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": scaling, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
                     "d2h_bytes_per_step": int(samples2 * 4 / max(args.steps, 1))},
@@ -335,6 +365,11 @@ def main():
             "roofline": roofline, "roofline_by_class": roofline_by_class,
             "kernel_classes": kc, "gemm_shapes": shapes,
             "stage_ms_rank0": {k: round(st[k], 2) for k in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")},
+            "stage_ms_e2e_rank0": {k: round(st_e2e[k], 2)
+                                   for k in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")},
+            "stage_note": "device time per stage over the K timed steps (CUDA events; flow_head_ms is the part of "
+                          "step_ms after the transformer, d2h_ms the PCM copies on the copy stream, which overlap "
+                          "compute); the value leg leaves PCM on the device, so its d2h_ms is 0 by construction",
             "mean_batch_occupancy": st["step_rows"] / max(st["steps"], 1),
             "steps_per_s_rank0": st["steps"] / (ms / 1e3),
             "realtime_factor_per_gpu": value / world,
@@ -396,10 +431,11 @@ def main():
         om = o.OracleModel(tensors)
         sample_chunks = wl.make_workload(cores, 5, 60, seed=7)[:cores]
         a, t, nfr = cpu_run(om, sample_chunks, args.cpu_sample_frames, cores)
+        cap_txt = f"capped at {args.cpu_sample_frames} frames each" if args.cpu_sample_frames > 0 else "whole chunks"
         out["cpu_baseline"] = {
             "value": a / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(sample_chunks)} chunks (first of the workload) capped at {args.cpu_sample_frames} "
-                      f"frames each ({nfr} frames), one chunk per host thread, {t:.1f} s of wall time",
+            "sample": f"{len(sample_chunks)} chunks (first of the workload), {cap_txt} ({nfr} frames), one chunk per "
+                      f"host thread, {t:.1f} s of wall time",
             "note": "C restatement of the reference path (oracle/); the Go reference cannot be built here"}
     if rank == 0:
         emit(json.dumps(out))

@@ -96,9 +96,14 @@ Engine::~Engine() {
     fh(h_pcm_ring[i]);
     fh(h_lat_ring[i]);
     fh(h_s16_ring[i]);
-    for (cudaEvent_t e2 : {ev_dec0[i], ev_pcm_ready[i], ev_copied[i]})
+    fh(h_mrow_pos_ring[i]); fh(h_mrow_frame0_ring[i]); fh(h_mmask_ring[i]); fh(h_moff_ring[i]);
+    for (cudaEvent_t e2 : {ev_dec0[i], ev_pcm_ready[i], ev_copied[i], ev_copy0[i], ev_lat_ready[i]})
       if (e2)
         cudaEventDestroy(e2);
+  }
+  if (st_mimi) {
+    cudaStreamSynchronize(st_mimi);
+    cudaStreamDestroy(st_mimi);
   }
   if (st_copy)
     cudaStreamDestroy(st_copy);
@@ -148,11 +153,11 @@ void Engine::prof_begin(cudaEvent_t *a, cudaEvent_t *b) {
     *b = prof_pool.back().second;
     prof_pool.pop_back();
   }
-  cudaEventRecord(*a, st);
+  cudaEventRecord(*a, cur_st());
 }
 void Engine::prof_end(cudaEvent_t a, cudaEvent_t b, const char *cls, double flops, double bytes,
                       const char *cls2) {
-  cudaEventRecord(b, st);
+  cudaEventRecord(b, cur_st());
   prof_pending.push_back(ProfRec{a, b, cls, flops, bytes, cls2 ? cls2 : ""});
 }
 void Engine::prof_collect() {
@@ -259,9 +264,10 @@ int Engine::make_conv_map(const ActSplit &a, int cin, int taps, void **out) {
 
 int Engine::pgemm(const GemmArgs &g0) {
   GemmArgs g = g0;
-  g.ws = gemm_ws;
+  cudaStream_t st = cur_st(); // lane 1 (Mimi decode) has its own stream and split-K scratch
+  g.ws = lane_ ? gemm_ws_m : gemm_ws;
   g.ws_floats = gemm_ws_floats;
-  g.counters = gemm_counters;
+  g.counters = lane_ ? gemm_counters_m : gemm_counters;
   g.n_counters = gemm_n_counters;
   const TcWeight *tw = nullptr;
   if (tc_on && g.M >= tc_min_m && tc_gemm_supported(g)) {
@@ -1056,6 +1062,9 @@ int Engine::finalize() {
   if ((rc = dmalloc((void **)&gemm_ws, (size_t)gemm_ws_floats * 4))) return rc;
   if ((rc = dmalloc((void **)&gemm_counters, (size_t)gemm_n_counters * 4))) return rc;
   CUDA_TRY(cudaMemset(gemm_counters, 0, (size_t)gemm_n_counters * 4));
+  if ((rc = dmalloc((void **)&gemm_ws_m, (size_t)gemm_ws_floats * 4))) return rc;
+  if ((rc = dmalloc((void **)&gemm_counters_m, (size_t)gemm_n_counters * 4))) return rc;
+  CUDA_TRY(cudaMemset(gemm_counters_m, 0, (size_t)gemm_n_counters * 4));
   // ---- FlowLM workspaces ----
   max_rows = cfg.max_prefill_tokens > max_batch ? cfg.max_prefill_tokens : max_batch;
   if ((rc = dmalloc((void **)&x, (size_t)max_rows * D * 4))) return rc;
@@ -1136,15 +1145,29 @@ int Engine::finalize() {
   }
   if ((rc = slack_alloc(&m_pcm, rows, 1))) return rc;
   CUDA_TRY(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+  {
+    // AR steps are latency-critical chains of short kernels: their stream outranks the Mimi one
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    CUDA_TRY(cudaStreamCreateWithPriority(&st_mimi, cudaStreamNonBlocking, lo_prio));
+    overlap_on = getenv("PTTS_NO_MIMI_OVERLAP") == nullptr;
+  }
   for (int i = 0; i < NPCM; i++) {
     if ((rc = slack_alloc(&m_pcm_ring[i], rows, 1))) return rc;
     CUDA_TRY(cudaMallocHost((void **)&h_pcm_ring[i], rows * sizeof(float)));
     if ((rc = dmalloc((void **)&m_s16_ring[i], rows * sizeof(int16_t)))) return rc;
     CUDA_TRY(cudaMallocHost((void **)&h_s16_ring[i], rows * sizeof(int16_t)));
     CUDA_TRY(cudaMallocHost((void **)&h_lat_ring[i], (size_t)mimi_frames_cap * ldim * sizeof(float)));
+    if ((rc = dmalloc((void **)&m_latin_ring[i], (size_t)mimi_frames_cap * ldim * 4))) return rc;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_lat_ready[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaMallocHost((void **)&h_mrow_pos_ring[i], Rb * 4));
+    CUDA_TRY(cudaMallocHost((void **)&h_mrow_frame0_ring[i], Rb * 4));
+    CUDA_TRY(cudaMallocHost((void **)&h_mmask_ring[i], Rb));
+    CUDA_TRY(cudaMallocHost((void **)&h_moff_ring[i], (size_t)mimi_frames_cap * 8));
     CUDA_TRY(cudaEventCreate(&ev_dec0[i]));
     CUDA_TRY(cudaEventCreate(&ev_pcm_ready[i]));
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&ev_copied[i]));
+    CUDA_TRY(cudaEventCreate(&ev_copy0[i]));
   }
   {
     // split planes of every Mimi activation that is a GEMM / conv input (8 zero slack rows
@@ -1726,7 +1749,7 @@ int Engine::flow_head(int B, int lsd_steps) {
 // new latent into the per-slot history.  Only fixed device pointers are used, so
 // the sequence can be captured into a CUDA graph.
 int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise,
-                      bool timed) {
+                      bool timed, bool capturing) {
   // the ~79 short dependent kernels of a frame are chained with programmatic dependent
   // launch (launch.cuh); the edges survive graph capture
   static const bool no_pdl = getenv("PTTS_NO_PDL") != nullptr;
@@ -1765,8 +1788,12 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
   int rc = flow_forward(Bp, max_keys, false);
   if (rc)
     return rc;
+  // start of the flow head: a plain record when run eagerly, an external event-record node when
+  // the body is being captured, so graph replays report flow_head_ms too
   if (timed)
     cudaEventRecord(ev[3], st);
+  else if (capturing)
+    cudaEventRecordWithFlags(ev[3], st, cudaEventRecordExternal);
   rc = flow_head(Bp, lsd_steps);
   if (rc)
     return rc;
@@ -1846,13 +1873,12 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     if (sg.exec) {
       CUDA_TRY(cudaGraphLaunch(sg.exec, st));
       times.kernel_launches += sg.launches;
-      timed = false;
     } else if (sg.uses >= 2) {
       const int64_t before = times.kernel_launches;
       cudaGraph_t graph = nullptr;
       CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       // attention smem is sized for the per-sequence KV cap so one graph serves any length
-      rc = step_body(Bp, cfg.max_seq_tokens, lsd_steps, gf, gn, false);
+      rc = step_body(Bp, cfg.max_seq_tokens, lsd_steps, gf, gn, false, true);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       if (rc)
         return rc;
@@ -1866,7 +1892,6 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
         PTTS_FAIL(PTTS_ECUDA, "cuda: graph instantiate failed: %s", cudaGetErrorString(ce));
       }
       CUDA_TRY(cudaGraphLaunch(sg.exec, st));
-      timed = false;
     } else {
       rc = step_body(Bp, max_keys, lsd_steps, gf, gn, true);
       if (rc)
@@ -1913,10 +1938,10 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[2], ev[4]);
   times.step_ms += ms;
-  if (timed) {
-    cudaEventElapsedTime(&ms, ev[3], ev[4]);
+  if (timed && cudaEventElapsedTime(&ms, ev[3], ev[4]) == cudaSuccess)
     times.flow_head_ms += ms;
-  }
+  else
+    cudaGetLastError();
   times.step_rows += B;
   times.steps += 1;
   debug_bufs["last_hidden"] = {fh_last, (size_t)B * D};
@@ -1930,6 +1955,27 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
 // ---------------------------------------------------------------------------
 int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, PcmJob *job) {
   float *pcm = job ? m_pcm_ring[job->buf] : m_pcm;
+  // Asynchronous groups (job) run on the Mimi stream beside the AR steps, everything else on
+  // `st` after the Mimi stream has drained (the activation workspace is shared).  Profiled
+  // passes keep one stream so the per-kernel event pairs do not measure contention.
+  const bool side = job && overlap_on && !prof_on;
+  if (!side)
+    CUDA_TRY(cudaStreamSynchronize(st_mimi));
+  struct LaneScope {
+    Engine *e;
+    LaneScope(Engine *e_, int l) : e(e_) { e->lane_ = l; }
+    ~LaneScope() { e->lane_ = 0; }
+  } lane_scope(this, side ? 1 : 0);
+  cudaStream_t st = cur_st(); // shadows the member: every launch below goes to the lane's stream
+  float *m_latin = job ? m_latin_ring[job->buf] : this->m_latin;
+  int32_t *h_mrow_pos = job ? h_mrow_pos_ring[job->buf] : this->h_mrow_pos;
+  int32_t *h_mrow_frame0 = job ? h_mrow_frame0_ring[job->buf] : this->h_mrow_frame0;
+  uint8_t *h_mmask = job ? h_mmask_ring[job->buf] : this->h_mmask;
+  if (job) {
+    // the latent rows were gathered on the AR stream (decode_async)
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_lat_ready[job->buf], 0));
+    CUDA_TRY(cudaMemcpyAsync(h_lat_ring[job->buf], m_latin, (size_t)total_frames * ldim * 4, cudaMemcpyDeviceToHost, st));
+  }
   int64_t &nl = times.kernel_launches;
   const int P = mimi_pad;
   int Rb = 0;
@@ -1982,14 +2028,29 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
     nl += pgemm(g);
     PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st));
     if (prof_on) {
-      double keys = 0;
-      for (int r = 0; r < Rb; r++)
-        if (h_mrow_pos[r] >= 0)
-          keys += h_mrow_pos[r] + 1 < Mctx ? h_mrow_pos[r] + 1 : Mctx;
+      // flops: every allowed (query, key) pair, 4 * head_dim per head.  bytes: what a flash-style
+      // kernel must move — per block of 64 query rows the q rows, the UNIQUE K and V rows of the
+      // block's windows (read once per block, not once per query) and the output rows.
+      double keys = 0, rows_moved = 0;
+      for (int r0 = 0; r0 < Rb; r0 += 64) {
+        int lo = Rb, hi = -1;
+        for (int r = r0; r < r0 + 64 && r < Rb; r++) {
+          const int pos = h_mrow_pos[r];
+          if (pos < 0)
+            continue;
+          const int n = pos + 1 < Mctx ? pos + 1 : Mctx;
+          keys += n;
+          if (r - n + 1 < lo)
+            lo = r - n + 1;
+          hi = r;
+        }
+        if (hi >= 0)
+          rows_moved += 2.0 * (hi - lo + 1) + 2.0 * 64; // K + V window rows, q rows in, out rows
+      }
       cudaEvent_t a, b;
       prof_begin(&a, &b);
       nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
-      prof_end(a, b, "attention_window", 4.0 * keys * Md, 8.0 * keys * Md);
+      prof_end(a, b, "attention_window", 4.0 * keys * Md, 4.0 * rows_moved * Md);
     } else
       nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
     GemmArgs o;
@@ -2103,6 +2164,7 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
       nl += pcm_to_s16(pcm, m_s16_ring[k], (size_t)rows, st);
     cudaEventRecord(ev_pcm_ready[k], st);
     CUDA_TRY(cudaStreamWaitEvent(st_copy, ev_pcm_ready[k], 0));
+    cudaEventRecord(ev_copy0[k], st_copy);
     if (job->copy)
       CUDA_TRY(cudaMemcpyAsync(h_pcm_ring[k], pcm, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, st_copy));
     if (job->copy_s16)
@@ -2175,7 +2237,7 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
       sg.row0 = 0;
       sg.host_out = nullptr;
       for (int f = 0; f < n; f++)
-        h_moff[tf + f] = ((int64_t)r->seq->slot * (max_frames + 1) + f + 1) * ldim;
+        h_moff_ring[k][tf + f] = ((int64_t)r->seq->slot * (max_frames + 1) + f + 1) * ldim;
       PcmJob::Seg js;
       js.r = r;
       js.lat_off = (size_t)tf * ldim;
@@ -2197,23 +2259,25 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
       continue;
     }
     int rc = PTTS_OK;
-    if (cudaMemcpyAsync(d_moff, h_moff, (size_t)tf * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    // The latent rows leave the per-slot history on the AR stream (ordered after the step that
+    // wrote them and before any later sequence reuses the slot); the decode itself follows on
+    // the Mimi stream.  Host staging is per ring slot, so nothing here waits for the GPU.
+    if (cudaMemcpyAsync(d_moff, h_moff_ring[k], (size_t)tf * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
       rc = PTTS_ECUDA;
     if (rc == PTTS_OK) {
-      times.kernel_launches += gather_rows(d_hist, d_moff, m_latin, tf, ldim, st);
-      cudaMemcpyAsync(h_lat_ring[k], m_latin, (size_t)tf * ldim * 4, cudaMemcpyDeviceToHost, st);
-      // h_moff is rewritten by the next group: its H2D must have been consumed
+      times.kernel_launches += gather_rows(d_hist, d_moff, m_latin_ring[k], tf, ldim, st);
+      cudaEventRecord(ev_lat_ready[k], st);
       rc = mimi_decode(segs, tf, false, &job);
-      if (rc == PTTS_OK && i < reqs.size())
-        cudaStreamSynchronize(st);
     }
     if (rc) {
       job.rc = rc;
       job.msg = last_error();
       // make the events valid for the finisher even though nothing ran
+      cudaEventRecord(ev_lat_ready[k], st);
       cudaEventRecord(ev_dec0[k], st);
       cudaEventRecord(ev_pcm_ready[k], st);
       cudaStreamWaitEvent(st_copy, ev_pcm_ready[k], 0);
+      cudaEventRecord(ev_copy0[k], st_copy);
       cudaEventRecord(ev_copied[k], st_copy);
     }
     {

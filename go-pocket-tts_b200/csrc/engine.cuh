@@ -235,10 +235,26 @@ struct Engine {
   static constexpr int NPCM = 4;
   static constexpr int NFIN = 3; // finisher threads (first-touch page faults of caller buffers dominate the host copy)
   cudaStream_t st_copy = nullptr;
+  // Mimi decode of finished groups runs on its own (low-priority) stream, concurrent with the
+  // AR steps on `st`: the skinny AR GEMMs leave SMs idle and wait on each other, the Mimi
+  // kernels fill them.  Everything a group needs is per ring slot (latent rows gathered on
+  // `st`, row descriptors, PCM); the activation workspace is shared, so groups serialise on
+  // st_mimi.  lane_ selects stream + split-K scratch for pgemm / PK.
+  cudaStream_t st_mimi = nullptr;
+  bool overlap_on = true;
+  int lane_ = 0;
+  float *gemm_ws_m = nullptr;
+  int *gemm_counters_m = nullptr;
+  cudaStream_t cur_st() const { return lane_ ? st_mimi : st; }
+  float *m_latin_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_lat_ready[NPCM]{};
+  int32_t *h_mrow_pos_ring[NPCM]{}, *h_mrow_frame0_ring[NPCM]{};
+  uint8_t *h_mmask_ring[NPCM]{};
+  int64_t *h_moff_ring[NPCM]{};
   float *m_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   float *h_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_lat_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   int16_t *m_s16_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_s16_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_dec0[NPCM]{}, ev_pcm_ready[NPCM]{}, ev_copied[NPCM]{};
+  cudaEvent_t ev_dec0[NPCM]{}, ev_pcm_ready[NPCM]{}, ev_copied[NPCM]{}, ev_copy0[NPCM]{};
   struct PcmJob {
     int buf = 0, rc = 0;
     bool copy = false, copy_s16 = false; // some request wants float / PCM16 samples on the host
@@ -339,7 +355,8 @@ struct Engine {
   };
   bool graphs_on = true;
   std::map<uint64_t, StepGraph> step_graphs;
-  int step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise, bool timed);
+  int step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise, bool timed,
+                bool capturing = false);
   int step(const std::vector<Seq *> &seqs, const float *frames_in_host,
            const float *noise_host, int lsd_steps, float *lat_out_host,
            float *eos_out_host);

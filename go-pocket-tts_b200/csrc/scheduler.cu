@@ -78,8 +78,12 @@ void Engine::finisher_loop() {
     }
     float ms = 0;
     if (job.rc == PTTS_OK && cudaEventElapsedTime(&ms, ev_dec0[k], ev_pcm_ready[k]) == cudaSuccess) {
+      float ms2 = 0; // PCM device -> pinned host on the copy stream
+      if (cudaEventElapsedTime(&ms2, ev_copy0[k], ev_copied[k]) != cudaSuccess)
+        ms2 = 0;
       std::unique_lock<std::mutex> lk(fin_mu);
       fin_mimi_ms += ms;
+      fin_d2h_ms += ms2;
     }
     const int spf = info.samples_per_frame;
     for (auto &sg : job.segs) {
@@ -788,11 +792,13 @@ int ptts_stage_times_get(ptts_engine *e, ptts_stage_times *out, int32_t reset) {
     *out = e->impl.times;
     std::unique_lock<std::mutex> lk(e->impl.fin_mu);
     out->mimi_ms += e->impl.fin_mimi_ms;
+    out->d2h_ms += e->impl.fin_d2h_ms;
   }
   if (reset) {
     e->impl.times = ptts_stage_times{};
     std::unique_lock<std::mutex> lk(e->impl.fin_mu);
     e->impl.fin_mimi_ms = 0;
+    e->impl.fin_d2h_ms = 0;
   }
   return PTTS_OK;
 }

@@ -510,8 +510,9 @@ def test_close_with_requests_in_flight_releases_waiters(pkg, small_tensors):
     and finished-but-undecoded requests all return 'engine destroyed' / canceled."""
     rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=256, max_frames=96,
                                mimi_group_frames=96)
+    n = 60  # 2 live, the rest queued: ~1 s of work, the engine is closed 50 ms in
     pend = [rt.submit(_tokens(5, 700 + i), pkg.RuntimeGenerateConfig(max_steps=90, eos_threshold=1e30, seed=i))
-            for i in range(5)]  # 2 live, 3 queued
+            for i in range(n)]
     outcomes = []
 
     def waiter(p):
@@ -525,11 +526,11 @@ def test_close_with_requests_in_flight_releases_waiters(pkg, small_tensors):
     for t in ths:
         t.start()
     import time
-    time.sleep(0.5)  # every waiter is inside ptts_wait by now
+    time.sleep(0.05)  # the waiters are inside ptts_wait by now
     rt.close()
     for t in ths:
         t.join(timeout=60)
     assert not any(t.is_alive() for t in ths), "a waiter is still blocked after close()"
-    assert len(outcomes) == 5
-    assert all(o == "ok" or o[0] == pkg.PTTS_ECANCELED for o in outcomes), outcomes
+    assert len(outcomes) == n
+    assert all(o == "ok" or o[0] in (pkg.PTTS_ECANCELED, pkg.PTTS_EINVAL) for o in outcomes), outcomes
     assert any(o != "ok" for o in outcomes)
