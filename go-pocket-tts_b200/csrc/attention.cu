@@ -61,6 +61,70 @@ __global__ void __launch_bounds__(ATT_THREADS)
   attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
 }
 
+// Decode step (one new row per sequence): RoPE of q and k (rope.go:81-105), the K/V append of
+// the row's own token (flow_transformer.go:32-67) and the attention over positions 0..pos in ONE
+// kernel.  The CTA of (row, head) rotates its q into shared memory, writes the rotated k and the v
+// of its head into the sequence's page, and then attends over the cache, its own token included.
+// Only valid when no other row of the launch belongs to the same sequence (the prefill keeps the
+// separate append kernel: there a row also reads keys written by other CTAs).
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_paged_decode_kernel(const float *qkv, long ldq, float *out, long ldo,
+                                  const int32_t *row_slot, const int32_t *row_pos, const float *cosT,
+                                  const float *sinT, KvGeom kv, int layer, SplitOut sp) {
+  PDL_TRIGGER();
+  PDL_WAIT();
+  extern __shared__ float smem[];
+  __shared__ float red[ATT_THREADS / 32];
+  __shared__ float4 pv[8 * 16];
+  __shared__ __align__(16) float qs[HD];
+  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int slot = row_slot[r], pos = row_pos[r];
+  float *o = out ? out + (long)r * ldo + h * HD : nullptr;
+  if (pos < 0) {
+    if (tid < 16) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o)
+        *reinterpret_cast<float4 *>(o + tid * 4) = z;
+      if (sp.hi)
+        split_store4(sp, r, h * HD + tid * 4, z);
+    }
+    return;
+  }
+  const int nkeys = pos + 1;
+  const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
+  const int PT = kv.page_tokens, D = kv.n_heads * HD;
+  const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
+  const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * PT * HD;
+  const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * PT * HD;
+  float *pool = kv.pool;
+  {
+    const float *row = qkv + (long)r * ldq;
+    float *page = pool + (long)pt[pos / PT] * page_stride + (long)(pos % PT) * HD;
+    if (tid < HD) { // pairs (2j, 2j+1): threads 0..31 rotate q, 32..63 rotate k
+      const int isk = tid >= HD / 2, j = tid & (HD / 2 - 1);
+      const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
+      const float a = src[0], b = src[1];
+      const float cj = cosT[(long)pos * (HD / 2) + j], sj = sinT[(long)pos * (HD / 2) + j];
+      const float o0 = a * cj - b * sj;
+      const float o1 = a * sj + b * cj;
+      float *dst = isk ? page + koff + 2 * j : qs + 2 * j;
+      dst[0] = o0;
+      dst[1] = o1;
+    } else { // threads 64..127: the head's v
+      const int d = tid - HD;
+      page[voff + d] = row[2 * D + h * HD + d];
+    }
+  }
+  __syncthreads(); // q in shared memory; this CTA's own k/v stores are visible to its loads below
+  auto keyp = [&](int j) {
+    return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
+  };
+  auto valp = [&](int j) {
+    return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
+  };
+  attend_row(qs, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
+}
+
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_window_kernel(const float *qkv, long ldq, float *out, long ldo,
                             int D, const int32_t *row_pos, int ctx, SplitOut sp) {
@@ -256,6 +320,18 @@ int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
   launch_k(attention_paged_kernel, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv, layer, sp);
+  return 1;
+}
+
+int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int rows, const int32_t *row_slot,
+                           const int32_t *row_pos, const float *cosT, const float *sinT, const KvGeom &kv, int layer,
+                           int max_keys, cudaStream_t st, SplitOut sp) {
+  if (rows <= 0)
+    return 0;
+  dim3 grid(rows, kv.n_heads);
+  size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
+  launch_k(attention_paged_decode_kernel, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, cosT,
+           sinT, kv, layer, sp);
   return 1;
 }
 

@@ -1536,7 +1536,9 @@ int Engine::setup_fused() {
 // FlowLM transformer over R rows already in x; row_slot/row_pos uploaded.
 // (flow_transformer.go:326-389, one pass of forwardWithState per layer)
 // ---------------------------------------------------------------------------
-int Engine::flow_forward(int R, int max_keys, bool) {
+int Engine::flow_forward(int R, int max_keys, bool decode) {
+  static const bool no_fuse = getenv("PTTS_NO_FUSED_ROPE_ATTN") != nullptr;
+  decode = decode && !no_fuse;
   int64_t &nl = times.kernel_launches;
   double prof_keys = 0; // sum over rows of keys attended (K and V rows read)
   if (prof_on)
@@ -1550,14 +1552,22 @@ int Engine::flow_forward(int R, int max_keys, bool) {
     g.epi.C = qkv; g.epi.ldc = 3 * D;
     use_act(g, s_nrm);
     nl += pgemm(g);
-    PK("rope_kv_append", 0, 0, rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st));
+    // decode step: RoPE + KV append + attention are one kernel; the prefill (several rows of a
+    // sequence per launch) appends first, then attends
+    if (!decode)
+      PK("rope_kv_append", 0, 0, rope_kv_append(qkv, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l, st));
+    auto attend = [&]() {
+      return decode ? attention_paged_decode(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, rope_cos, rope_sin, kvg, l,
+                                             max_keys, st, s_att.out())
+                    : attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st, s_att.out());
+    };
     if (prof_on) {
       cudaEvent_t a, b;
       prof_begin(&a, &b);
-      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st, s_att.out());
+      nl += attend();
       prof_end(a, b, "attention_paged", 4.0 * prof_keys * D, 8.0 * prof_keys * D);
     } else
-      nl += attention_paged(qkv, 3 * D, att, D, R, d_row_slot, d_row_pos, kvg, l, max_keys, st, s_att.out());
+      nl += attend();
     GemmArgs o;
     o.A = att; o.lda = D; o.W = ly.out_proj.w; o.ldw = D; o.M = R; o.N = D; o.K = D;
     o.epi.residual = x; o.epi.ldr = D; o.epi.C = x; o.epi.ldc = D;
@@ -1785,7 +1795,7 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     use_act(g, s_in);
     nl += pgemm(g);
   }
-  int rc = flow_forward(Bp, max_keys, false);
+  int rc = flow_forward(Bp, max_keys, true);
   if (rc)
     return rc;
   // start of the flow head: a plain record when run eagerly, an external event-record node when

@@ -340,7 +340,7 @@ struct Engine {
   int sync_pagetab(Seq *s);
 
   // passes (caller holds gpu_mu)
-  int flow_forward(int R, int max_keys, bool mask_none);
+  int flow_forward(int R, int max_keys, bool decode); // decode: one new row per sequence
   int prefill(const std::vector<Seq *> &seqs, const std::vector<const int64_t *> &tok,
               const std::vector<int> &ntok, const std::vector<const float *> &voice,
               const std::vector<int> &nvoice);

@@ -143,6 +143,12 @@ int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
                     const KvGeom &kv, int layer, int max_keys, cudaStream_t st,
                     SplitOut sp = SplitOut());
 
+// Decode-step fusion of rope_kv_append + attention_paged: every row is the single new token of
+// its sequence (qkv is left untouched; K/V of the token are appended to the cache).
+int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int rows, const int32_t *row_slot,
+                           const int32_t *row_pos, const float *cosT, const float *sinT, const KvGeom &kv, int layer,
+                           int max_keys, cudaStream_t st, SplitOut sp = SplitOut());
+
 // RoPE in place on q and k of qkv [R, 3*D] with per-row positions (<0 = skip).
 int rope_inplace(float *qkv, int rows, int D, int n_heads, const int32_t *row_pos,
                  const float *cosT, const float *sinT, cudaStream_t st);

@@ -618,10 +618,13 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     } // S > 1 / cluster path
   }
   if (items.cluster) {
-    // ===== split-K across a cluster: every CTA's partial accumulator goes from TMEM straight
-    // into the leader's shared memory (its operand ring is idle by then) through DSMEM; the
-    // leader sums the S partials in split order (deterministic) and runs the epilogue.  No
-    // partials through L2, no atomics, no second kernel. =====
+    // ===== split-K across a cluster, distributed reduction.  The S CTAs of a tile each own a
+    // band of its 128 rows (rows_per = ceil(128 / S)).  Every CTA moves its partial accumulator
+    // TMEM -> (per-warp transpose) -> the OWNER's shared memory through DSMEM (the operand ring
+    // is idle by then), band by band; after the second cluster barrier each CTA sums the S
+    // partials of its own band in split order (deterministic) and runs the fused epilogue on
+    // it.  No partials through L2, no atomics, no serial leader: the exchange is one tile's
+    // worth of bytes per CTA whatever S is, and the epilogue work is split S ways. =====
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     int m0, n0, kb_begin, nkb, z, tile;
@@ -630,10 +633,9 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     const int q = warp & 3;
     const int c_first = EW == 8 ? ((warp - 2) >> 2) * 32 : 0;
     constexpr int C_STEP = EW == 8 ? 64 : 32;
+    const int rows_per = (TC_BM + S - 1) / S;
     if (epi_warp) {
-      uint32_t leader_base;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_base) : "r"(smem_u32(smem)), "r"(0));
-      const uint32_t slot = leader_base + (uint32_t)z * (uint32_t)(TC_BM * BN * 4);
+      const uint32_t my_base = smem_u32(smem);
       const uint32_t stg_addr_c = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
 #pragma unroll 1
       for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
@@ -660,8 +662,12 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const int row = j * 4 + (lane >> 3);
+          const int r = q * 32 + row;            // row of the tile
+          const int owner = r / rows_per, rloc = r - owner * rows_per;
           const float4 a = lds128(stg_addr_c + (uint32_t)(row * SM::STG_LD + (lane & 7) * 4) * 4);
-          const uint32_t dst = slot + (uint32_t)(((q * 32 + row) * BN + c0 + (lane & 7) * 4) * 4);
+          uint32_t owner_base;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(owner_base) : "r"(my_base), "r"(owner));
+          const uint32_t dst = owner_base + (uint32_t)((((z * rows_per + rloc) * BN) + c0 + (lane & 7) * 4) * 4);
           asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
                        : "memory");
         }
@@ -670,61 +676,36 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     }
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (epi_warp && z == 0) {
+    if (epi_warp) {
       const GemmEpi &e = g.epi;
-      const uint32_t stg_addr = smem_u32(stg_base + (warp - 2) * SM::STG_WARP);
-      const int rsub = lane >> 3, cf = (lane & 7) * 4;
-      uint32_t rows = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int m = m0 + q * 32 + j * 4 + rsub;
-        if (m < M) {
-          rows |= 1u << j;
-          if (!e.rowmask || e.rowmask[m / e.mask_div])
-            rows |= 0x100u << j;
-        }
-      }
-      const bool full = __all_sync(0xffffffffu, (rows & 0xFFu) == 0xFFu);
+      const int r_begin = z * rows_per;
+      const int rows_here = min(TC_BM, r_begin + rows_per) - r_begin;
       const uint32_t slots = smem_u32(smem);
-#pragma unroll 1
-      for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
-        const int n = n0 + c0 + cf;
-        const bool nok = n < N;
-        float4 res[8];
-        const bool have_res = e.residual != nullptr;
-        if (have_res) {
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const int m = m0 + q * 32 + j * 4 + rsub;
-            res[j] = (nok && ((rows >> j) & 1)) ? *reinterpret_cast<const float4 *>(e.residual + (long)m * e.ldr + n)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      constexpr int C4 = BN / 4;
+      const int total = rows_here * C4;
+      for (int idx = threadIdx.x - 64; idx < total; idx += EW * 32) {
+        const int rloc = idx / C4, c4 = idx - rloc * C4;
+        const int m = m0 + r_begin + rloc, n = n0 + c4 * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < S; sp++) {
+          const float4 u = lds128(slots + (uint32_t)((((sp * rows_per + rloc) * BN) + c4 * 4) * 4));
+          a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        }
+        if (m < M && n < N) {
+          float4 o = epi_vec4(e, a, m, n);
+          if (e.rowmask && !e.rowmask[m / e.mask_div])
+            o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.C)
+            *reinterpret_cast<float4 *>(e.C + (long)m * e.ldc + n) = o;
+          if (e.Cs.hi)
+            split_store4(e.Cs, m, n, o);
+          if (e.C2 || e.C2s.hi) {
+            const float4 u2 = elu4(o);
+            if (e.C2)
+              *reinterpret_cast<float4 *>(e.C2 + (long)m * e.ldc2 + n) = u2;
+            if (e.C2s.hi)
+              split_store4(e.C2s, m, n, u2);
           }
-        }
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (nok) {
-          if (e.bias)
-            bias4 = __ldg(reinterpret_cast<const float4 *>(e.bias + n));
-          if (e.colscale)
-            cs4 = __ldg(reinterpret_cast<const float4 *>(e.colscale + n));
-        }
-        // sum the S partials of this lane's 8 x 4 outputs in split order into the warp's staging
-        // buffer (each lane reads back only what it wrote)
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int row = q * 32 + j * 4 + rsub;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int sp = 0; sp < S; sp++) {
-            const float4 u = lds128(slots + (uint32_t)sp * (uint32_t)(TC_BM * BN * 4) + (uint32_t)((row * BN + c0 + cf) * 4));
-            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
-          }
-          sts128(stg_addr + (uint32_t)((j * 4 + rsub) * SM::STG_LD + cf) * 4, __float_as_uint(a.x), __float_as_uint(a.y),
-                 __float_as_uint(a.z), __float_as_uint(a.w));
-        }
-        if (nok) {
-          const uint32_t rd_addr = stg_addr + (uint32_t)(rsub * SM::STG_LD + cf) * 4;
-          const long m_first = m0 + q * 32 + rsub;
-          epi_rows_dispatch(items.epi_kind, e, rd_addr, SM::STG_LD * 4, m_first, n, rows, bias4, cs4, res, have_res,
-                            full);
         }
       }
     }
@@ -754,6 +735,47 @@ EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+// How many clusters of `cs` CTAs of this kernel instance can be resident at once.  A GPC holds
+// ~18 SMs and a cluster never spans GPCs, so "CTAs <= SMs" is not enough: 48 clusters of 3 do
+// not fit although 144 <= 148, and the launch would run in two waves.
+template <int BN, int STAGES, bool ATMA, int EW>
+int tc_max_clusters(int cs) {
+  using SM = TcSmem<BN, STAGES, EW>;
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cs < 2 || cs > 8)
+    return 0;
+  if (cache[cs] == 0) {
+    cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cs * 8));
+    cfg.blockDim = dim3(tc_threads(EW, ATMA));
+    cfg.dynamicSmemBytes = SM::BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<BN, STAGES, ATMA, EW>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = -1;
+    }
+    cache[cs] = n > 0 ? n : -1;
+  }
+  return cache[cs] > 0 ? cache[cs] : 0;
+}
+// The same for the TMA-fed instance the tile width maps to (cost model + launch agree on it).
+int tc_cluster_capacity(int bn, int cs) {
+  switch (bn) {
+  case 256: return tc_max_clusters<256, 2, true, 4>(cs);
+  case 128: return tc_max_clusters<128, 3, true, 4>(cs);
+  case 64: return tc_max_clusters<64, 4, true, 4>(cs);
+  default: return tc_max_clusters<32, 4, true, 4>(cs);
+  }
 }
 
 template <int BN, int STAGES, bool ATMA, int EW = 4>
@@ -786,7 +808,8 @@ int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   // split-K through a cluster (DSMEM) when the S partial tiles fit the leader's operand ring
   static const bool no_cluster = getenv("PTTS_TC_NO_CLUSTER") != nullptr;
   it.cluster = (ATMA && !no_cluster && S > 1 && S <= 8 && it.total <= tc_num_sms() &&
-                (long)S * TC_BM * BN * 4 <= (long)STAGES * SM::STAGE)
+                (long)S * ((TC_BM + S - 1) / S) * BN * 4 <= (long)STAGES * SM::STAGE &&
+                tiles <= tc_max_clusters<BN, STAGES, ATMA, EW>(S))
                    ? 1
                    : 0;
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
@@ -829,15 +852,19 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
       bn /= 2;
     return;
   }
-  // Cost model (us), fitted to CTA timelines on B200 (tools/gemm_timeline.py):
-  //  * a k-block takes >= 0.58 us with TMA-fed operands (latency of the 3-4 stage ring),
-  //    1.3 us when A goes through the converter warps, or longer when the CTA's operand
-  //    bytes (~105 GB/s per SM) or the MMA issue rate bound it;
-  //  * the whole grid cannot pull more than ~8 TB/s through L2;
-  //  * the epilogue costs ~0.9 us per 32-column chunk; persistent CTAs overlap it with
-  //    the next item's main loop;
-  //  * the split-K fix-up (partials through L2, last CTA sums) is expensive: 5 us + 2.5 us
-  //    per 64 columns + 1 us per 64 columns and split.
+  // Cost model (us), fitted to the forced (BN, S) sweep of the AR-step shapes on B200
+  // (tools/skinny_sweep.py, profiles/skinny_sweep_r02.txt):
+  //  * ~6 us per launch are fixed (launch gap, barrier init + TMEM alloc, first operand round trip,
+  //    teardown);
+  //  * a CTA ingests its operands at ~95 GB/s (L2 -> SM), so a k-block costs (128 + BN) * 256 B /
+  //    95 GB/s, but never less than the ring's latency floor: 0.58 us with 3-4 stages, 1.3 us with
+  //    the two 96 KB stages of BN = 256 (and 1.3 us when A goes through the converter warps);
+  //  * the whole grid cannot pull more than ~11 TB/s through L2;
+  //  * the epilogue costs ~0.7 us per 32-column chunk; persistent CTAs overlap it with the next
+  //    item's main loop;
+  //  * split-K through a cluster (distributed reduction): two cluster barriers + one tile of DSMEM
+  //    traffic per CTA (0.9 us per 64 columns) + 1/S of the epilogue; through L2 (more CTAs than
+  //    SMs, or S > 8): 5 us + 2.5 us per 64 columns + 1 us per 64 columns and split.
   const bool atma = g.amap != nullptr;
   double best = 1e30;
   bn = 32;
@@ -856,24 +883,24 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
       const long items = tiles * s;
       const long per_cta = (items + sms - 1) / sms; // items a CTA runs back to back
       const double kb_bytes = (128.0 + b) * 256.0;
-      double t_kb = atma ? 0.58 : 1.3;
-      if (kb_bytes / 105e3 > t_kb)
-        t_kb = kb_bytes / 105e3;
+      double t_kb = !atma ? 1.3 : (b == 256 ? 1.3 : 0.58);
+      if (kb_bytes / 95e3 > t_kb)
+        t_kb = kb_bytes / 95e3;
       const double t_mma = 128.0 * b * 64.0 * 6.0 / 9.0e6; // ~9 TFLOP/s issued per SM
       if (t_mma > t_kb)
         t_kb = t_mma;
       const double t_loop = t_kb * kb_per;
-      const double t_epi = 0.9 * (b / 32.0);
-      double t = 1.7 + per_cta * t_loop + t_epi + (per_cta > 1 ? (per_cta - 1) * (t_epi > t_loop ? t_epi - t_loop : 0.0) : 0.0);
-      const double l2_floor = (double)items * kb_per * kb_bytes / 8.0e6;
-      if (l2_floor > t)
-        t = l2_floor;
+      const double t_epi = 0.7 * (b / 32.0);
+      double t = 6.0 + per_cta * t_loop + (s == 1 ? t_epi : 0.0) +
+                 (per_cta > 1 ? (per_cta - 1) * (t_epi > t_loop ? t_epi - t_loop : 0.0) : 0.0);
+      const double l2_floor = (double)items * kb_per * kb_bytes / 11.0e6;
+      if (6.0 + l2_floor > t)
+        t = 6.0 + l2_floor;
       if (s > 1) {
-        // through a cluster (DSMEM) when the partial tiles fit the leader's operand ring
-        // (stages x stage bytes: 160 KB for b = 32, 192 KB otherwise), else through L2
         const long ring = b == 32 ? 4L * 40960 : 196608L;
-        const bool cl = atma && s <= 8 && items <= sms && (long)s * 128 * b * 4 <= ring;
-        t += cl ? 3.5 + (b / 64.0) * (1.0 + 0.5 * s) : 5.0 + (b / 64.0) * (2.5 + 1.0 * s); // measured
+        const bool cl = atma && s <= 8 && items <= sms && (long)s * ((128 + s - 1) / s) * b * 4 <= ring &&
+                        tiles <= tc_cluster_capacity(b, s);
+        t += cl ? 2.5 + (b / 64.0) * 0.9 + t_epi / s : 5.0 + (b / 64.0) * (2.5 + 1.0 * s) + t_epi;
       }
       if (t < best) {
         best = t;

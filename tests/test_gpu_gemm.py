@@ -93,3 +93,22 @@ def test_tma_fed_causal_conv_form(small_rt, M, cin, taps, N):
     im2col = np.concatenate([xp[t:t + M] for t in range(taps)], axis=1)  # [M, taps*cin]
     got = small_rt.debug_gemm_tma(x, W, b, act=3, taps=taps)
     _check(got, im2col, W, b, 3, 4e-5)
+
+
+@pytest.mark.parametrize("M,K,N,bn,S", [(256, 1024, 3072, 256, 4), (256, 1024, 1024, 256, 8), (200, 4096, 1024, 128, 8),
+                                        (64, 1024, 4096, 256, 3), (500, 512, 512, 128, 6), (1000, 1024, 1024, 256, 2),
+                                        (300, 512, 10240, 256, 1), (90, 1024, 512, 64, 5), (256, 4096, 1024, 32, 7)])
+def test_cluster_split_k_distributed_reduction(small_rt, M, K, N, bn, S):
+    """Split-K through a thread-block cluster: the S CTAs of a tile exchange row bands of their partial
+    accumulators through DSMEM and each reduces + stores its own band (any S <= 8, any tile width);
+    results match the fp64 reference, are deterministic, and equal the epilogue's split-plane copy."""
+    A, W, b = _case(M, K, N, M + N + S)
+    small_rt.tc_force(bn, S)
+    try:
+        got, sp = small_rt.debug_gemm_tma(A, W, b, act=1, want_split=True)
+        again = small_rt.debug_gemm_tma(A, W, b, act=1)
+    finally:
+        small_rt.tc_force(0, 0)
+    _check(got, A, W, b, 1, 4e-5)
+    np.testing.assert_array_equal(got, again)
+    assert np.abs(sp - got).max() <= 2.0 ** -15 * max(1.0, np.abs(got).max())
