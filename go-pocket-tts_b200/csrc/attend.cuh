@@ -4,7 +4,9 @@
 #pragma once
 #include "kernels.cuh"
 #include "split.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
+#include <type_traits>
 
 namespace ptts {
 
@@ -40,7 +42,36 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
   return r;
 }
 
-// KeyFn(j) -> pointer to the 64 floats of key j; ValFn(j) likewise for values.
+// Element type of a K/V row: fp32 (Mimi: rows of the qkv GEMM output; FlowLM cache in exact mode)
+// or fp16 (the FlowLM paged cache by default: the cache stream is what bounds the batched AR step,
+// and 11 mantissa bits on K and V keep the attention output ~1e-4 relative, inside the 1e-3 latent
+// tolerance; the arithmetic — scores, softmax, P.V — stays fp32).  Lane `part` of a key's 8 lanes
+// owns elements [8 part, 8 part + 8); a value lane owns 4 consecutive elements.
+__device__ __forceinline__ void kv_load8(const float *p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void kv_load8(const __half *p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4 *>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&u.z));
+  const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&u.w));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ float4 kv_load4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 kv_load4(const __half *p) {
+  const uint2 u = *reinterpret_cast<const uint2 *>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void kv_store(float *p, float v) { *p = v; }
+__device__ __forceinline__ void kv_store(__half *p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ float kv_get(const float *p) { return *p; }
+__device__ __forceinline__ float kv_get(const __half *p) { return __half2float(*p); }
+
+// KeyFn(j) -> pointer to the 64 elements of key j; ValFn(j) likewise for values.
 template <class KeyFn, class ValFn>
 __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp,
                                            ValFn valp, float *out, float *scores,
@@ -50,24 +81,23 @@ __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp
   const float scale = 0.125f; // 1/sqrt(64)
   // phase 1
   const int part = tid & 7, kslot = tid >> 3; // 16 keys per pass
-  const float4 q0 = *reinterpret_cast<const float4 *>(q + part * 4);
-  const float4 q1 = *reinterpret_cast<const float4 *>(q + 32 + part * 4);
+  const float4 q0 = *reinterpret_cast<const float4 *>(q + part * 8);
+  const float4 q1 = *reinterpret_cast<const float4 *>(q + part * 8 + 4);
   float lmax = -INFINITY;
   for (int j0 = 0; j0 < nkeys; j0 += 16) {
     const int j = j0 + kslot;
     float s = 0.0f;
     if (j < nkeys) {
-      const float *kp = keyp(j);
-      float4 a = *reinterpret_cast<const float4 *>(kp + part * 4);
-      float4 b = *reinterpret_cast<const float4 *>(kp + 32 + part * 4);
-      s = q0.x * a.x;
-      s = fmaf(q0.y, a.y, s);
-      s = fmaf(q0.z, a.z, s);
-      s = fmaf(q0.w, a.w, s);
-      s = fmaf(q1.x, b.x, s);
-      s = fmaf(q1.y, b.y, s);
-      s = fmaf(q1.z, b.z, s);
-      s = fmaf(q1.w, b.w, s);
+      float k[8];
+      kv_load8(keyp(j) + part * 8, k);
+      s = q0.x * k[0];
+      s = fmaf(q0.y, k[1], s);
+      s = fmaf(q0.z, k[2], s);
+      s = fmaf(q0.w, k[3], s);
+      s = fmaf(q1.x, k[4], s);
+      s = fmaf(q1.y, k[5], s);
+      s = fmaf(q1.z, k[6], s);
+      s = fmaf(q1.w, k[7], s);
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -94,7 +124,7 @@ __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j = grp; j < nkeys; j += 8) {
     const float w = scores[j] * inv;
-    const float4 v = *reinterpret_cast<const float4 *>(valp(j) + c4 * 4);
+    const float4 v = kv_load4(valp(j) + c4 * 4);
     acc.x = fmaf(w, v.x, acc.x);
     acc.y = fmaf(w, v.y, acc.y);
     acc.z = fmaf(w, v.z, acc.z);

@@ -23,6 +23,7 @@
 
 namespace ptts {
 
+template <typename KT>
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_kernel(const float *qkv, long ldq, float *out, long ldo,
                            const int32_t *row_slot, const int32_t *row_pos,
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
   const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * PT * HD;
   const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * PT * HD;
-  const float *pool = kv.pool;
+  const KT *pool = static_cast<const KT *>(kv.pool);
   auto keyp = [&](int j) {
     return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
   };
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 // of its head into the sequence's page, and then attends over the cache, its own token included.
 // Only valid when no other row of the launch belongs to the same sequence (the prefill keeps the
 // separate append kernel: there a row also reads keys written by other CTAs).
+template <typename KT>
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_decode_kernel(const float *qkv, long ldq, float *out, long ldo,
                                   const int32_t *row_slot, const int32_t *row_pos, const float *cosT,
@@ -96,10 +98,10 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
   const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * PT * HD;
   const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * PT * HD;
-  float *pool = kv.pool;
+  KT *pool = static_cast<KT *>(kv.pool);
   {
     const float *row = qkv + (long)r * ldq;
-    float *page = pool + (long)pt[pos / PT] * page_stride + (long)(pos % PT) * HD;
+    KT *page = pool + (long)pt[pos / PT] * page_stride + (long)(pos % PT) * HD;
     if (tid < HD) { // pairs (2j, 2j+1): threads 0..31 rotate q, 32..63 rotate k
       const int isk = tid >= HD / 2, j = tid & (HD / 2 - 1);
       const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
@@ -107,12 +109,16 @@ __global__ void __launch_bounds__(ATT_THREADS)
       const float cj = cosT[(long)pos * (HD / 2) + j], sj = sinT[(long)pos * (HD / 2) + j];
       const float o0 = a * cj - b * sj;
       const float o1 = a * sj + b * cj;
-      float *dst = isk ? page + koff + 2 * j : qs + 2 * j;
-      dst[0] = o0;
-      dst[1] = o1;
+      if (isk) {
+        kv_store(page + koff + 2 * j, o0);
+        kv_store(page + koff + 2 * j + 1, o1);
+      } else {
+        qs[2 * j] = o0;
+        qs[2 * j + 1] = o1;
+      }
     } else { // threads 64..127: the head's v
       const int d = tid - HD;
-      page[voff + d] = row[2 * D + h * HD + d];
+      kv_store(page + voff + d, row[2 * D + h * HD + d]);
     }
   }
   __syncthreads(); // q in shared memory; this CTA's own k/v stores are visible to its loads below
@@ -319,7 +325,12 @@ int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
     return 0;
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
-  launch_k(attention_paged_kernel, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv, layer, sp);
+  if (kv.half)
+    launch_k(attention_paged_kernel<__half>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv,
+             layer, sp);
+  else
+    launch_k(attention_paged_kernel<float>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv,
+             layer, sp);
   return 1;
 }
 
@@ -330,8 +341,12 @@ int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int
     return 0;
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
-  launch_k(attention_paged_decode_kernel, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, cosT,
-           sinT, kv, layer, sp);
+  if (kv.half)
+    launch_k(attention_paged_decode_kernel<__half>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, cosT, sinT, kv, layer, sp);
+  else
+    launch_k(attention_paged_decode_kernel<float>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, cosT, sinT, kv, layer, sp);
   return 1;
 }
 
@@ -363,6 +378,7 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
 // ---------------------------------------------------------------------------
 // RoPE + KV append
 // ---------------------------------------------------------------------------
+template <typename KT>
 __global__ void __launch_bounds__(256)
     rope_kv_append_kernel(float *qkv, const int32_t *row_slot,
                           const int32_t *row_pos, const float *cosT,
@@ -378,16 +394,16 @@ __global__ void __launch_bounds__(256)
   const float *c = cosT + (long)pos * half, *s = sinT + (long)pos * half;
   const int PT = kv.page_tokens;
   const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
-  float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
+  KT *page = static_cast<KT *>(kv.pool) + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
   const int tok = pos % PT;
-  if (D <= 4 * (int)blockDim.x) {
-    // Same arithmetic with every load of the thread issued before the first store: qkv and the
-    // page may alias as far as the compiler knows, so the loops below run one dependent memory
-    // round trip per iteration (11 us per launch, once per layer per frame).
+  // Every load of a pass is issued before its first store: qkv and the page may alias as far as
+  // the compiler knows, so a load-store-load order would cost one dependent memory round trip
+  // per element.  Thread p handles pair p of q|k (D pairs in all) and element p of v.
+  for (int p0 = 0; p0 < D; p0 += 4 * (int)blockDim.x) {
     float a[4], b[4], cj[4], sj[4], vv[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const int p = threadIdx.x + k * blockDim.x;
+      const int p = p0 + threadIdx.x + k * blockDim.x;
       if (p < D) {
         const int isk = p >= D / 2;
         const int pp = isk ? p - D / 2 : p;
@@ -402,43 +418,24 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const int p = threadIdx.x + k * blockDim.x;
+      const int p = p0 + threadIdx.x + k * blockDim.x;
       if (p < D) {
         const int isk = p >= D / 2;
         const int pp = isk ? p - D / 2 : p;
         const int h = pp / half, j = pp % half;
         const float o0 = a[k] * cj[k] - b[k] * sj[k];
         const float o1 = a[k] * sj[k] + b[k] * cj[k];
-        float *dst = isk ? page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + 2 * j
-                         : row + h * HD + 2 * j;
-        dst[0] = o0;
-        dst[1] = o1;
-        page[((long)(layer * 2 + 1) * H + p / HD) * PT * HD + (long)tok * HD + p % HD] = vv[k];
+        if (isk) {
+          KT *dst = page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + 2 * j;
+          kv_store(dst, o0);
+          kv_store(dst + 1, o1);
+        } else {
+          row[h * HD + 2 * j] = o0;
+          row[h * HD + 2 * j + 1] = o1;
+        }
+        kv_store(page + ((long)(layer * 2 + 1) * H + p / HD) * PT * HD + (long)tok * HD + p % HD, vv[k]);
       }
     }
-    return;
-  }
-  // q and k pairs
-  for (int p = threadIdx.x; p < D; p += blockDim.x) { // D/2 pairs each for q,k
-    const int isk = p >= D / 2;
-    const int pp = isk ? p - D / 2 : p;
-    const int h = pp / half, j = pp % half;
-    float *src = row + (isk ? D : 0) + h * HD + 2 * j;
-    const float a = src[0], b = src[1];
-    const float o0 = a * c[j] - b * s[j];
-    const float o1 = a * s[j] + b * c[j];
-    if (!isk) {
-      src[0] = o0;
-      src[1] = o1;
-    } else {
-      float *dst = page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + 2 * j;
-      dst[0] = o0;
-      dst[1] = o1;
-    }
-  }
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    page[((long)(layer * 2 + 1) * H + h) * PT * HD + (long)tok * HD + d] = row[2 * D + i];
   }
 }
 
@@ -447,22 +444,26 @@ int rope_kv_append(float *qkv, int rows, const int32_t *row_slot,
                    const KvGeom &kv, int layer, cudaStream_t st) {
   if (rows <= 0)
     return 0;
-  launch_k(rope_kv_append_kernel, dim3(rows), dim3(256), 0, st, qkv, row_slot, row_pos, cosT, sinT, kv, layer);
+  if (kv.half)
+    launch_k(rope_kv_append_kernel<__half>, dim3(rows), dim3(256), 0, st, qkv, row_slot, row_pos, cosT, sinT, kv, layer);
+  else
+    launch_k(rope_kv_append_kernel<float>, dim3(rows), dim3(256), 0, st, qkv, row_slot, row_pos, cosT, sinT, kv, layer);
   return 1;
 }
 
+template <typename KT>
 __global__ void __launch_bounds__(256)
     kv_write_rows_kernel(const float *rk, const float *rv, int slot, int pos0,
                          KvGeom kv, int layer) {
   const int t = blockIdx.x, pos = pos0 + t;
   const int H = kv.n_heads, D = H * HD, PT = kv.page_tokens;
   const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
-  float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
+  KT *page = static_cast<KT *>(kv.pool) + (long)kv.pagetab[(long)slot * kv.max_pages + pos / PT] * page_stride;
   const int tok = pos % PT;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
-    page[((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + d] = rk[(long)t * D + i];
-    page[((long)(layer * 2 + 1) * H + h) * PT * HD + (long)tok * HD + d] = rv[(long)t * D + i];
+    kv_store(page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + d, rk[(long)t * D + i]);
+    kv_store(page + ((long)(layer * 2 + 1) * H + h) * PT * HD + (long)tok * HD + d, rv[(long)t * D + i]);
   }
 }
 
@@ -470,21 +471,24 @@ int kv_write_rows(const float *rows_k, const float *rows_v, int T, int slot,
                   int pos0, const KvGeom &kv, int layer, cudaStream_t st) {
   if (T <= 0)
     return 0;
-  kv_write_rows_kernel<<<T, 256, 0, st>>>(rows_k, rows_v, slot, pos0, kv, layer);
+  if (kv.half)
+    kv_write_rows_kernel<__half><<<T, 256, 0, st>>>(rows_k, rows_v, slot, pos0, kv, layer);
+  else
+    kv_write_rows_kernel<float><<<T, 256, 0, st>>>(rows_k, rows_v, slot, pos0, kv, layer);
   return 1;
 }
 
+template <typename KT>
 __global__ void __launch_bounds__(256)
     kv_read_rows_kernel(float *out, int T, int slot, KvGeom kv, int layer, int which) {
   const int t = blockIdx.x;
   const int H = kv.n_heads, D = H * HD, PT = kv.page_tokens;
   const long page_stride = (long)kv.n_layers * 2 * H * PT * HD;
-  const float *page = kv.pool + (long)kv.pagetab[(long)slot * kv.max_pages + t / PT] * page_stride;
+  const KT *page = static_cast<const KT *>(kv.pool) + (long)kv.pagetab[(long)slot * kv.max_pages + t / PT] * page_stride;
   const int tok = t % PT;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     const int h = i / HD, d = i % HD;
-    out[((long)h * T + t) * HD + d] =
-        page[((long)(layer * 2 + which) * H + h) * PT * HD + (long)tok * HD + d];
+    out[((long)h * T + t) * HD + d] = kv_get(page + ((long)(layer * 2 + which) * H + h) * PT * HD + (long)tok * HD + d);
   }
 }
 
@@ -492,7 +496,10 @@ int kv_read_rows(float *out, int T, int slot, const KvGeom &kv, int layer,
                  int which, cudaStream_t st) {
   if (T <= 0)
     return 0;
-  kv_read_rows_kernel<<<T, 256, 0, st>>>(out, T, slot, kv, layer, which);
+  if (kv.half)
+    kv_read_rows_kernel<__half><<<T, 256, 0, st>>>(out, T, slot, kv, layer, which);
+  else
+    kv_read_rows_kernel<float><<<T, 256, 0, st>>>(out, T, slot, kv, layer, which);
   return 1;
 }
 

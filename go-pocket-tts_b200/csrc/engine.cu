@@ -1037,8 +1037,12 @@ int Engine::finalize() {
   page_tokens = cfg.page_tokens;
   max_pages = (cfg.max_seq_tokens + page_tokens - 1) / page_tokens;
   n_pages = cfg.kv_pages > 0 ? cfg.kv_pages : max_batch * max_pages;
+  // The cache holds K (rotated) and V as fp16 by default: its stream is what bounds the batched AR
+  // step (48 KB per token and sequence as fp32), and 11 mantissa bits keep the attention output
+  // ~1e-4 relative — inside the latent tolerance; PTTS_ENGINE_KV_F32 keeps the reference's fp32.
+  kv_half = !(cfg.flags & PTTS_ENGINE_KV_F32) && !getenv("PTTS_KV_F32");
   size_t page_floats = (size_t)L * 2 * H * page_tokens * Dh;
-  if ((rc = dmalloc((void **)&kv_pool, (size_t)n_pages * page_floats * sizeof(float)))) return rc;
+  if ((rc = dmalloc((void **)&kv_pool, (size_t)n_pages * page_floats * (kv_half ? 2 : 4)))) return rc;
   for (int i = n_pages - 1; i >= 0; i--)
     free_pages.push_back(i);
   for (int i = max_batch - 1; i >= 0; i--)
@@ -1046,7 +1050,7 @@ int Engine::finalize() {
   h_pagetab.assign((size_t)max_batch * max_pages, 0);
   if ((rc = dmalloc((void **)&d_pagetab, h_pagetab.size() * sizeof(int32_t)))) return rc;
   CUDA_TRY(cudaMemset(d_pagetab, 0, h_pagetab.size() * sizeof(int32_t)));
-  kvg.pool = kv_pool; kvg.pagetab = d_pagetab; kvg.max_pages = max_pages;
+  kvg.pool = kv_pool; kvg.half = kv_half ? 1 : 0; kvg.pagetab = d_pagetab; kvg.max_pages = max_pages;
   kvg.page_tokens = page_tokens; kvg.n_layers = L; kvg.n_heads = H; kvg.head_dim = Dh;
   if ((rc = dmalloc((void **)&d_hist, (size_t)(max_batch + 1) * (max_frames + 1) * ldim * sizeof(float)))) return rc;
   if ((rc = dmalloc((void **)&d_noise, (size_t)(max_batch + 1) * max_frames * ldim * sizeof(float)))) return rc;
@@ -1451,7 +1455,7 @@ void Engine::seq_free(Seq *s) {
 int Engine::setup_fused() {
   fused_on = false;
   voice_share_on = getenv("PTTS_NO_VOICE_SHARING") == nullptr;
-  if (getenv("PTTS_NO_FUSED_STEP") || L > FUSED_MAX_LAYERS || depth > FUSED_MAX_LAYERS || Dh != 64 || D % 4 || C % 4 ||
+  if (getenv("PTTS_NO_FUSED_STEP") || !kv_half /* the frame kernel reads the fp16 cache */ || L > FUSED_MAX_LAYERS || depth > FUSED_MAX_LAYERS || Dh != 64 || D % 4 || C % 4 ||
       ldim > 128 || ldim % 4 || F % 4 || rb[0].mlp0.out % 4 || ada_n % 2)
     return PTTS_OK;
   FusedParams hp{};
@@ -1565,7 +1569,7 @@ int Engine::flow_forward(int R, int max_keys, bool decode) {
       cudaEvent_t a, b;
       prof_begin(&a, &b);
       nl += attend();
-      prof_end(a, b, "attention_paged", 4.0 * prof_keys * D, 8.0 * prof_keys * D);
+      prof_end(a, b, "attention_paged", 4.0 * prof_keys * D, (kv_half ? 4.0 : 8.0) * prof_keys * D);
     } else
       nl += attend();
     GemmArgs o;

@@ -189,7 +189,8 @@ struct Engine {
   int gemm_n_counters = 4096;
 
   // ---- KV pool ----
-  float *kv_pool = nullptr;
+  void *kv_pool = nullptr; // fp16 elements unless PTTS_ENGINE_KV_F32
+  bool kv_half = true;
   int n_pages = 0, page_tokens = 16, max_pages = 0;
   std::vector<int> free_pages, free_slots;
   int32_t *d_pagetab = nullptr;

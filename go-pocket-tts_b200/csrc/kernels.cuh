@@ -116,7 +116,8 @@ int embed_gather(const int64_t *ids, const float *table, float *out, int rows,
                  int D, cudaStream_t st);
 
 struct KvGeom {
-  float *pool;          // paged KV pool
+  void *pool;           // paged KV pool: __half elements (default) or float (half == 0)
+  int half;
   const int32_t *pagetab; // [slots, max_pages]
   int max_pages, page_tokens, n_layers, n_heads, head_dim;
 };

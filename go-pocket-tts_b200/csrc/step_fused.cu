@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(FT, 2)
       const int PT = kv.page_tokens;
       const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
       const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
-      float *page = kv.pool + (long)pt[pos / PT] * page_stride;
+      __half *page = static_cast<__half *>(kv.pool) + (long)pt[pos / PT] * page_stride;
       const int tok = pos % PT;
       const long koff = ((long)(l * 2 + 0) * kv.n_heads + h) * PT * HD;
       const long voff = ((long)(l * 2 + 1) * kv.n_heads + h) * PT * HD;
@@ -449,15 +449,15 @@ __global__ void __launch_bounds__(FT, 2)
         q_s[2 * j] = qa * c - qb * s;
         q_s[2 * j + 1] = qa * s + qb * c;
         const float ka = ldcg1(P.qkv + D + h * HD + 2 * j), kb = ldcg1(P.qkv + D + h * HD + 2 * j + 1);
-        float *dst = page + koff + (long)tok * HD + 2 * j;
-        dst[0] = ka * c - kb * s;
-        dst[1] = ka * s + kb * c;
+        __half *dst = page + koff + (long)tok * HD + 2 * j;
+        kv_store(dst, ka * c - kb * s);
+        kv_store(dst + 1, ka * s + kb * c);
       } else if (threadIdx.x < half + HD) {
         const int d = threadIdx.x - half;
-        page[voff + (long)tok * HD + d] = ldcg1(P.qkv + 2 * D + h * HD + d);
+        kv_store(page + voff + (long)tok * HD + d, ldcg1(P.qkv + 2 * D + h * HD + d));
       }
       __syncthreads();
-      const float *pool = kv.pool;
+      const __half *pool = static_cast<const __half *>(kv.pool);
       auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
       auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
       attend_row(q_s, pos + 1, keyp, valp, P.att + h * HD, dsm, red, pv, SplitOut(), 0, 0);
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(FT, 2)
       const int PT = kv.page_tokens;
       const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * PT * HD;
       const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
-      float *page = kv.pool + (long)pt[pos / PT] * page_stride;
+      __half *page = static_cast<__half *>(kv.pool) + (long)pt[pos / PT] * page_stride;
       const int tok = pos % PT;
       const long koff = ((long)(l * 2 + 0) * kv.n_heads + h) * PT * HD;
       const long voff = ((long)(l * 2 + 1) * kv.n_heads + h) * PT * HD;
@@ -796,16 +796,16 @@ __global__ void __launch_bounds__(FT, 2)
         const float2 kk = ll_get2(P.ll_qkv, D + h * HD + 2 * j, t_qkv, pl);
         q_s[2 * j] = qq.x * c - qq.y * s;
         q_s[2 * j + 1] = qq.x * s + qq.y * c;
-        float *dst = page + koff + (long)tok * HD + 2 * j;
-        dst[0] = kk.x * c - kk.y * s;
-        dst[1] = kk.x * s + kk.y * c;
+        __half *dst = page + koff + (long)tok * HD + 2 * j;
+        kv_store(dst, kk.x * c - kk.y * s);
+        kv_store(dst + 1, kk.x * s + kk.y * c);
       } else if (threadIdx.x < half + HD) {
         const int d = threadIdx.x - half;
-        page[voff + (long)tok * HD + d] = ll_get1(P.ll_qkv, 2 * D + h * HD + d, t_qkv, pl);
+        kv_store(page + voff + (long)tok * HD + d, ll_get1(P.ll_qkv, 2 * D + h * HD + d, t_qkv, pl));
       }
       __syncthreads();
       FSTAMP();
-      const float *pool = kv.pool;
+      const __half *pool = static_cast<const __half *>(kv.pool);
       auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
       auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
       attend_row(q_s, pos + 1, keyp, valp, nullptr, dsm, red, pv, SplitOut(), 0, 0, P.ll_att + h * HD, T);

@@ -59,6 +59,8 @@ typedef struct {
 
 #define PTTS_ENGINE_NO_GRAPHS 1 /* disable CUDA-graph replay of the B<=8 step */
 #define PTTS_ENGINE_NO_TENSOR_CORES 2 /* keep every GEMM on the fp32 CUDA-core path */
+#define PTTS_ENGINE_KV_F32 4 /* FlowLM KV cache as fp32 like the reference (flow_transformer.go:26-108);
+                                default: fp16 storage, fp32 attention arithmetic (half the cache stream) */
 
 /* Per-call generation knobs: mirrors tts.RuntimeGenerateConfig
  * (reference internal/tts/runtime.go:11-31). */

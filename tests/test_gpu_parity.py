@@ -49,15 +49,33 @@ def test_prefill_kv_matches_oracle(small_rt, small_oracle):
     st.prompt(small_oracle.text_embeddings(toks))
     try:
         assert s.kv_len == st.offset(0) == 23
+        # the cache stores fp16 by default (half-ulp 4.9e-4 relative on top of the compute error); the
+        # latent tolerance is checked on the outputs, the fp32-cache mode holds ABS/REL on K/V itself
+        # (test_kv_cache_fp32_mode_matches_oracle_and_default)
         for layer in range(small_oracle.L):
             for which in (0, 1):
                 got, want = s.read_kv(layer, which), st.read_kv(layer, which)
-                assert allclose_ref(got, want, ABS, REL), (layer, which, np.abs(got - want).max())
+                assert allclose_ref(got, want, 5e-4, 2e-3), (layer, which, np.abs(got - want).max())
     finally:
         s.close()
 
 
-def test_step_teacher_forced_matches_oracle(small_rt, small_oracle, pkg):
+@pytest.fixture(scope="module")
+def small_rt32(pkg, small_tensors):
+    """Exact-cache mode: FlowLM K/V kept as fp32 like the reference (PTTS_ENGINE_KV_F32)."""
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=16, max_seq_tokens=256, max_frames=32,
+                               mimi_group_frames=64, flags=4)
+    yield rt
+    rt.close()
+
+
+@pytest.mark.parametrize("mode", ["kv_f16", "kv_f32"])
+def test_step_teacher_forced_matches_oracle(small_rt, small_rt32, small_oracle, pkg, mode):
+    """Latents and the EOS logit hold the north-star tolerance in both cache modes.  The internal
+    hidden state (an O(1) vector after out_norm) is held to the same per-element bound with the
+    fp32 cache and to 1e-3 absolute with the default fp16 cache (K/V rounded to 11 bits)."""
+    small_rt = small_rt if mode == "kv_f16" else small_rt32
+    hid_abs = 1e-3 if mode == "kv_f16" else ABS
     toks = _tokens(9, 2)
     noise = pkg.make_noise(6, 0.7, 5)
     s = small_rt.seq_open(toks, reserve_frames=8)
@@ -69,7 +87,7 @@ def test_step_teacher_forced_matches_oracle(small_rt, small_oracle, pkg):
             want_lat, want_eos, want_last = st.step(frame, noise[i])
             lat, eos = small_rt.step([s], noise[i], frames_in=frame)
             last = small_rt.debug_fetch("last_hidden")
-            assert allclose_ref(last, want_last, ABS, REL), (i, np.abs(last - want_last).max())
+            assert allclose_ref(last, want_last, hid_abs, REL), (i, np.abs(last - want_last).max())
             assert abs(eos[0] - want_eos) <= ABS + REL * abs(want_eos), (i, eos[0], want_eos)
             assert allclose_ref(lat[0], want_lat, ABS, REL), (i, np.abs(lat[0] - want_lat).max())
             frame = want_lat  # teacher forcing
@@ -534,3 +552,28 @@ def test_close_with_requests_in_flight_releases_waiters(pkg, small_tensors):
     assert len(outcomes) == n
     assert all(o == "ok" or o[0] in (pkg.PTTS_ECANCELED, pkg.PTTS_EINVAL) for o in outcomes), outcomes
     assert any(o != "ok" for o in outcomes)
+
+
+def test_kv_cache_fp32_mode_matches_oracle_and_default(pkg, small_tensors, small_oracle, small_rt):
+    """The FlowLM KV cache is fp16 by default (fp32 attention arithmetic); PTTS_ENGINE_KV_F32 keeps the
+    reference's fp32 cache.  Both modes hold the latent tolerance against the oracle, prefill K/V included."""
+    rt32 = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=4, max_seq_tokens=256, max_frames=32,
+                                 mimi_group_frames=64, flags=4)
+    try:
+        toks = _tokens(19, 71)
+        noise = pkg.make_noise(10, 0.7, 72)
+        kw = dict(max_steps=10, eos_threshold=1e30, force_eos_step=6, frames_after_eos=2)
+        _, lat, _ = small_oracle.generate_audio(toks, noise=noise, want_pcm=False, **kw)
+        a = rt32.generate(toks, pkg.RuntimeGenerateConfig(noise=noise, **kw), want_latents=True)
+        b = small_rt.generate(toks, pkg.RuntimeGenerateConfig(noise=noise, **kw), want_latents=True)
+        assert a.n_frames == b.n_frames == lat.shape[0]
+        assert allclose_ref(a.latents, lat, ABS, REL) and allclose_ref(b.latents, lat, ABS, REL)
+        assert np.abs(a.latents - lat).max() <= np.abs(b.latents - lat).max() + 1e-5  # fp32 cache is the tighter one
+        s = rt32.seq_open(toks, reserve_frames=4)
+        st = small_oracle.new_state()
+        st.prompt(small_oracle.text_embeddings(toks))
+        for which in (0, 1):
+            assert allclose_ref(s.read_kv(1, which), st.read_kv(1, which), ABS, REL)
+        s.close()
+    finally:
+        rt32.close()
