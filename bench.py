@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native-cuda", choices=["native-cuda", "reference"])
     ap.add_argument("--utterances", type=int, default=TOTAL_UTTERANCES // MAX_GPUS, help="per GPU")
+    ap.add_argument("--pool", action="store_true",
+                    help="ONE process drives --gpus devices through the in-process pool (ptts_pool_*: least-loaded "
+                         "dispatch of one shared queue) instead of one torchrun rank per GPU")
     ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--arch", default="full", choices=["full", "small"])
     ap.add_argument("--cpu-sample-frames", type=int, default=0,
@@ -166,7 +169,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus > 1 and world == 1:
+    if args.gpus > 1 and world == 1 and not args.pool:
         # convenience: relaunch under torchrun (the driver does this itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
@@ -179,7 +182,17 @@ def main():
     sh = importlib.import_module("pockettts_b200.sharding")
     arch = ck.ArchConfig.full() if args.arch == "full" else ck.ArchConfig.small()
     scaling = "weak"
-    if args.queue > 0:  # C5 as written: one queue of N utterances, whatever the GPU count
+    n_dev = args.gpus if args.pool else 1  # devices THIS process drives
+    n_gpus_job = args.gpus if args.pool else world
+    if args.pool and args.queue <= 0:
+        args.queue = args.utterances * args.gpus  # same total work as the sharded mode
+    if args.queue > 0 and args.pool:  # one shared queue, dispatched in-process
+        scaling = "strong" if args.queue == TOTAL_UTTERANCES else "weak"
+        args.utterances = args.queue
+        workload_name = (f"C5 through the in-process pool: {args.queue} queued utterances x U{{5..60}} words, one process, "
+                         f"{args.gpus} GPU(s), least-loaded dispatch, <=50-token chunks, forced-EOS schedule, "
+                         f"lsd_steps=1, random-init PocketTTS ({args.arch}), seed 20260118")
+    elif args.queue > 0:  # C5 as written: one queue of N utterances, whatever the GPU count
         scaling = "strong"
         args.utterances = sh.shard_range(rank, world, args.queue)[1] - sh.shard_range(rank, world, args.queue)[0]
         workload_name = (f"C5: {args.queue} queued utterances in total x U{{5..60}} words split over {world} GPU(s), "
@@ -189,9 +202,13 @@ def main():
         workload_name = (f"C5 shard: {args.utterances} utterances/GPU x U{{5..60}} words, <=50-token chunks, "
                          f"forced-EOS schedule, lsd_steps=1, random-init PocketTTS ({args.arch}), seed 20260118")
     DTYPE = "f32 storage/accumulate, split-bf16x3 operands"
-    config = {"workload": workload_name, "utterances_per_gpu": args.utterances, "max_batch": args.max_batch,
+    config = {"workload": workload_name,
+              "utterances_per_gpu": args.utterances // args.gpus if args.pool else args.utterances,
+              "max_batch": args.max_batch,
+              "parallelism": (f"in-process pool over {args.gpus} GPU(s), least-loaded dispatch, no collective" if args.pool
+                              else "one process per GPU, utterances sharded by rank, no collective"),
               "l2": "working set (weights 341 MB + KV + Mimi workspace, several GB) >> 126 MB L2; no flush needed",
-              "weights": "fp32 as stored by the reference"}
+              "weights": "fp32 as stored by the reference", "kv_cache": "fp16 storage, fp32 attention arithmetic"}
 
     # ---------------- reference arm: CPU port on host cores -----------------
     if args.impl == "reference":
@@ -237,10 +254,14 @@ def main():
 
     pkg.build_library()
     tensors = ck.make_checkpoint(arch)
-    rt = pkg.NativeCudaRuntime(tensors=tensors, device=local_rank, max_batch=args.max_batch, max_seq_tokens=512,
-                               max_frames=256, mimi_group_frames=2048)
-    first_utt = sh.shard_range(rank, world, args.queue)[0] if args.queue > 0 else \
-        sh.shard_range(rank, world, args.utterances)[0]
+    if args.pool:
+        rt = pkg.NativeCudaPool(tensors=tensors, devices=list(range(args.gpus)), max_batch=args.max_batch,
+                                max_seq_tokens=512, max_frames=256, mimi_group_frames=2048)
+    else:
+        rt = pkg.NativeCudaRuntime(tensors=tensors, device=local_rank, max_batch=args.max_batch, max_seq_tokens=512,
+                                   max_frames=256, mimi_group_frames=2048)
+    first_utt = 0 if args.pool else (sh.shard_range(rank, world, args.queue)[0] if args.queue > 0 else
+                                     sh.shard_range(rank, world, args.utterances)[0])
     chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=first_utt)
     noises = [c.noise() for c in chunks]
     h2d = sum(c.tokens.nbytes + n.nbytes for c, n in zip(chunks, noises))
@@ -291,12 +312,15 @@ def main():
     clocks = sampler.stop() if rank == 0 else {}
     # (3) one more timed step with per-launch CUDA events (roofline accounting;
     #     event pairs around every GEMM/attention launch, CUDA graphs off)
+    eng0 = rt.engine(0) if args.pool else rt  # per-kernel profile and the latency leg run on one engine
     rt.stage_times(reset=True)
-    rt.profile(True)
+    for i in range(n_dev):
+        (rt.engine(i) if args.pool else rt).profile(True)
     ms3, frames3, _, _ = timed(True, 1)
-    prof = rt.profile_report()
+    prof = eng0.profile_report()
     st3 = rt.stage_times()
-    rt.profile(False)
+    for i in range(n_dev):
+        (rt.engine(i) if args.pool else rt).profile(False)
     value = sh.job_throughput(frames, ms)
     e2e = sh.job_throughput(frames2, ms2)
     out = None
@@ -355,7 +379,7 @@ def main():
         roofline_by_class = {k: roofline_of(k, v) for k, v in classes if v["ms"] > 0 and (v["flops"] or v["bytes"])}
         alg_flops = 2.0 * (info.macs_ar_frame + info.macs_mimi_frame) * frames
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus_job, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config,
             "clocks": clocks,
@@ -372,9 +396,9 @@ def main():
                           "compute); the value leg leaves PCM on the device, so its d2h_ms is 0 by construction",
             "mean_batch_occupancy": st["step_rows"] / max(st["steps"], 1),
             "steps_per_s_rank0": st["steps"] / (ms / 1e3),
-            "realtime_factor_per_gpu": value / world,
+            "realtime_factor_per_gpu": value / n_gpus_job,
             "achieved_tflops_job": alg_flops / (ms * 1e9),
-            "frac_of_tensor_roofline_job": alg_flops / (ms * 1e9) / (peaks["tf_sustained"] * world),
+            "frac_of_tensor_roofline_job": alg_flops / (ms * 1e9) / (peaks["tf_sustained"] * n_gpus_job),
             "wall_ms_per_step": wall_ms / max(args.steps, 1),
             "frames_per_step": frames / max(args.steps, 1),
         }
@@ -387,27 +411,27 @@ def main():
         for i in range(12):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            s = rt.seq_open(c2.tokens, reserve_frames=8)
-            rt.step([s], n2[0])
+            s = eng0.seq_open(c2.tokens, reserve_frames=8)
+            eng0.step([s], n2[0])
             pcm = s.decode(0, 1)
             ttfa.append((time.perf_counter() - t0) * 1e3)
             s.close()
         ttfa = sorted(ttfa[2:])
-        s = rt.seq_open(c2.tokens, reserve_frames=256)
+        s = eng0.seq_open(c2.tokens, reserve_frames=256)
         for i in range(8):
-            rt.step([s], n2[i])
-        rt.stage_times(reset=True)
+            eng0.step([s], n2[i])
+        eng0.stage_times(reset=True)
         t0 = time.perf_counter()
         nb1 = 64
         for i in range(nb1):
-            rt.step([s], n2[8 + i])
+            eng0.step([s], n2[8 + i])
         b1_wall = (time.perf_counter() - t0) / nb1
-        st1 = rt.stage_times()
-        rt.profile(True)   # separate instrumented steps for the per-kernel GB/s (graphs off)
+        st1 = eng0.stage_times()
+        eng0.profile(True)   # separate instrumented steps for the per-kernel GB/s (graphs off)
         for i in range(16):
-            rt.step([s], n2[80 + i])
-        p1 = rt.profile_report()
-        rt.profile(False)
+            eng0.step([s], n2[80 + i])
+        p1 = eng0.profile_report()
+        eng0.profile(False)
         s.close()
         gv = p1.get("gemv_f32", {"ms": 0, "bytes": 0, "launches": 1})
         peaks = load_peaks()
@@ -425,7 +449,7 @@ def main():
         }
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ---------------
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.pool and not args.no_cpu_baseline:
         o = ge.oracle()
         cores = os.cpu_count() or 1
         om = o.OracleModel(tensors)

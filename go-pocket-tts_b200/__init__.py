@@ -24,7 +24,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libpockettts_cuda.so")
-CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "attention_mma.cu", "step_fused.cu", "resblock.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "safetensors.cpp"]
+CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "attention_mma.cu", "step_fused.cu", "resblock.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "pool.cu", "safetensors.cpp"]
 
 PTTS_OK, PTTS_EINVAL, PTTS_ECUDA, PTTS_ENOMEM, PTTS_ESTATE, PTTS_ECANCELED = 0, -1, -2, -3, -4, -5
 PTTS_REQ_NO_PCM_D2H = 1
@@ -131,6 +131,10 @@ EXPORTS = [
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
     "ptts_voice_cache_stats", "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
+    "ptts_pool_create", "ptts_pool_destroy", "ptts_pool_size", "ptts_pool_engine", "ptts_pool_load_tensor",
+    "ptts_pool_load_safetensors", "ptts_pool_finalize_weights", "ptts_pool_submit", "ptts_pool_wait", "ptts_pool_cancel",
+    "ptts_pool_ticket_error", "ptts_pool_ticket_latents", "ptts_pool_ticket_release", "ptts_pool_generate_audio",
+    "ptts_pool_load",
 ]
 
 _lib = None
@@ -185,6 +189,22 @@ def lib() -> C.CDLL:
     L.ptts_debug_gemm_bench.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp]
     L.ptts_debug_gemm.argtypes = [vp, fp, C.c_int32, C.c_int32, fp, C.c_int32, fp, C.c_int32, C.c_int32, fp]
     L.ptts_profile_report.argtypes = [vp, C.c_char_p, C.c_int32]
+    L.ptts_pool_create.argtypes = [C.POINTER(PttsConfig), ip, C.c_int32, C.POINTER(vp)]
+    L.ptts_pool_destroy.argtypes = [vp]
+    L.ptts_pool_destroy.restype = None
+    L.ptts_pool_size.argtypes = [vp]
+    L.ptts_pool_engine.argtypes = [vp, C.c_int32, C.POINTER(vp)]
+    L.ptts_pool_load_tensor.argtypes = [vp, C.c_char_p, i64p, C.c_int32, C.c_int32, vp]
+    L.ptts_pool_load_safetensors.argtypes = [vp, C.c_char_p]
+    L.ptts_pool_finalize_weights.argtypes = [vp]
+    L.ptts_pool_submit.argtypes = gen_args + [i64p, ip]
+    L.ptts_pool_wait.argtypes = [vp, C.c_int64, C.POINTER(PttsResult)]
+    L.ptts_pool_cancel.argtypes = [vp, C.c_int64]
+    L.ptts_pool_ticket_error.argtypes = [vp, C.c_int64, C.c_char_p, C.c_int32]
+    L.ptts_pool_ticket_latents.argtypes = [vp, C.c_int64, fp, fp, C.c_int32]
+    L.ptts_pool_ticket_release.argtypes = [vp, C.c_int64]
+    L.ptts_pool_generate_audio.argtypes = gen_args + [C.POINTER(PttsResult)]
+    L.ptts_pool_load.argtypes = [vp, i64p, ip, i64p, C.c_int32]
     _lib = L
     return L
 
@@ -403,36 +423,56 @@ class NativeCudaRuntime:
         pcm = None if cfg.no_pcm_d2h else np.empty(ms * SAMPLES_PER_FRAME,
                                                     dtype=np.int16 if getattr(cfg, "pcm16", False) else np.float32)
         ticket = C.c_int64()
-        _check(self._lib.ptts_submit(self._h, toks.ctypes.data_as(C.POINTER(C.c_int64)), toks.size, vemb, vframes,
-                                     vkv, C.byref(g), _fptr(noise), noise.shape[0],
-                                     None if pcm is None else pcm.ctypes.data_as(C.POINTER(C.c_float)),
-                                     0 if pcm is None else pcm.size, C.byref(ticket)))
+        _check(self._submit(toks.ctypes.data_as(C.POINTER(C.c_int64)), toks.size, vemb, vframes,
+                            vkv, C.byref(g), _fptr(noise), noise.shape[0],
+                            None if pcm is None else pcm.ctypes.data_as(C.POINTER(C.c_float)),
+                            0 if pcm is None else pcm.size, C.byref(ticket)))
         return _Pending(ticket.value, keep, pcm, ms)
+
+    # the five entry points a pool overrides (ptts_pool_*)
+    def _submit(self, *a):
+        return self._lib.ptts_submit(self._h, *a)
+
+    def _wait(self, ticket, res):
+        return self._lib.ptts_wait(self._h, ticket, res)
+
+    def _ticket_error(self, ticket, buf, cap):
+        return self._lib.ptts_ticket_error(self._h, ticket, buf, cap)
+
+    def _ticket_latents(self, ticket, lat, eos, cap):
+        return self._lib.ptts_ticket_latents(self._h, ticket, lat, eos, cap)
+
+    def _ticket_release(self, ticket):
+        return self._lib.ptts_ticket_release(self._h, ticket)
+
+    def _cancel(self, ticket):
+        return self._lib.ptts_cancel(self._h, ticket)
 
     def wait(self, p: _Pending, want_latents: bool = False) -> GenerateResult:
         res = PttsResult()
-        rc = self._lib.ptts_wait(self._h, p.ticket, C.byref(res))
+        rc = self._wait(p.ticket, C.byref(res))
         try:
             if rc != 0:  # the request's own message (not the calling thread's last error)
                 if self._h is None:  # engine closed under the waiter: ptts_wait left the text on this thread
                     raise NativeCudaError(rc, self._lib.ptts_last_error().decode("utf-8", "replace"))
                 buf = C.create_string_buffer(512)
-                self._lib.ptts_ticket_error(self._h, p.ticket, buf, len(buf))
+                self._ticket_error(p.ticket, buf, len(buf))
                 raise NativeCudaError(rc, buf.value.decode("utf-8", "replace"))
             lat = eos = None
             if want_latents:
                 lat = np.empty((res.n_frames, LATENT_DIM), dtype=np.float32)
                 eos = np.empty(res.n_frames, dtype=np.float32)
-                n = self._lib.ptts_ticket_latents(self._h, p.ticket, _fptr(lat), _fptr(eos), res.n_frames)
+                n = self._ticket_latents(p.ticket, _fptr(lat), _fptr(eos), res.n_frames)
                 if n < 0:
                     _check(n)
             pcm = p.pcm[: res.n_samples] if p.pcm is not None else np.empty(0, np.float32)  # view: no extra host copy
             return GenerateResult(pcm, res.n_frames, res.queue_ms, res.first_frame_ms, res.total_ms, lat, eos)
         finally:
-            self._lib.ptts_ticket_release(self._h, p.ticket)
+            if self._h is not None:
+                self._ticket_release(p.ticket)
 
     def cancel(self, p: _Pending):
-        _check(self._lib.ptts_cancel(self._h, p.ticket))
+        _check(self._cancel(p.ticket))
 
     def generate_audio(self, tokens: Sequence[int], cfg: Optional[RuntimeGenerateConfig] = None) -> np.ndarray:
         """GenerateAudio(ctx, tokens, cfg) ([]float32, error)."""
@@ -541,6 +581,89 @@ class NativeCudaRuntime:
         out = np.empty(n, dtype=np.float32)
         self._lib.ptts_debug_fetch(self._h, name.encode(), _fptr(out), n)
         return out
+
+
+class NativeCudaPool(NativeCudaRuntime):
+    """One process, several GPUs: a `tts.Runtime` whose GenerateAudio calls are dispatched
+    to the least-loaded of N engines (one per device, weights replicated).  submit / wait / generate /
+    cancel are those of NativeCudaRuntime; `engine(i)` borrows one engine for stage times and stats."""
+
+    def __init__(self, checkpoint: Optional[str] = None, *, devices: Optional[Sequence[int]] = None,
+                 max_batch: int = 256, max_seq_tokens: int = 1024, max_frames: int = 512, mimi_group_frames: int = 0,
+                 kv_pages: int = 0, tensors: Optional[dict] = None, flags: int = 0):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        cfg = PttsConfig(device=0, max_batch=max_batch, max_seq_tokens=max_seq_tokens, max_frames=max_frames,
+                         mimi_group_frames=mimi_group_frames, kv_pages=kv_pages, flags=flags)
+        devs = None if devices is None else (C.c_int32 * len(devices))(*devices)
+        _check(self._lib.ptts_pool_create(C.byref(cfg), devs, 0 if devices is None else len(devices), C.byref(self._h)))
+        try:
+            if checkpoint is not None:
+                _check(self._lib.ptts_pool_load_safetensors(self._h, checkpoint.encode()))
+            for k, a in (tensors or {}).items():
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                shape = (C.c_int64 * a.ndim)(*a.shape)
+                _check(self._lib.ptts_pool_load_tensor(self._h, k.encode(), shape, a.ndim, 0, a.ctypes.data_as(C.c_void_p)))
+            _check(self._lib.ptts_pool_finalize_weights(self._h))
+            info = PttsModelInfo()
+            _check(self._lib.ptts_model_info_get(self._engine_handle(0), C.byref(info)))
+            self.info = info
+        except Exception:
+            self.close()
+            raise
+
+    @property
+    def size(self) -> int:
+        return self._lib.ptts_pool_size(self._h)
+
+    def _engine_handle(self, i: int):
+        h = C.c_void_p()
+        _check(self._lib.ptts_pool_engine(self._h, i, C.byref(h)))
+        return h
+
+    def engine(self, i: int) -> NativeCudaRuntime:
+        """Borrowed view of engine i (stage_times, voice_cache_stats, profile); do not close it."""
+        v = NativeCudaRuntime.__new__(NativeCudaRuntime)
+        v._lib, v._h, v.info = self._lib, self._engine_handle(i), self.info
+        v.close = lambda: None
+        return v
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.ptts_pool_destroy(h)
+
+    def load(self) -> dict:
+        n = self.size
+        cost, req, disp = (C.c_int64 * n)(), (C.c_int32 * n)(), (C.c_int64 * n)()
+        self._lib.ptts_pool_load(self._h, cost, req, disp, n)
+        return {"inflight_cost": list(cost), "inflight_requests": list(req), "dispatched": list(disp)}
+
+    def stage_times(self, reset: bool = False) -> dict:
+        """Sum over the engines (they run concurrently: the ms figures are device time, not wall time)."""
+        tot = None
+        for i in range(self.size):
+            t = self.engine(i).stage_times(reset)
+            tot = t if tot is None else {k: tot[k] + t[k] for k in t}
+        return tot
+
+    def _submit(self, *a):
+        return self._lib.ptts_pool_submit(self._h, *a, None)
+
+    def _wait(self, ticket, res):
+        return self._lib.ptts_pool_wait(self._h, ticket, res)
+
+    def _ticket_error(self, ticket, buf, cap):
+        return self._lib.ptts_pool_ticket_error(self._h, ticket, buf, cap)
+
+    def _ticket_latents(self, ticket, lat, eos, cap):
+        return self._lib.ptts_pool_ticket_latents(self._h, ticket, lat, eos, cap)
+
+    def _ticket_release(self, ticket):
+        return self._lib.ptts_pool_ticket_release(self._h, ticket)
+
+    def _cancel(self, ticket):
+        return self._lib.ptts_pool_cancel(self._h, ticket)
 
 
 class Sequence_:

@@ -6,7 +6,7 @@
 
 namespace ptts {
 
-static bool g_pdl = false;
+static thread_local bool g_pdl = false;
 bool pdl_enabled() { return g_pdl; }
 void pdl_set(bool on) { g_pdl = on; }
 

@@ -314,6 +314,10 @@ struct Engine {
   int64_t next_ticket = 1;
   std::thread sched;
   bool sched_running = false, sched_stop = false;
+  // load seen by a multi-GPU dispatcher (pool.cu): frames still to generate + prompt tokens still to
+  // prefill, over every request submitted and not yet completed
+  std::atomic<long> inflight_cost{0};
+  std::atomic<int> inflight_requests{0};
 
   ~Engine();
   int create(const ptts_config *c);
@@ -388,6 +392,8 @@ struct Seq {
 
 struct Request {
   int64_t ticket = 0;
+  Engine *eng = nullptr; // owner (load accounting)
+  long cost = 0;
   std::vector<int64_t> tokens;
   const float *voice_emb = nullptr;
   int voice_frames = 0;

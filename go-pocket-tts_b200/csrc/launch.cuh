@@ -16,9 +16,20 @@ namespace ptts {
 #define PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 
-// Set by the engine around the AR step (graph capture keeps the programmatic edges).
+// Set by the engine around the AR step (graph capture keeps the programmatic edges).  Per thread:
+// every engine of a multi-GPU pool launches from its own scheduler thread.
 bool pdl_enabled();
 void pdl_set(bool on);
+
+// cudaFuncSetAttribute is per device: launch wrappers that configure a kernel lazily keep one
+// flag per device ordinal (several engines of one process may sit on different GPUs).
+// Returns the flag of the current device; the caller sets it AFTER configuring (two engines on one
+// device may both configure once, which is harmless; neither launches unconfigured).
+inline volatile bool &device_flag(volatile bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return flags[dev & 63];
+}
 
 // cluster > 1: thread-block clusters of that many consecutive CTAs along x (grid.x must be a
 // multiple of it).

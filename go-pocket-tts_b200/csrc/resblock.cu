@@ -342,11 +342,12 @@ __global__ void __launch_bounds__(rb_threads(C), 1)
 template <int C, int H>
 int launch_rb(const TcWeight &w1, const TcWeight &w2, const void *amap, const RbArgs &a, cudaStream_t st) {
   using SM = RbSmem<C, H>;
-  static bool configured = false;
-  if (!configured) {
+  static volatile bool configured[64] = {};
+  volatile bool &conf = device_flag(configured);
+  if (!conf) {
     if (cudaFuncSetAttribute(resblock_kernel<C, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES) != cudaSuccess)
       return -1;
-    configured = true;
+    conf = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -30,6 +30,12 @@ static int resolve_max_steps(const ptts_gen_cfg &c, int ntok) {
 
 void complete_request(const std::shared_ptr<Request> &r, int status, const char *msg) {
   std::unique_lock<std::mutex> lk(r->mu);
+  if (r->done)
+    return;
+  if (r->eng) {
+    r->eng->inflight_cost.fetch_sub(r->cost);
+    r->eng->inflight_requests.fetch_sub(1);
+  }
   r->res.status = status;
   if (msg)
     r->err = msg;
@@ -538,11 +544,15 @@ int ptts_submit(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const f
   r->max_steps = ms;
   r->lsd_steps = cfg->lsd_decode_steps > 0 ? cfg->lsd_decode_steps : 1;
   r->t_submit = std::chrono::steady_clock::now();
+  r->eng = &E;
+  r->cost = (long)ms + n_tokens + (voice_emb ? voice_frames : 0);
   E.ensure_sched();
   {
     std::unique_lock<std::mutex> lk(E.q_mu);
     if (E.sched_stop)
       PTTS_FAIL(PTTS_ESTATE, "native-cuda runtime unavailable: engine is shutting down");
+    E.inflight_cost.fetch_add(r->cost);
+    E.inflight_requests.fetch_add(1);
     r->ticket = E.next_ticket++;
     E.tickets[r->ticket] = r;
     E.queue.push_back(r);
@@ -648,6 +658,7 @@ int ptts_seq_open(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const
     PTTS_FAIL(PTTS_EINVAL, "generate: voice embedding and voice model state are mutually exclusive");
   Engine &E = e->impl;
   std::unique_lock<std::mutex> gl(E.gpu_mu);
+  cudaSetDevice(E.device);
   if (reserve_frames <= 0)
     reserve_frames = E.max_frames;
   int vt = voice_kv ? voice_kv->layers[0].offset : (voice_emb ? voice_frames : 0);
@@ -677,6 +688,7 @@ int ptts_step(ptts_engine *e, ptts_seq *const *seqs, int32_t batch, const float 
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: step: noise is NULL");
   Engine &E = e->impl;
   std::unique_lock<std::mutex> gl(E.gpu_mu);
+  cudaSetDevice(E.device);
   std::vector<Seq *> v;
   for (int i = 0; i < batch; i++) {
     if (!seqs[i])
@@ -693,6 +705,7 @@ int ptts_decode(ptts_engine *e, ptts_seq *seq, int32_t first_frame, int32_t n_fr
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: decode: bad arguments");
   Engine &E = e->impl;
   std::unique_lock<std::mutex> gl(E.gpu_mu);
+  cudaSetDevice(E.device);
   const int spf = E.info.samples_per_frame;
   if (first_frame == 0)
     return E.decode_seqs({&seq->impl}, {0}, {n_frames}, {pcm_out}, true);
@@ -720,6 +733,7 @@ int ptts_decode_latents(ptts_engine *e, const float *latents, const int32_t *fra
     PTTS_FAIL(PTTS_EINVAL, "native: latent tensor is nil");
   Engine &E = e->impl;
   std::unique_lock<std::mutex> gl(E.gpu_mu);
+  cudaSetDevice(E.device);
   const int spf = E.info.samples_per_frame;
   const int max_segs = (E.mimi_rows_cap - E.up_stride * E.mimi_frames_cap) / E.mimi_pad;
   int i = 0;
@@ -763,6 +777,7 @@ int ptts_seq_read_kv(ptts_engine *e, ptts_seq *s, int32_t layer, int32_t which, 
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: read_kv: bad arguments");
   Engine &E = e->impl;
   std::unique_lock<std::mutex> gl(E.gpu_mu);
+  cudaSetDevice(E.device);
   int T = s->impl.kv_len;
   if (T == 0)
     return PTTS_OK;
@@ -884,6 +899,7 @@ int64_t ptts_debug_fetch(ptts_engine *e, const char *name, float *out, int64_t c
     return -1;
   Engine &E = e->impl;
   std::unique_lock<std::mutex> gl(E.gpu_mu);
+  cudaSetDevice(E.device);
   auto it = E.debug_bufs.find(name);
   if (it == E.debug_bufs.end())
     return -1;

@@ -781,12 +781,12 @@ int tc_cluster_capacity(int bn, int cs) {
 template <int BN, int STAGES, bool ATMA, int EW = 4>
 int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES, EW>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SM::BYTES) != cudaSuccess)
+  static volatile bool configured[64] = {};
+  volatile bool &conf = device_flag(configured);
+  if (!conf) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES) != cudaSuccess)
       return -1;
-    configured = true;
+    conf = true;
   }
   const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(
       BN == 256 ? w.map256 : (BN == 128 ? w.map128 : (BN == 64 ? w.map64 : w.map32)));

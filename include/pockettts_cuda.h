@@ -190,6 +190,44 @@ int ptts_ticket_latents(ptts_engine *e, int64_t ticket, float *latents,
 int ptts_ticket_error(ptts_engine *e, int64_t ticket, char *buf, int32_t cap);
 int ptts_ticket_release(ptts_engine *e, int64_t ticket);
 
+/* ---- multi-GPU pool: one process, one engine per device -------------------
+ * Replaces the server's worker semaphore on a multi-GPU box (reference
+ * internal/server/server.go:114,402-421): every device holds a full weight replica, its own
+ * paged KV pool and scheduler thread; a submitted chunk goes to the least-loaded device (frames
+ * still to generate + prompt tokens still to prefill over its unfinished requests).  Chunks are
+ * independent (internal/tts/service.go:138-153), so nothing crosses GPUs: no collective.
+ * devices == NULL / n_devices == 0: every visible GPU.  cfg->device is ignored. */
+typedef struct ptts_pool ptts_pool;
+int ptts_pool_create(const ptts_config *cfg, const int32_t *devices, int32_t n_devices, ptts_pool **out);
+void ptts_pool_destroy(ptts_pool *p); /* NULL-safe */
+int ptts_pool_size(ptts_pool *p);
+/* Borrows engine `index` (model info, stage times, voice cache stats); owned by the pool. */
+int ptts_pool_engine(ptts_pool *p, int32_t index, ptts_engine **out);
+int ptts_pool_load_tensor(ptts_pool *p, const char *key, const int64_t *shape, int32_t rank, int32_t dtype,
+                          const void *host_ptr);
+int ptts_pool_load_safetensors(ptts_pool *p, const char *path);
+int ptts_pool_finalize_weights(ptts_pool *p);
+/* Same contract as ptts_submit / ptts_wait / ...; engine_index (optional) receives the device slot
+ * the chunk was sent to.  A multi-chunk utterance may fan out over GPUs: the caller re-assembles
+ * its chunks in order (service.go:138-153 concatenates them anyway). */
+int ptts_pool_submit(ptts_pool *p, const int64_t *tokens, int32_t n_tokens, const float *voice_emb,
+                     int32_t voice_frames, const ptts_voice_kv *voice_kv, const ptts_gen_cfg *cfg,
+                     const float *noise, int32_t noise_rows, float *pcm_out, int64_t pcm_cap, int64_t *ticket,
+                     int32_t *engine_index);
+int ptts_pool_wait(ptts_pool *p, int64_t ticket, ptts_result *result);
+int ptts_pool_cancel(ptts_pool *p, int64_t ticket);
+int ptts_pool_ticket_error(ptts_pool *p, int64_t ticket, char *buf, int32_t cap);
+int ptts_pool_ticket_latents(ptts_pool *p, int64_t ticket, float *latents, float *eos_logits, int32_t cap_frames);
+int ptts_pool_ticket_release(ptts_pool *p, int64_t ticket);
+int ptts_pool_generate_audio(ptts_pool *p, const int64_t *tokens, int32_t n_tokens, const float *voice_emb,
+                             int32_t voice_frames, const ptts_voice_kv *voice_kv, const ptts_gen_cfg *cfg,
+                             const float *noise, int32_t noise_rows, float *pcm_out, int64_t pcm_cap,
+                             ptts_result *result);
+/* Dispatcher view, one entry per engine (up to cap): outstanding load, unfinished requests,
+ * requests dispatched so far.  Returns the number of entries written. */
+int ptts_pool_load(ptts_pool *p, int64_t *inflight_cost, int32_t *inflight_requests, int64_t *dispatched,
+                   int32_t cap);
+
 /* ---- stage-level API: mirrors native.Model
  *      {NewFlowState, NewFlowStateFromVoiceModelState, PromptFlow,
  *       SampleNextLatentStateful, LatentToMimi, MimiDecode}
