@@ -29,6 +29,7 @@ CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "attention_mma.cu", "step_fused.
 PTTS_OK, PTTS_EINVAL, PTTS_ECUDA, PTTS_ENOMEM, PTTS_ESTATE, PTTS_ECANCELED = 0, -1, -2, -3, -4, -5
 PTTS_REQ_NO_PCM_D2H = 1
 PTTS_REQ_PCM16 = 2
+PTTS_REQ_STREAM = 4
 LATENT_DIM = 32
 SAMPLES_PER_FRAME = 1920
 SAMPLE_RATE = 24000
@@ -95,7 +96,8 @@ class PttsConfig(C.Structure):
 class PttsGenCfg(C.Structure):
     _fields_ = [("temperature", C.c_double), ("eos_threshold", C.c_double), ("max_steps", C.c_int32),
                 ("estimated_max_steps", C.c_int32), ("lsd_decode_steps", C.c_int32),
-                ("frames_after_eos", C.c_int32), ("force_eos_step", C.c_int32), ("flags", C.c_int32)]
+                ("frames_after_eos", C.c_int32), ("force_eos_step", C.c_int32), ("flags", C.c_int32),
+                ("stream_frames", C.c_int32)]
 
 
 class PttsVoiceLayer(C.Structure):
@@ -127,13 +129,14 @@ class PttsResult(C.Structure):
 EXPORTS = [
     "ptts_last_error", "ptts_version", "ptts_device_count", "ptts_create", "ptts_destroy", "ptts_load_tensor",
     "ptts_load_safetensors", "ptts_finalize_weights", "ptts_model_info_get", "ptts_generate_audio",
-    "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_error", "ptts_ticket_release", "ptts_seq_open",
+    "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_error", "ptts_ticket_read",
+    "ptts_ticket_release", "ptts_seq_open",
     "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
     "ptts_voice_cache_stats", "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
     "ptts_pool_create", "ptts_pool_destroy", "ptts_pool_size", "ptts_pool_engine", "ptts_pool_load_tensor",
     "ptts_pool_load_safetensors", "ptts_pool_finalize_weights", "ptts_pool_submit", "ptts_pool_wait", "ptts_pool_cancel",
-    "ptts_pool_ticket_error", "ptts_pool_ticket_latents", "ptts_pool_ticket_release", "ptts_pool_generate_audio",
+    "ptts_pool_ticket_error", "ptts_pool_ticket_latents", "ptts_pool_ticket_read", "ptts_pool_ticket_release", "ptts_pool_generate_audio",
     "ptts_pool_load",
 ]
 
@@ -169,6 +172,7 @@ def lib() -> C.CDLL:
     L.ptts_cancel.argtypes = [vp, C.c_int64]
     L.ptts_ticket_latents.argtypes = [vp, C.c_int64, fp, fp, C.c_int32]
     L.ptts_ticket_error.argtypes = [vp, C.c_int64, C.c_char_p, C.c_int32]
+    L.ptts_ticket_read.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, ip, ip]
     L.ptts_ticket_release.argtypes = [vp, C.c_int64]
     L.ptts_seq_open.argtypes = [vp, i64p, C.c_int32, fp, C.c_int32, C.POINTER(PttsVoiceKV), C.c_int32,
                                 C.POINTER(vp)]
@@ -202,6 +206,7 @@ def lib() -> C.CDLL:
     L.ptts_pool_cancel.argtypes = [vp, C.c_int64]
     L.ptts_pool_ticket_error.argtypes = [vp, C.c_int64, C.c_char_p, C.c_int32]
     L.ptts_pool_ticket_latents.argtypes = [vp, C.c_int64, fp, fp, C.c_int32]
+    L.ptts_pool_ticket_read.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, ip, ip]
     L.ptts_pool_ticket_release.argtypes = [vp, C.c_int64]
     L.ptts_pool_generate_audio.argtypes = gen_args + [C.POINTER(PttsResult)]
     L.ptts_pool_load.argtypes = [vp, i64p, ip, i64p, C.c_int32]
@@ -267,6 +272,7 @@ class RuntimeGenerateConfig:
     force_eos_step: int = -1
     no_pcm_d2h: bool = False
     pcm16: bool = False  # PCM16 samples quantised on the device (wav_stream.go:44-54); GenerateResult.pcm is int16
+    stream_frames: int = 0  # > 0: frame-level streaming (PTTS_REQ_STREAM), PCM delivered every this many frames
 
 
 def estimate_max_frames(n_tokens: int, frame_rate: float = 12.5) -> int:
@@ -417,9 +423,12 @@ class NativeCudaRuntime:
         flags = PTTS_REQ_NO_PCM_D2H if cfg.no_pcm_d2h else 0
         if getattr(cfg, "pcm16", False):
             flags |= PTTS_REQ_PCM16
+        if getattr(cfg, "stream_frames", 0) > 0:
+            flags |= PTTS_REQ_STREAM
         g = PttsGenCfg(temperature=cfg.temperature, eos_threshold=cfg.eos_threshold, max_steps=cfg.max_steps,
                        estimated_max_steps=cfg.estimated_max_steps, lsd_decode_steps=cfg.lsd_decode_steps,
-                       frames_after_eos=cfg.frames_after_eos, force_eos_step=cfg.force_eos_step, flags=flags)
+                       frames_after_eos=cfg.frames_after_eos, force_eos_step=cfg.force_eos_step, flags=flags,
+                       stream_frames=max(getattr(cfg, "stream_frames", 0), 0))
         pcm = None if cfg.no_pcm_d2h else np.empty(ms * SAMPLES_PER_FRAME,
                                                     dtype=np.int16 if getattr(cfg, "pcm16", False) else np.float32)
         ticket = C.c_int64()
@@ -444,6 +453,9 @@ class NativeCudaRuntime:
 
     def _ticket_release(self, ticket):
         return self._lib.ptts_ticket_release(self._h, ticket)
+
+    def _ticket_read(self, ticket, have, timeout, ready, done):
+        return self._lib.ptts_ticket_read(self._h, ticket, have, timeout, ready, done)
 
     def _cancel(self, ticket):
         return self._lib.ptts_cancel(self._h, ticket)
@@ -473,6 +485,32 @@ class NativeCudaRuntime:
 
     def cancel(self, p: _Pending):
         _check(self._cancel(p.ticket))
+
+    def read(self, p: _Pending, have_frames: int = 0, timeout_ms: int = -1):
+        """ptts_ticket_read: (frames_ready, done).  PCM of frames [0, frames_ready) is valid in p.pcm."""
+        ready, done = C.c_int32(0), C.c_int32(0)
+        rc = self._ticket_read(p.ticket, have_frames, timeout_ms, C.byref(ready), C.byref(done))
+        if rc != 0:
+            raise NativeCudaError(rc, self._lib.ptts_last_error().decode("utf-8", "replace"))
+        return ready.value, bool(done.value)
+
+    def stream(self, tokens, cfg: RuntimeGenerateConfig):
+        """SynthesizeStream at frame granularity (tts/runtime.go:33-38 PCMChunk): yields the PCM of the
+        frames delivered since the previous yield, as views into one buffer."""
+        if cfg.stream_frames <= 0:
+            cfg = RuntimeGenerateConfig(**{**cfg.__dict__, "stream_frames": 1})
+        p = self.submit(tokens, cfg)
+        have = 0
+        try:
+            while True:
+                ready, done = self.read(p, have)
+                if ready > have:
+                    yield p.pcm[have * SAMPLES_PER_FRAME: ready * SAMPLES_PER_FRAME]
+                    have = ready
+                if done:
+                    break
+        finally:
+            self.wait(p)
 
     def generate_audio(self, tokens: Sequence[int], cfg: Optional[RuntimeGenerateConfig] = None) -> np.ndarray:
         """GenerateAudio(ctx, tokens, cfg) ([]float32, error)."""
@@ -661,6 +699,9 @@ class NativeCudaPool(NativeCudaRuntime):
 
     def _ticket_release(self, ticket):
         return self._lib.ptts_pool_ticket_release(self._h, ticket)
+
+    def _ticket_read(self, ticket, have, timeout, ready, done):
+        return self._lib.ptts_pool_ticket_read(self._h, ticket, have, timeout, ready, done)
 
     def _cancel(self, ticket):
         return self._lib.ptts_pool_cancel(self._h, ticket)

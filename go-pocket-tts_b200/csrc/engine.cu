@@ -2217,11 +2217,11 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
 // and hand each group to the finisher thread (PCM D2H and request completion overlap the
 // following AR steps).  The sequences can be released as soon as this returns: every read
 // of their frame history is already ordered on the stream.
-int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
+int Engine::decode_async(const std::vector<DecodeItem> &items) {
   ensure_finisher();
   size_t i = 0;
   const int max_segs = (mimi_rows_cap - up_stride * mimi_frames_cap) / mimi_pad;
-  while (i < reqs.size()) {
+  while (i < items.size()) {
     PcmJob job;
     std::vector<MimiSeg> segs;
     int tf = 0;
@@ -2233,9 +2233,10 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
     }
     pcm_next = (pcm_next + 1) % NPCM;
     job.buf = k;
-    while (i < reqs.size() && (int)segs.size() < max_segs) {
-      const std::shared_ptr<Request> &r = reqs[i];
-      const int n = r->seq->frames;
+    while (i < items.size() && (int)segs.size() < max_segs) {
+      const DecodeItem &it = items[i];
+      const std::shared_ptr<Request> &r = it.r;
+      const int n = it.count;
       if (n <= 0 || n > mimi_frames_cap) { // cannot happen (finalize raises the workspace to max_frames): fail it alone
         char msg[128];
         snprintf(msg, sizeof msg, "native-cuda: %d frames exceed mimi_group_frames %d", n, mimi_frames_cap);
@@ -2251,11 +2252,15 @@ int Engine::decode_async(const std::vector<std::shared_ptr<Request>> &reqs) {
       sg.row0 = 0;
       sg.host_out = nullptr;
       for (int f = 0; f < n; f++)
-        h_moff_ring[k][tf + f] = ((int64_t)r->seq->slot * (max_frames + 1) + f + 1) * ldim;
+        h_moff_ring[k][tf + f] = ((int64_t)r->seq->slot * (max_frames + 1) + it.first + f + 1) * ldim;
       PcmJob::Seg js;
       js.r = r;
       js.lat_off = (size_t)tf * ldim;
       js.n_frames = n;
+      js.skip = it.skip;
+      js.out_frame0 = it.first + it.skip;
+      js.final = it.final;
+      js.stream_seq = r->stream_frames > 0 ? ++r->stream_seq : 0;
       job.segs.push_back(js);
       if (!(r->cfg.flags & PTTS_REQ_NO_PCM_D2H) && r->pcm_out) {
         if (r->cfg.flags & PTTS_REQ_PCM16)

@@ -263,7 +263,11 @@ struct Engine {
     struct Seg {
       std::shared_ptr<Request> r;
       size_t pcm_off = 0, lat_off = 0;
-      int n_frames = 0;
+      int n_frames = 0;   // frames decoded in this segment (window included)
+      int skip = 0;       // leading window frames: decoded for context only, not delivered
+      int out_frame0 = 0; // position of the first delivered frame in the request's PCM
+      int stream_seq = 0; // > 0: k-th delivery of a streaming request (applied in order)
+      bool final = true;  // complete the request after this segment
     };
     std::vector<Seg> segs;
   };
@@ -277,7 +281,17 @@ struct Engine {
   double fin_mimi_ms = 0, fin_d2h_ms = 0;
   void finisher_loop();
   void ensure_finisher();
-  int decode_async(const std::vector<std::shared_ptr<Request>> &reqs);
+  // One span of a request's latent frames to decode: [first, first + count), of which the first
+  // `skip` are context only.
+  struct DecodeItem {
+    std::shared_ptr<Request> r;
+    int first = 0, count = 0, skip = 0;
+    bool final = true;
+  };
+  int decode_async(const std::vector<DecodeItem> &items);
+  int mimi_window_frames() const { // receptive field of one output frame, in latent frames (f2)
+    return (ML * (Mctx > 0 ? Mctx - 1 : 8192) + 8 + up_stride - 1) / up_stride + 1;
+  }
 
   // ---- timing / counters ----
   ptts_stage_times times{};
@@ -411,6 +425,12 @@ struct Request {
   int countdown = 0;
   std::atomic<bool> cancel{false};
   std::vector<float> latents, eos;
+  // frame-level streaming (PTTS_REQ_STREAM)
+  int stream_frames = 0;  // 0: off
+  int stream_issued = 0;  // frames handed to a decode so far
+  int stream_seq = 0;     // deliveries issued
+  int stream_applied = 0; // deliveries applied by the finishers (in order)
+  int frames_ready = 0;   // PCM valid for frames [0, frames_ready)   (guarded by mu)
   std::chrono::steady_clock::time_point t_submit;
   int finished_at_iter = 0;
   // completion

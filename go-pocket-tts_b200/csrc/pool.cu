@@ -198,6 +198,14 @@ int ptts_pool_ticket_latents(ptts_pool *p, int64_t ticket, float *latents, float
   return rc ? rc : ptts_ticket_latents(e, t, latents, eos_logits, cap_frames);
 }
 
+int ptts_pool_ticket_read(ptts_pool *p, int64_t ticket, int32_t have_frames, int32_t timeout_ms, int32_t *frames_ready,
+                          int32_t *done) {
+  ptts_engine *e;
+  int64_t t;
+  int rc = pool_split(p, ticket, &e, &t);
+  return rc ? rc : ptts_ticket_read(e, t, have_frames, timeout_ms, frames_ready, done);
+}
+
 int ptts_pool_ticket_release(ptts_pool *p, int64_t ticket) {
   ptts_engine *e;
   int64_t t;

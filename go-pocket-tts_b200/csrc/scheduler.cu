@@ -94,16 +94,37 @@ void Engine::finisher_loop() {
     const int spf = info.samples_per_frame;
     for (auto &sg : job.segs) {
       Request &r = *sg.r;
-      if (job.rc == PTTS_OK) {
-        r.latents.assign(h_lat_ring[k] + sg.lat_off, h_lat_ring[k] + sg.lat_off + (size_t)sg.n_frames * ldim);
+      const int n_out = sg.n_frames - sg.skip; // the leading `skip` frames were decoded for context only
+      // Deliveries of a streaming request are applied in issue order, and under the request's lock:
+      // a cancelled / failed request is complete, its caller may already have released pcm_out.
+      std::unique_lock<std::mutex> slk(r.mu, std::defer_lock);
+      if (sg.stream_seq > 0) {
+        slk.lock();
+        r.cv.wait(slk, [&] { return r.stream_applied == sg.stream_seq - 1 || r.done; });
+      }
+      if (job.rc == PTTS_OK && n_out > 0 && !(sg.stream_seq > 0 && r.done)) {
+        const float *lat = h_lat_ring[k] + sg.lat_off + (size_t)sg.skip * ldim;
+        if (sg.stream_seq > 0)
+          r.latents.insert(r.latents.end(), lat, lat + (size_t)n_out * ldim);
+        else
+          r.latents.assign(lat, lat + (size_t)n_out * ldim);
         if (!(r.cfg.flags & PTTS_REQ_NO_PCM_D2H) && r.pcm_out) {
+          const size_t src = sg.pcm_off + (size_t)sg.skip * spf, dst = (size_t)sg.out_frame0 * spf;
           if (r.cfg.flags & PTTS_REQ_PCM16)
-            memcpy(r.pcm_out, h_s16_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(int16_t));
+            memcpy(reinterpret_cast<int16_t *>(r.pcm_out) + dst, h_s16_ring[k] + src, (size_t)n_out * spf * sizeof(int16_t));
           else
-            memcpy(r.pcm_out, h_pcm_ring[k] + sg.pcm_off, (size_t)sg.n_frames * spf * sizeof(float));
+            memcpy(r.pcm_out + dst, h_pcm_ring[k] + src, (size_t)n_out * spf * sizeof(float));
         }
       }
-      complete_request(sg.r, job.rc, job.rc ? job.msg.c_str() : nullptr);
+      if (sg.stream_seq > 0) {
+        r.stream_applied = sg.stream_seq;
+        if (job.rc == PTTS_OK && !r.done)
+          r.frames_ready = sg.out_frame0 + n_out;
+        r.cv.notify_all();
+        slk.unlock();
+      }
+      if (sg.final || job.rc)
+        complete_request(sg.r, job.rc, job.rc ? job.msg.c_str() : nullptr);
     }
     {
       std::unique_lock<std::mutex> lk(fin_mu);
@@ -339,6 +360,19 @@ void Engine::sched_loop() {
         }
       }
       std::vector<std::shared_ptr<Request>> keep;
+      std::vector<DecodeItem> deliveries; // PTTS_REQ_STREAM: new frames + their receptive field
+      const int wctx = mimi_window_frames();
+      auto deliver = [&](const std::shared_ptr<Request> &r, bool final) {
+        DecodeItem it;
+        it.r = r;
+        const int from = r->stream_issued, to = r->seq->frames;
+        it.first = from > wctx ? from - wctx : 0;
+        it.skip = from - it.first;
+        it.count = to - it.first;
+        it.final = final;
+        r->stream_issued = to;
+        deliveries.push_back(it);
+      };
       for (size_t i = 0; i < active.size(); i++) {
         auto &r = active[i];
         if (failed[i]) {
@@ -347,11 +381,29 @@ void Engine::sched_loop() {
           r->seq = nullptr;
           complete_request(r, fail_rc, fail_msg.c_str());
         } else if (finished[i]) {
-          r->finished_at_iter = (int)iter;
-          pending_frames += r->seq->frames;
-          pending.push_back(r);
-        } else
+          if (r->stream_frames > 0) { // the tail of a streaming request goes out at once
+            r->res.n_frames = r->seq->frames;
+            r->res.n_samples = (int64_t)r->seq->frames * info.samples_per_frame;
+            deliver(r, true);
+          } else {
+            r->finished_at_iter = (int)iter;
+            pending_frames += r->seq->frames;
+            pending.push_back(r);
+          }
+        } else {
+          if (r->stream_frames > 0 && r->seq->frames - r->stream_issued >= r->stream_frames)
+            deliver(r, false);
           keep.push_back(r);
+        }
+      }
+      if (!deliveries.empty()) {
+        decode_async(deliveries);
+        for (auto &it : deliveries)
+          if (it.final) { // every read of the sequence's state is ordered on the stream already
+            seq_free(it.r->seq);
+            delete reinterpret_cast<ptts_seq *>(it.r->seq);
+            it.r->seq = nullptr;
+          }
       }
       active.swap(keep);
     }
@@ -370,7 +422,14 @@ void Engine::sched_loop() {
         r->res.n_frames = r->seq->frames;
         r->res.n_samples = (int64_t)r->seq->frames * info.samples_per_frame;
       }
-      decode_async(pending); // every request is completed by the finisher (or, on error, inside)
+      std::vector<DecodeItem> whole;
+      for (auto &r : pending) {
+        DecodeItem it;
+        it.r = r;
+        it.count = r->seq->frames;
+        whole.push_back(it);
+      }
+      decode_async(whole); // every request is completed by the finisher (or, on error, inside)
       for (auto &r : pending) {
         // every read of this sequence's state is ordered on the stream already
         seq_free(r->seq);
@@ -543,6 +602,8 @@ int ptts_submit(ptts_engine *e, const int64_t *tokens, int32_t n_tokens, const f
   r->pcm_cap = pcm_cap;
   r->max_steps = ms;
   r->lsd_steps = cfg->lsd_decode_steps > 0 ? cfg->lsd_decode_steps : 1;
+  if ((cfg->flags & PTTS_REQ_STREAM) && !(cfg->flags & PTTS_REQ_NO_PCM_D2H))
+    r->stream_frames = cfg->stream_frames > 0 ? cfg->stream_frames : 1;
   r->t_submit = std::chrono::steady_clock::now();
   r->eng = &E;
   r->cost = (long)ms + n_tokens + (voice_emb ? voice_frames : 0);
@@ -622,6 +683,30 @@ int ptts_ticket_error(ptts_engine *e, int64_t ticket, char *buf, int32_t cap) {
   memcpy(buf, r->err.data(), n);
   buf[n] = 0;
   return (int)n;
+}
+
+int ptts_ticket_read(ptts_engine *e, int64_t ticket, int32_t have_frames, int32_t timeout_ms, int32_t *frames_ready,
+                     int32_t *done) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  auto r = find_ticket(e->impl, ticket);
+  if (!r)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: unknown ticket %lld", (long long)ticket);
+  std::unique_lock<std::mutex> lk(r->mu);
+  auto ready = [&] { return r->done || r->frames_ready > have_frames; };
+  if (timeout_ms < 0)
+    r->cv.wait(lk, ready);
+  else
+    r->cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), ready);
+  if (frames_ready)
+    *frames_ready = r->done && r->res.status == PTTS_OK && r->stream_frames == 0 ? r->res.n_frames : r->frames_ready;
+  if (done)
+    *done = r->done ? 1 : 0;
+  if (r->done && r->res.status != PTTS_OK) {
+    set_error("%s", r->err.c_str());
+    return r->res.status;
+  }
+  return PTTS_OK;
 }
 
 int ptts_ticket_release(ptts_engine *e, int64_t ticket) {

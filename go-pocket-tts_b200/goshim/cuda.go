@@ -46,6 +46,9 @@ type GenConfig struct {
 	EstimatedMaxSteps int
 	LSDDecodeSteps    int
 	FramesAfterEOS    int
+	// StreamFrames > 0 asks for frame-level delivery (PTTS_REQ_STREAM): PCM becomes valid in
+	// the ticket's buffer every StreamFrames latent frames; see Ticket.Read.
+	StreamFrames int
 }
 
 // VoiceLayer is one `transformer.layers.{i}.self_attn` module of an upstream
@@ -188,6 +191,10 @@ func (e *Engine) Submit(tokens []int64, voiceEmb []float32, voiceFrames int, voi
 	g.lsd_decode_steps = C.int32_t(cfg.LSDDecodeSteps)
 	g.frames_after_eos = C.int32_t(cfg.FramesAfterEOS)
 	g.force_eos_step = -1
+	if cfg.StreamFrames > 0 {
+		g.flags |= C.PTTS_REQ_STREAM
+		g.stream_frames = C.int32_t(cfg.StreamFrames)
+	}
 
 	t.pins.Pin(&tokens[0])
 	t.pins.Pin(&noise[0])
@@ -254,3 +261,20 @@ func (e *Engine) Wait(t *Ticket) ([]float32, int, error) {
 
 // Cancel evicts the request at the next step boundary.
 func (e *Engine) Cancel(t *Ticket) { C.ptts_cancel(e.h, t.id) }
+
+// Read blocks until more than have frames of PCM are valid (or the request is done) and returns the
+// new frame count; samples [have*1920, ready*1920) of the returned slice are the freshly decoded
+// audio.  This is what lets Service.SynthesizeStream (internal/tts/service.go:161-200) emit a
+// PCMChunk (internal/tts/runtime.go:33-38) per frame instead of per text chunk.
+func (e *Engine) Read(t *Ticket, have int) (pcm []float32, ready int, done bool, err error) {
+	var r, d C.int32_t
+	rc := C.ptts_ticket_read(e.h, t.id, C.int32_t(have), -1, &r, &d)
+	if rc == C.PTTS_ECANCELED {
+		return nil, have, true, ErrCanceled
+	} else if rc != 0 {
+		var buf [512]C.char
+		C.ptts_ticket_error(e.h, t.id, &buf[0], C.int32_t(len(buf)))
+		return nil, have, true, errors.New(C.GoString(&buf[0]))
+	}
+	return t.pcm[have*C.PTTS_SAMPLES_PER_FRAME : int(r)*C.PTTS_SAMPLES_PER_FRAME], int(r), d != 0, nil
+}

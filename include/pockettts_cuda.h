@@ -76,11 +76,19 @@ typedef struct {
                            EOS at this 0-based step (random-init weights have
                            no meaningful EOS logit)            */
   int32_t flags;          /* PTTS_REQ_* */
+  int32_t stream_frames;  /* PTTS_REQ_STREAM: emit PCM every this many latent frames (<= 0: 1) */
 } ptts_gen_cfg;
 
 #define PTTS_REQ_NO_PCM_D2H 1 /* leave PCM on the device (bench "value" leg) */
 #define PTTS_REQ_PCM16 2      /* pcm_out is int16_t[pcm_cap]: clamp(v,-1,1)*32767 truncated on the device
                                  (internal/audio/wav_stream.go:44-54), half the D2H bytes */
+
+#define PTTS_REQ_STREAM 4     /* frame-level streaming (reference PLAN.md:9-17, service.go:161-200,
+                                 tts/runtime.go:33-38 PCMChunk): while the AR loop of the request is still running,
+                                 every `stream_frames` new latent frames are decoded — only their receptive field,
+                                 the previous 33 frames, is re-run through Mimi — and their samples land in pcm_out
+                                 at their final position; ptts_ticket_read tells the caller how far the PCM is
+                                 valid.  The concatenation equals the whole-chunk decode (causal decoder). */
 
 /* Upstream voice model state for one transformer layer: the
  * `transformer.layers.{i}.self_attn/cache` tensor, layout [2,1,T,H,Dh] fp32
@@ -188,6 +196,12 @@ int ptts_ticket_latents(ptts_engine *e, int64_t ticket, float *latents,
  * which OS thread asks: a Go caller reads it after ptts_wait without runtime.LockOSThread
  * (errors of GenerateAudio, runtime_native_safetensors.go:91,173,214). */
 int ptts_ticket_error(ptts_engine *e, int64_t ticket, char *buf, int32_t cap);
+/* Drains a PTTS_REQ_STREAM request: blocks until more than `have_frames` frames of PCM are valid in
+ * the request's pcm_out (samples [0, 1920 * *frames_ready)), the request is complete, or timeout_ms
+ * (< 0: no timeout) has passed.  *done is set once every frame has been delivered (or the request
+ * failed: then the return value is its status and ptts_ticket_error has the text). */
+int ptts_ticket_read(ptts_engine *e, int64_t ticket, int32_t have_frames, int32_t timeout_ms,
+                     int32_t *frames_ready, int32_t *done);
 int ptts_ticket_release(ptts_engine *e, int64_t ticket);
 
 /* ---- multi-GPU pool: one process, one engine per device -------------------
@@ -218,6 +232,8 @@ int ptts_pool_wait(ptts_pool *p, int64_t ticket, ptts_result *result);
 int ptts_pool_cancel(ptts_pool *p, int64_t ticket);
 int ptts_pool_ticket_error(ptts_pool *p, int64_t ticket, char *buf, int32_t cap);
 int ptts_pool_ticket_latents(ptts_pool *p, int64_t ticket, float *latents, float *eos_logits, int32_t cap_frames);
+int ptts_pool_ticket_read(ptts_pool *p, int64_t ticket, int32_t have_frames, int32_t timeout_ms,
+                          int32_t *frames_ready, int32_t *done);
 int ptts_pool_ticket_release(ptts_pool *p, int64_t ticket);
 int ptts_pool_generate_audio(ptts_pool *p, const int64_t *tokens, int32_t n_tokens, const float *voice_emb,
                              int32_t voice_frames, const ptts_voice_kv *voice_kv, const ptts_gen_cfg *cfg,

@@ -1,0 +1,73 @@
+"""Frame-level streaming of scheduler requests (PTTS_REQ_STREAM + ptts_ticket_read): PCM is
+delivered while the AR loop is still running; the concatenated stream equals the whole-chunk decode of
+the same request (causal decoder), against the oracle too."""
+import numpy as np
+import pytest
+
+from conftest import allclose_ref, snr_db
+
+pytestmark = pytest.mark.gpu
+
+
+def _tokens(n, seed):
+    return np.random.default_rng(seed).integers(0, 4000, size=n).astype(np.int64)
+
+
+@pytest.mark.parametrize("stream_frames", [1, 3])
+def test_stream_equals_whole_chunk_and_oracle(small_rt, small_oracle, pkg, stream_frames):
+    toks = _tokens(13, 61)
+    n = 40  # > the small model's 18-frame receptive field: deliveries with a full window
+    noise = pkg.make_noise(n, 0.7, 62)
+    kw = dict(max_steps=n, eos_threshold=1e30, force_eos_step=33, frames_after_eos=3, noise=noise)
+    whole = small_rt.generate(toks, pkg.RuntimeGenerateConfig(**kw), want_latents=True)
+    p = small_rt.submit(toks, pkg.RuntimeGenerateConfig(stream_frames=stream_frames, **kw))
+    have, marks, pieces = 0, [], []
+    while True:
+        ready, done = small_rt.read(p, have)
+        assert ready >= have
+        if ready > have:
+            pieces.append(p.pcm[have * 1920: ready * 1920].copy())  # valid as soon as it is announced
+            marks.append(ready)
+            have = ready
+        if done:
+            break
+    got = small_rt.wait(p, want_latents=True)
+    assert got.n_frames == whole.n_frames == 37 and have == 37
+    assert len(marks) >= 37 // stream_frames  # really incremental, not one final delivery
+    np.testing.assert_array_equal(got.latents, whole.latents)
+    stream = np.concatenate(pieces)
+    assert stream.shape == whole.pcm.shape
+    assert snr_db(whole.pcm, stream) >= 60.0, snr_db(whole.pcm, stream)
+    np.testing.assert_array_equal(stream, got.pcm)
+    pcm, lat, _ = small_oracle.generate_audio(toks, **kw)
+    assert allclose_ref(got.latents, lat, 2e-4, 1e-3)
+    assert snr_db(pcm, stream) >= 40.0
+
+
+def test_stream_generator_among_batched_requests(small_rt, pkg):
+    """A streaming request batched with ordinary ones: everybody completes, the stream is contiguous."""
+    others = [small_rt.submit(_tokens(5 + i, 70 + i), pkg.RuntimeGenerateConfig(max_steps=12 + i, eos_threshold=1e30, seed=i))
+              for i in range(5)]
+    cfg = pkg.RuntimeGenerateConfig(max_steps=25, eos_threshold=1e30, seed=9, stream_frames=2)
+    chunks = list(small_rt.stream(_tokens(8, 80), cfg))
+    assert sum(c.size for c in chunks) == 25 * 1920 and len(chunks) >= 10
+    ref = small_rt.generate(_tokens(8, 80), pkg.RuntimeGenerateConfig(max_steps=25, eos_threshold=1e30, seed=9))
+    assert snr_db(ref.pcm, np.concatenate(chunks)) >= 60.0
+    for i, p in enumerate(others):
+        assert small_rt.wait(p).n_frames == 12 + i
+
+
+def test_stream_cancel_mid_flight(pkg, small_tensors):
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=256, max_frames=96,
+                               mimi_group_frames=96)
+    try:
+        p = rt.submit(_tokens(6, 3), pkg.RuntimeGenerateConfig(max_steps=90, eos_threshold=1e30, stream_frames=1))
+        ready, done = rt.read(p, 0)
+        assert ready >= 1 and not done
+        rt.cancel(p)
+        with pytest.raises(pkg.NativeCudaError) as ei:
+            rt.wait(p)
+        assert ei.value.status == pkg.PTTS_ECANCELED
+        assert rt.generate_audio(_tokens(4, 4), pkg.RuntimeGenerateConfig(max_steps=2, eos_threshold=1e30)).shape == (3840,)
+    finally:
+        rt.close()
