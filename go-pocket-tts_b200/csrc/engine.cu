@@ -90,7 +90,7 @@ Engine::~Engine() {
       cudaFreeHost(p);
   };
   fh(h_row_slot); fh(h_row_pos); fh(h_ids); fh(h_off_a); fh(h_off_b); fh(h_off_c);
-  fh(h_fused_err);
+  fh(h_fused_err); fh(h_fh_err);
   fh(h_eos); fh(h_lat); fh(h_stage); fh(h_mrow_pos); fh(h_mrow_frame0); fh(h_mmask); fh(h_moff);
   for (int i = 0; i < NPCM; i++) {
     fh(h_pcm_ring[i]);
@@ -1210,6 +1210,7 @@ int Engine::finalize() {
   CUDA_TRY(cudaMallocHost((void **)&h_moff, (size_t)mimi_frames_cap * 8));
 
   if ((rc = setup_fused())) return rc;
+  if ((rc = setup_flow_head())) return rc;
   host.clear(); // device copies are authoritative from here on
   finalized = true;
   return PTTS_OK;
@@ -1691,6 +1692,143 @@ int Engine::prefill(const std::vector<Seq *> &seqs, const std::vector<const int6
   return PTTS_OK;
 }
 
+// Parameter block of the persistent flow-head kernel: the phase list of ONE LSD step (the
+// reference's default, config.go LSDDecodeSteps = 1); more steps take the multi-kernel path.
+int Engine::setup_flow_head() {
+  fh_on = false;
+  // Opt-in (PTTS_FUSED_HEAD=1).  Measured on B200 (profiles/flow_head_r02.txt): at B = 256 the kernel takes
+  // ~380 us against ~200 us for the same head as 27 launches — 22 grid barriers (2.4 us each, plus the wait
+  // for the slowest CTA of every phase), GEMM phases without the cluster split-K the stand-alone kernel
+  // uses for these tiny shapes, and ~40 us of cooperative-launch overhead.  The multi-kernel head stays
+  // the default; the kernel is kept, parity-tested, for the follow-up (split-K inside a cluster launch).
+  if (!tc_on || !getenv("PTTS_FUSED_HEAD") || D != 1024 || C != 512 || ldim != 32 || ada_n != depth * 3 * C + 2 * C ||
+      2 + 3 * depth + 3 > FH_MAX_PHASES)
+    return PTTS_OK;
+  const int hid = rb[0].mlp0.out;
+  for (auto &b : rb)
+    if (b.mlp0.out != hid || b.mlp2.in != hid || hid % 64)
+      return PTTS_OK;
+  auto tw = [&](const float *w) -> const TcWeight * {
+    auto it = tc_map.find(w);
+    return it == tc_map.end() ? nullptr : it->second;
+  };
+  int rc;
+  // device copies of the TMA descriptors the kernel dereferences
+  auto dev_map = [&](const void *blob, const CUtensorMap **out) -> int {
+    void *d = nullptr;
+    int r = dmalloc(&d, 128);
+    if (r)
+      return r;
+    CUDA_TRY(cudaMemcpy(d, blob, 128, cudaMemcpyHostToDevice));
+    *out = static_cast<const CUtensorMap *>(d);
+    return PTTS_OK;
+  };
+  FhParams hp{};
+  hp.D = D; hp.C = C; hp.ldim = ldim; hp.ada_n = ada_n;
+  hp.debug = getenv("PTTS_FH_DEBUG") ? atoi(getenv("PTTS_FH_DEBUG")) : 0;
+  hp.x = x; hp.noise = fh_noise; hp.last = fh_last; hp.eos = fh_eos; hp.cur = fh_cur; hp.xf = fh_x; hp.ada = fh_ada;
+  hp.s_last = s_last.out(); hp.s_cur = s_cur.out(); hp.s_h = s_h.out();
+  hp.on_w = out_norm.w; hp.on_b = out_norm.b; hp.on_eps = out_norm.eps;
+  hp.eos_w = out_eos_lin.w; hp.eos_b = out_eos_bias;
+  hp.ip_w = input_proj.w; hp.ip_b = input_proj.b;
+  // cond_embed bias + (TE0(0) + TE1(1)) / 2 of the single Euler step
+  {
+    float *tv = nullptr;
+    if ((rc = get_tvec(1, &tv))) return rc;
+    std::vector<float> t((size_t)C), cb((size_t)C, 0.0f);
+    CUDA_TRY(cudaMemcpy(t.data(), tv, (size_t)C * 4, cudaMemcpyDeviceToHost));
+    if (cond_embed.b)
+      CUDA_TRY(cudaMemcpy(cb.data(), cond_embed.b, (size_t)C * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < C; i++)
+      cb[(size_t)i] += t[(size_t)i];
+    if ((rc = upload(cb, &fh_cond_bias))) return rc;
+  }
+  int np = 0;
+  bool ok = true;
+  auto add_gemm = [&](const float *w, const ActSplit &a, int N, int K, int bn, const GemmEpi &e) -> int {
+    const TcWeight *t = tw(w);
+    if (!t || !a.map) {
+      ok = false;
+      return PTTS_OK;
+    }
+    FhPhase &f = hp.phase[np++];
+    f.kind = FH_GEMM;
+    const void *blob = bn == 128 ? t->map128 : (bn == 64 ? t->map64 : t->map32);
+    int r;
+    if ((r = dev_map(blob, &f.g.wmap))) return r;
+    if ((r = dev_map(a.map, &f.g.amap))) return r;
+    f.g.n_rows_hi = t->N;
+    f.g.a_lo_row = (int)a.plane_rows;
+    f.g.N = N; f.g.K = K; f.g.bn = bn;
+    f.g.epi = e;
+    f.g.epi_kind = flow_head_epi_kind(e);
+    return PTTS_OK;
+  };
+  hp.phase[np++].kind = FH_ROWS_HEAD;
+  {
+    GemmEpi e;
+    e.bias = fh_cond_bias; e.act = ACT_SILU; e.Cs = s_sy.out();
+    if ((rc = add_gemm(cond_embed.w, s_last, C, D, 32, e))) return rc;
+  }
+  {
+    GemmEpi e;
+    e.bias = ada_all.b; e.C = fh_ada; e.ldc = ada_n;
+    if ((rc = add_gemm(ada_all.w, s_sy, ada_n, C, 128, e))) return rc;
+  }
+  for (int b = 0; b < depth && ok; b++) {
+    FhPhase &f = hp.phase[np++];
+    f.kind = FH_ROWS_LN;
+    f.ln_w = rb[b].in_ln.w; f.ln_b = rb[b].in_ln.b; f.ln_eps = rb[b].in_ln.eps;
+    f.shift_off = b * 3 * C; f.scale_off = b * 3 * C + C;
+    GemmEpi e0;
+    e0.bias = rb[b].mlp0.b; e0.act = ACT_SILU; e0.Cs = s_h2.out();
+    if ((rc = add_gemm(rb[b].mlp0.w, s_h, hid, C, 32, e0))) return rc;
+    GemmEpi e2;
+    e2.bias = rb[b].mlp2.b; e2.mul = fh_ada + (size_t)b * 3 * C + 2 * C; e2.ldmul = ada_n;
+    e2.residual = fh_x; e2.ldr = C; e2.C = fh_x; e2.ldc = C;
+    if ((rc = add_gemm(rb[b].mlp2.w, s_h2, C, hid, 32, e2))) return rc;
+  }
+  if (ok) {
+    FhPhase &f = hp.phase[np++];
+    f.kind = FH_ROWS_LN;
+    f.ln_w = nullptr; f.ln_b = nullptr; f.ln_eps = 1e-6f;
+    f.shift_off = depth * 3 * C; f.scale_off = depth * 3 * C + C;
+    GemmEpi e;
+    e.bias = final_linear.b; e.residual = fh_cur; e.ldr = ldim; e.C = fh_cur; e.ldc = ldim;
+    if ((rc = add_gemm(final_linear.w, s_h, ldim, C, 32, e))) return rc;
+  }
+  if (!ok)
+    return PTTS_OK; // some weight has no tensor-core copy: keep the multi-kernel head
+  hp.n_phases = np;
+  fh_grid = flow_head_grid();
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  if (fh_grid <= 0 || !coop)
+    return PTTS_OK;
+  if ((rc = dmalloc((void **)&d_fh_bar, FH_BARRIER_BYTES))) return rc;
+  if ((rc = dmalloc((void **)&d_fh_err, 256))) return rc;
+  CUDA_TRY(cudaMemset(d_fh_err, 0, 256));
+  CUDA_TRY(cudaMallocHost((void **)&h_fh_err, sizeof(int)));
+  *h_fh_err = 0;
+  hp.barrier = d_fh_bar;
+  hp.error = d_fh_err;
+  if ((rc = dmalloc((void **)&d_fh, sizeof(FhParams)))) return rc;
+  CUDA_TRY(cudaMemcpy(d_fh, &hp, sizeof(FhParams), cudaMemcpyHostToDevice));
+  fh_on = true;
+  return PTTS_OK;
+}
+
+int Engine::flow_head_fused(int B) {
+  const int n = flow_head_launch(d_fh, fh_grid, B, d_fh_bar, st);
+  if (n < 0) {
+    cudaGetLastError();
+    PTTS_FAIL(PTTS_ECUDA, "cuda: cooperative launch of the flow-head kernel failed");
+  }
+  times.kernel_launches += n;
+  fh_used = true;
+  return PTTS_OK;
+}
+
 // flow_lm.go:262-353: out_norm, EOS logit, LSD Euler decode with the flow net.
 // Input: x [B, D] (transformer output), fh_noise [B, ldim].  Output fh_cur.
 int Engine::flow_head(int B, int lsd_steps) {
@@ -1808,7 +1946,11 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     cudaEventRecord(ev[3], st);
   else if (capturing)
     cudaEventRecordWithFlags(ev[3], st, cudaEventRecordExternal);
-  rc = flow_head(Bp, lsd_steps);
+  // one LSD step (the default): the whole head is one persistent cooperative kernel
+  if (fh_on && lsd_steps == 1 && !prof_on && Bp >= tc_min_m)
+    rc = flow_head_fused(Bp);
+  else
+    rc = flow_head(Bp, lsd_steps);
   if (rc)
     return rc;
   PK("gather_scatter", 0, 0, scatter_rows(fh_cur, d_hist, d_off_b, Bp, ldim, st));
@@ -1922,6 +2064,9 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     timed = false; // no flow-head split inside the single kernel
     CUDA_TRY(cudaMemcpyAsync(h_fused_err, d_fused_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
+  const bool used_fh = fh_on && lsd_steps == 1 && !prof_on && Bp >= tc_min_m && !used_fused;
+  if (used_fh)
+    CUDA_TRY(cudaMemcpyAsync(h_fh_err, d_fh_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(h_eos, fh_eos, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (lat_out_host)
     CUDA_TRY(cudaMemcpyAsync(h_lat, fh_cur, (size_t)B * ldim * 4, cudaMemcpyDeviceToHost, st));
@@ -1939,6 +2084,15 @@ int Engine::step(const std::vector<Seq *> &seqs, const float *frames_in_host,
     fused_on = false; // fall back to the multi-kernel path from here on
     cudaMemset(d_fused_err, 0, sizeof(int));
     PTTS_FAIL(PTTS_ECUDA, "native-cuda: fused frame kernel: grid barrier timed out");
+  }
+  if (used_fh && *h_fh_err) {
+    fh_on = false; // the multi-kernel head from here on (graphs that embed the kernel are dropped)
+    cudaMemset(d_fh_err, 0, sizeof(int));
+    for (auto &kv : step_graphs)
+      if (kv.second.exec)
+        cudaGraphExecDestroy(kv.second.exec);
+    step_graphs.clear();
+    PTTS_FAIL(PTTS_ECUDA, "native-cuda: flow-head kernel: grid barrier timed out");
   }
   if (eos_out_host)
     memcpy(eos_out_host, h_eos, (size_t)B * 4);

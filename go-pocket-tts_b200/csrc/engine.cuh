@@ -4,6 +4,7 @@
 #include "../../include/pockettts_cuda.h"
 #include "kernels.cuh"
 #include "step_fused.cuh"
+#include "flow_head.cuh"
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -181,6 +182,16 @@ struct Engine {
   size_t fused_smem = 0;
   bool fused_on = false, fused_ll = true;
   int setup_fused();
+
+  // ---- persistent batched flow head (flow_head.cu): one cooperative kernel per frame ----
+  FhParams *d_fh = nullptr;
+  unsigned *d_fh_bar = nullptr;
+  int *d_fh_err = nullptr, *h_fh_err = nullptr;
+  float *fh_cond_bias = nullptr; // cond_embed bias + the (s,t) embedding of the single LSD step
+  int fh_grid = 0;
+  bool fh_on = false, fh_used = false;
+  int setup_flow_head();
+  int flow_head_fused(int B);
 
   // ---- split-K scratch for skinny GEMMs ----
   float *gemm_ws = nullptr;
