@@ -63,6 +63,7 @@ def parse_args():
                     help="ONE process drives --gpus devices through the in-process pool (ptts_pool_*: least-loaded "
                          "dispatch of one shared queue) instead of one torchrun rank per GPU")
     ap.add_argument("--max-batch", type=int, default=1024)
+    ap.add_argument("--mimi-group", type=int, default=2048, help="latent frames per batched Mimi decode workspace")
     ap.add_argument("--arch", default="full", choices=["full", "small"])
     ap.add_argument("--cpu-sample-frames", type=int, default=0,
                     help="cap on frames per chunk of the CPU sample (0 = whole chunks, the default: a cap keeps the "
@@ -256,10 +257,10 @@ def main():
     tensors = ck.make_checkpoint(arch)
     if args.pool:
         rt = pkg.NativeCudaPool(tensors=tensors, devices=list(range(args.gpus)), max_batch=args.max_batch,
-                                max_seq_tokens=512, max_frames=256, mimi_group_frames=2048)
+                                max_seq_tokens=512, max_frames=256, mimi_group_frames=args.mimi_group)
     else:
         rt = pkg.NativeCudaRuntime(tensors=tensors, device=local_rank, max_batch=args.max_batch, max_seq_tokens=512,
-                                   max_frames=256, mimi_group_frames=2048)
+                                   max_frames=256, mimi_group_frames=args.mimi_group)
     first_utt = 0 if args.pool else (sh.shard_range(rank, world, args.queue)[0] if args.queue > 0 else
                                      sh.shard_range(rank, world, args.utterances)[0])
     chunks = wl.make_workload(args.utterances, 5, 60, seed=7, first_utt=first_utt)
