@@ -355,6 +355,16 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      cudaStream_t st, SplitOut sp) {
   if (rows <= 0)
     return 0;
+  // tcgen05 formulation (attention_tc.cu: S and P.V in TMEM): parity-green, but its synchronous
+  // load -> MMA -> softmax -> MMA chain per key block makes it 18-22 % slower than the pipelined
+  // register-fragment kernel on B200 (171 vs 140 us for 1024 frames, profiles/README_r02.md), so it is
+  // opt-in until it is warp-specialised.
+  static const bool use_tc = getenv("PTTS_ATTN_TC") != nullptr;
+  if (use_tc && ctx > 0) {
+    const int n = attention_window_tc(qkv, ldq, out, ldo, rows, D, n_heads, row_pos, ctx, st, sp);
+    if (n > 0)
+      return n;
+  }
   static const bool no_mma = getenv("PTTS_ATTN_NO_MMA") != nullptr;
   if (!no_mma && ctx > 0) {
     const int n = attention_window_mma(qkv, ldq, out, ldo, rows, D, n_heads, row_pos, ctx, st, sp);

@@ -171,7 +171,12 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      int D, int n_heads, const int32_t *row_pos, int ctx,
                      cudaStream_t st, SplitOut sp = SplitOut());
 
-// Tensor-core version (attention_mma.cu: flash-style, split-bf16 mma.sync, head_dim 64);
+// tcgen05 version (attention_tc.cu: flash-style, S and P.V accumulators in TMEM, split-bf16 operands,
+// head_dim 64); returns 0 without launching when the shape is not supported.
+int attention_window_tc(const float *qkv, long ldq, float *out, long ldo, int rows, int D,
+                        int n_heads, const int32_t *row_pos, int ctx, cudaStream_t st,
+                        SplitOut sp = SplitOut());
+// Legacy tensor-core version (attention_mma.cu: flash-style, split-bf16 mma.sync, head_dim 64);
 // returns 0 without launching when the shape is not supported.
 int attention_window_mma(const float *qkv, long ldq, float *out, long ldo, int rows, int D,
                          int n_heads, const int32_t *row_pos, int ctx, cudaStream_t st,

@@ -659,3 +659,37 @@ def test_layernorm_folded_into_gemms_matches_oracle(pkg, small_tensors, small_or
             s_.close()
     finally:
         rt.close()
+
+
+def test_tcgen05_window_attention_matches_default_and_oracle(pkg, small_tensors, small_oracle, monkeypatch):
+    """PTTS_ATTN_TC=1: the Mimi window-250 attention with S and P.V accumulated in TMEM (attention_tc.cu,
+    K as K-major and V as MN-major B operands) against the oracle and the default kernel: ragged batch with
+    segments longer than the window."""
+    rng = np.random.default_rng(21)
+    sizes = [1, 20, 3, 33]  # 33 frames = 528 rows > 250: full windows, several key blocks
+    lat = rng.standard_normal((sum(sizes), 32)).astype(np.float32)
+    outs = {}
+    for mode in ("tc", "default"):
+        if mode == "tc":
+            monkeypatch.setenv("PTTS_ATTN_TC", "1")
+        else:
+            monkeypatch.delenv("PTTS_ATTN_TC", raising=False)
+        # the switch is read once per process by the dispatcher: a fresh interpreter keeps the two runs apart
+        import subprocess, sys, json, tempfile, os
+        code = (
+            "import sys, numpy as np; sys.path.insert(0, %r); import __graft_entry__ as ge, importlib;"
+            "pkg = ge.package(); ck = importlib.import_module('pockettts_b200.checkpoint');"
+            "rt = pkg.NativeCudaRuntime(tensors=ck.make_checkpoint(ck.ArchConfig.small(), seed=7), max_batch=4, max_seq_tokens=128,"
+            " max_frames=8, mimi_group_frames=128);"
+            "lat = np.load(sys.argv[1]); pcm = rt.decode_latents(lat, %r); np.save(sys.argv[2], pcm); rt.close()"
+        ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), sizes)
+        with tempfile.TemporaryDirectory() as td:
+            np.save(os.path.join(td, "lat.npy"), lat)
+            subprocess.run([sys.executable, "-c", code, os.path.join(td, "lat.npy"), os.path.join(td, "pcm.npy")], check=True)
+            outs[mode] = np.load(os.path.join(td, "pcm.npy"))
+    assert snr_db(outs["default"], outs["tc"]) >= 70.0
+    off = 0
+    for nfr in sizes:
+        want = small_oracle.decode_latents(lat[off:off + nfr])
+        assert snr_db(want, outs["tc"][off * 1920:(off + nfr) * 1920]) >= 40.0
+        off += nfr
