@@ -248,14 +248,24 @@ __global__ void __launch_bounds__(AM_THREADS)
     if (qa < rows) {
       if (out)
         *reinterpret_cast<float2 *>(out + (long)qa * ldo + col) = va;
-      if (sp.hi)
-        split_store2(sp, qa, col, va.x, va.y);
+      if (sp.hi) {
+        uint32_t hi, lo;
+        split2(va.x, va.y, hi, lo);
+        uint16_t *p = sp.hi + (long)qa * sp.ld + col;
+        *reinterpret_cast<uint32_t *>(p) = hi;
+        *reinterpret_cast<uint32_t *>(p + sp.lo_off) = lo;
+      }
     }
     if (qb < rows) {
       if (out)
         *reinterpret_cast<float2 *>(out + (long)qb * ldo + col) = vb;
-      if (sp.hi)
-        split_store2(sp, qb, col, vb.x, vb.y);
+      if (sp.hi) {
+        uint32_t hi, lo;
+        split2(vb.x, vb.y, hi, lo);
+        uint16_t *p = sp.hi + (long)qb * sp.ld + col;
+        *reinterpret_cast<uint32_t *>(p) = hi;
+        *reinterpret_cast<uint32_t *>(p + sp.lo_off) = lo;
+      }
     }
   }
 }

@@ -204,47 +204,15 @@ static inline float bf16_to_f32(uint16_t h) {
 
 // Splits W [N,K] fp32 into bf16 hi rows [0,N) and lo rows [N,2N) (x ~= hi + lo,
 // ~16 mantissa bits), uploads it and builds the TMA descriptors.
-static inline uint16_t f32_to_f16_rn(float x) { // round to nearest even, overflow -> inf, subnormals kept
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  const uint32_t sign = (u >> 16) & 0x8000u;
-  const int32_t exp = (int32_t)((u >> 23) & 0xFF) - 127 + 15;
-  uint32_t man = u & 0x7FFFFFu;
-  if (((u >> 23) & 0xFF) == 0xFF)
-    return (uint16_t)(sign | 0x7C00u | (man ? 0x200u : 0));
-  if (exp >= 31)
-    return (uint16_t)(sign | 0x7C00u);
-  if (exp <= 0) {
-    if (exp < -10)
-      return (uint16_t)sign;
-    man |= 0x800000u;
-    const int shift = 14 - exp; // 13 + (1 - exp)
-    uint32_t h = man >> shift;
-    const uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
-    if (rem > halfway || (rem == halfway && (h & 1)))
-      h++;
-    return (uint16_t)(sign | h);
-  }
-  uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
-  const uint32_t rem = man & 0x1FFFu;
-  if (rem > 0x1000u || (rem == 0x1000u && (h & 1)))
-    h++; // may carry into the exponent (and to inf): still the correctly rounded value
-  return (uint16_t)(sign | h);
-}
-
-int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, int K, bool single) {
+int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, int K) {
   if (!tc_on || K % 8 != 0 || N % 16 != 0 || K < 32 || N < 32)
     return PTTS_OK; // stays on the CUDA-core path
-  std::vector<uint16_t> sp((size_t)(single ? 1 : 2) * N * K);
-  if (single) {
-    for (size_t i = 0; i < (size_t)N * K; i++)
-      sp[i] = f32_to_f16_rn(w[i]);
-  } else
-    for (size_t i = 0; i < (size_t)N * K; i++) {
-      uint16_t h = f32_to_bf16_rn(w[i]);
-      sp[i] = h;
-      sp[(size_t)N * K + i] = f32_to_bf16_rn(w[i] - bf16_to_f32(h));
-    }
+  std::vector<uint16_t> sp((size_t)2 * N * K);
+  for (size_t i = 0; i < (size_t)N * K; i++) {
+    uint16_t h = f32_to_bf16_rn(w[i]);
+    sp[i] = h;
+    sp[(size_t)N * K + i] = f32_to_bf16_rn(w[i] - bf16_to_f32(h));
+  }
   void *d = nullptr;
   int rc = dmalloc(&d, sp.size() * 2);
   if (rc)
@@ -252,20 +220,19 @@ int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, i
   CUDA_TRY(cudaMemcpy(d, sp.data(), sp.size() * 2, cudaMemcpyHostToDevice));
   TcWeight *t = new TcWeight();
   tc_owned.push_back(t);
-  int r = tc_weight_init(t, d, N, K, single ? 1 : 2);
+  int r = tc_weight_init(t, d, N, K);
   if (r)
     PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed (%d) for a [%d,%d] weight", r, N, K);
   tc_map[d_w_fp32] = t;
   return PTTS_OK;
 }
 
-int Engine::make_act(ActSplit &a, long rows_cap, int K, int lead, bool single) {
+int Engine::make_act(ActSplit &a, long rows_cap, int K, int lead) {
   a.rows_cap = rows_cap;
   a.K = K;
   a.lead = lead;
-  a.single = single;
   a.plane_rows = rows_cap + lead;
-  const size_t elems = (size_t)(single ? 1 : 2) * a.plane_rows * K;
+  const size_t elems = (size_t)2 * a.plane_rows * K;
   int rc = dmalloc((void **)&a.base, elems * 2);
   if (rc)
     return rc;
@@ -275,7 +242,7 @@ int Engine::make_act(ActSplit &a, long rows_cap, int K, int lead, bool single) {
     return PTTS_OK;
   a.map = aligned_alloc(64, 128);
   host_maps.push_back(a.map);
-  if (tc_act_map_init(a.map, a.p, single ? rows_cap : a.plane_rows + rows_cap, K, 0, 0))
+  if (tc_act_map_init(a.map, a.p, a.plane_rows + rows_cap, K, 0, 0))
     PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed for a [%ld,%d] activation", rows_cap, K);
   return PTTS_OK;
 }
@@ -289,8 +256,7 @@ int Engine::make_conv_map(const ActSplit &a, int cin, int taps, void **out) {
   void *m = aligned_alloc(64, 128);
   host_maps.push_back(m);
   // row m, tap t -> plane row m - (taps-1) + t
-  if (tc_act_map_init(m, a.p - (size_t)(taps - 1) * cin, (a.single ? 0 : a.plane_rows) + a.rows_cap + taps - 1, cin * taps, cin,
-                      taps))
+  if (tc_act_map_init(m, a.p - (size_t)(taps - 1) * cin, a.plane_rows + a.rows_cap + taps - 1, cin * taps, cin, taps))
     PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed for a conv map (cin %d, taps %d)", cin, taps);
   *out = m;
   return PTTS_OK;
@@ -672,7 +638,7 @@ struct Loader {
   }
   bool has(const std::string &k) { return get(k) != nullptr; }
   // internal/native/linear.go:19-49 (loadLinear)
-  int linear(const std::string &name, bool with_bias, DLinear *l, bool defer_tc = false, bool single = false) {
+  int linear(const std::string &name, bool with_bias, DLinear *l, bool defer_tc = false) {
     const HostTensor *w = get(name + ".weight");
     if (!w)
       PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", name.c_str());
@@ -684,7 +650,7 @@ struct Loader {
     if (rc)
       return rc;
     if (!(defer_tc && e->tc_on)) // FlowLM in_proj / linear1: the tensor-core copy is the LayerNorm-folded one
-      if ((rc = e->make_tc(l->w, w->data, l->out, l->in, single)))
+      if ((rc = e->make_tc(l->w, w->data, l->out, l->in)))
         return rc;
     l->b = nullptr;
     if (with_bias) {
@@ -743,11 +709,10 @@ struct Loader {
     if ((rc = lnorm(p + ".norm1", 1e-5f, &l->n1))) return rc;
     if ((rc = lnorm(p + ".norm2", 1e-5f, &l->n2))) return rc;
     const bool fold = !mimi && e->tc_on && e->ln_fold_on;
-    const bool sg = mimi && e->mimi_f16; // Mimi transformer: one fp16 operand plane
-    if ((rc = linear(p + ".self_attn.in_proj", false, &l->in_proj, fold, sg))) return rc;
-    if ((rc = linear(p + ".self_attn.out_proj", false, &l->out_proj, false, sg))) return rc;
-    if ((rc = linear(p + ".linear1", false, &l->l1, fold, sg))) return rc;
-    if ((rc = linear(p + ".linear2", false, &l->l2, false, sg))) return rc;
+    if ((rc = linear(p + ".self_attn.in_proj", false, &l->in_proj, fold))) return rc;
+    if ((rc = linear(p + ".self_attn.out_proj", false, &l->out_proj))) return rc;
+    if ((rc = linear(p + ".linear1", false, &l->l1, fold))) return rc;
+    if ((rc = linear(p + ".linear2", false, &l->l2))) return rc;
     if (fold) {
       if (l->n1.d != l->in_proj.in || l->n2.d != l->l1.in)
         PTTS_FAIL(PTTS_EINVAL, "native-cuda: transformer layer norm / linear widths differ");
@@ -765,7 +730,7 @@ struct Loader {
   }
   // Conv1d [Cout,Cin,k] -> GEMM weight [Cout, k*Cin] (tap-major K so that the
   // A row of output t is the contiguous channels-last span t-k+1..t).
-  int conv(const std::string &p, DConvG *c, bool single = false) {
+  int conv(const std::string &p, DConvG *c) {
     const HostTensor *w = get(p + ".weight");
     if (!w)
       PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", p.c_str());
@@ -782,7 +747,7 @@ struct Loader {
     int rc = e->upload(wp, &c->w);
     if (rc)
       return rc;
-    if ((rc = e->make_tc(c->w, wp, c->N, c->K, single)))
+    if ((rc = e->make_tc(c->w, wp, c->N, c->K)))
       return rc;
     c->b = nullptr;
     if (const HostTensor *b = get(p + ".bias"))
@@ -792,7 +757,7 @@ struct Loader {
   }
   // ConvTranspose1d [Cin,Cout,k], stride s, right trim k-s -> s phase GEMMs
   // stacked along N: W[(r*Cout+oc), (j*Cin+ic)] = w[ic][oc][r + s*(J-1-j)].
-  int convtr(const std::string &p, int stride, DConvG *c, bool single = false) {
+  int convtr(const std::string &p, int stride, DConvG *c) {
     const HostTensor *w = get(p + ".weight");
     if (!w)
       PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", p.c_str());
@@ -816,7 +781,7 @@ struct Loader {
     int rc = e->upload(wp, &c->w);
     if (rc)
       return rc;
-    if ((rc = e->make_tc(c->w, wp, c->N, c->K, single)))
+    if ((rc = e->make_tc(c->w, wp, c->N, c->K)))
       return rc;
     c->b = nullptr;
     if (const HostTensor *b = get(p + ".bias")) {
@@ -856,10 +821,6 @@ int Engine::finalize() {
   // >= 128-column tiles forced on the producers cost more than the LayerNorm kernels saved
   // (B = 256: 952 vs 909 us per frame, B = 1024: 2133 vs 1831; profiles/README_r02.md).
   ln_fold_on = getenv("PTTS_LN_FOLD") != nullptr;
-  // Opt-in (PTTS_MIMI_F16=1): measured on B200 the decode gets 8 % faster (5.59 vs 6.08 ms for 2048 frames)
-  // while the PCM drops from ~90 dB to ~60 dB SNR against the oracle and leaves the reference's own
-  // mimi_decode tolerance (abs 2e-4 / rel 5e-2, scripts/dump_python_parity.py) — not worth it by default.
-  mimi_f16 = tc_on && getenv("PTTS_MIMI_F16") != nullptr;
   Loader ld{this};
   int rc;
   // ---- FlowLM (flow_lm.go:51-119) ----
@@ -1036,9 +997,7 @@ int Engine::finalize() {
     if ((rc = upload(c, &mrope_cos))) return rc;
     if ((rc = upload(s, &mrope_sin))) return rc;
   }
-  // one fp16 operand plane for the tensor-bound head of the decoder (transformer, init conv, stage 1, second
-  // up-conv); stages 2 and 3 are HBM-bound and keep the split-bf16 planes their fused kernels read
-  if ((rc = ld.conv("mimi.decoder.model.0.conv", &init_conv, mimi_f16))) return rc;
+  if ((rc = ld.conv("mimi.decoder.model.0.conv", &init_conv))) return rc;
   const int strides[3] = {6, 5, 4};
   const char *upk[3] = {"2", "5", "8"};
   const char *rsk[3] = {"3", "6", "9"};
@@ -1047,12 +1006,12 @@ int Engine::finalize() {
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: seanet init conv expects %d input channels", Md);
   for (int s = 0; s < 3; s++) {
     std::string base = "mimi.decoder.model.";
-    if ((rc = ld.convtr(base + upk[s] + ".convtr", strides[s], &up[s], mimi_f16 && s <= 1))) return rc;
+    if ((rc = ld.convtr(base + upk[s] + ".convtr", strides[s], &up[s]))) return rc;
     if (up[s].cin != ch)
       PTTS_FAIL(PTTS_EINVAL, "native-cuda: seanet stage %d channel mismatch", s);
     ch = up[s].cout;
-    if ((rc = ld.conv(base + rsk[s] + ".block.1.conv", &res1[s], mimi_f16 && s == 0))) return rc;
-    if ((rc = ld.conv(base + rsk[s] + ".block.3.conv", &res2[s], mimi_f16 && s == 0))) return rc;
+    if ((rc = ld.conv(base + rsk[s] + ".block.1.conv", &res1[s]))) return rc;
+    if ((rc = ld.conv(base + rsk[s] + ".block.3.conv", &res2[s]))) return rc;
     if (res1[s].cin != ch || res2[s].cout != ch || res2[s].cin != res1[s].cout)
       PTTS_FAIL(PTTS_EINVAL, "native-cuda: seanet res block %d channel mismatch", s);
   }
@@ -1260,20 +1219,19 @@ int Engine::finalize() {
     // in front = the causal left context of the first segment)
     const int lead = 8;
     if ((rc = make_act(sm_latin, mimi_frames_cap, ldim, 0))) return rc;
-    const bool sg = mimi_f16;
-    if ((rc = make_act(sm_nrm, Rb, Md, lead, sg))) return rc;
-    if ((rc = make_act(sm_att, Rb, Md, lead, sg))) return rc;
-    if ((rc = make_act(sm_ff, Rb, MF, lead, sg))) return rc;
-    if ((rc = make_act(sm_x, Rb, Md, lead, sg))) return rc;
-    if ((rc = make_act(sm_y0e, Rb, init_conv.cout, lead, sg))) return rc;
+    if ((rc = make_act(sm_nrm, Rb, Md, lead))) return rc;
+    if ((rc = make_act(sm_att, Rb, Md, lead))) return rc;
+    if ((rc = make_act(sm_ff, Rb, MF, lead))) return rc;
+    if ((rc = make_act(sm_x, Rb, Md, lead))) return rc;
+    if ((rc = make_act(sm_y0e, Rb, init_conv.cout, lead))) return rc;
     if ((rc = make_conv_map(sm_x, init_conv.cin, init_conv.taps, &init_conv.amap))) return rc;
     size_t r2 = Rb;
     for (int s = 0; s < 3; s++) {
       const ActSplit &src = s == 0 ? sm_y0e : sm_ye[s - 1];
       if ((rc = make_conv_map(src, up[s].cin, up[s].taps, &up[s].amap))) return rc;
       r2 *= (size_t)up[s].stride;
-      if ((rc = make_act(sm_ye[s], r2, up[s].cout, lead, sg && s == 0))) return rc;
-      if ((rc = make_act(sm_he[s], r2, res1[s].cout, lead, sg && s == 0))) return rc;
+      if ((rc = make_act(sm_ye[s], r2, up[s].cout, lead))) return rc;
+      if ((rc = make_act(sm_he[s], r2, res1[s].cout, lead))) return rc;
       if ((rc = make_conv_map(sm_ye[s], res1[s].cin, res1[s].taps, &res1[s].amap))) return rc;
       if (res2[s].taps != 1)
         if ((rc = make_conv_map(sm_he[s], res2[s].cin, res2[s].taps, &res2[s].amap))) return rc;

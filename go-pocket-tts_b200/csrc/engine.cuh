@@ -75,13 +75,12 @@ struct ActSplit {
   uint16_t *base = nullptr, *p = nullptr; // allocation / hi plane row 0
   long plane_rows = 0, rows_cap = 0;
   int K = 0, lead = 0;
-  bool single = false; // one fp16 plane instead of bf16 hi + lo
   void *map = nullptr; // CUtensorMap over {K, rows}: dense A (row stride K)
   SplitOut out() const {
     SplitOut o;
     o.hi = p;
     o.ld = K;
-    o.lo_off = single ? 0 : plane_rows * (long)K;
+    o.lo_off = plane_rows * (long)K;
     return o;
   }
 };
@@ -153,11 +152,7 @@ struct Engine {
   int tc_min_m = 9; // M <= 8 stays on the weight-streaming GEMV
   std::unordered_map<const float *, TcWeight *> tc_map;
   std::vector<TcWeight *> tc_owned;
-  int make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, int K, bool single = false);
-  // Mimi's tensor-bound GEMMs (decoder transformer, init conv, first up-conv, stage-1 residual block, second
-  // up-conv) can run on ONE fp16 operand plane instead of bf16 hi + lo: a third of the MMAs, half the
-  // operand bytes.  Opt-in (PTTS_MIMI_F16=1): see Engine::finalize for the measured trade.
-  bool mimi_f16 = false;
+  int make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, int K);
   int debug_gemm(const float *A, int M, int K, const float *W, int N, const float *bias, int act,
                  int path, float *C);
   int debug_gemm_bench(int M, int K, int N, int lda, int path, int reps, float *avg_us);
@@ -177,7 +172,7 @@ struct Engine {
   ActSplit sm_yf[3];
   void *up_alt_amap[3] = {nullptr, nullptr, nullptr};
   std::vector<void *> host_maps;
-  int make_act(ActSplit &a, long rows_cap, int K, int lead, bool single = false);
+  int make_act(ActSplit &a, long rows_cap, int K, int lead);
   // conv form of an activation's map: {cin, taps, rows} over the same planes
   int make_conv_map(const ActSplit &a, int cin, int taps, void **out);
   void use_act(GemmArgs &g, const ActSplit &a) const {

@@ -74,8 +74,6 @@ struct GemmArgs {
   // overlapping rows, map dims {cin, taps, rows}, k = tap * cin + c.
   const void *amap = nullptr;
   int a_lo_row = 0, a_cin = 0;
-  // 1: single-plane fp16 operands (A behind amap and the weight): one MMA per k-step, no lo tiles
-  int single = 0;
   // optional timeline of CTA 0 (globaltimer ns; tools only)
   unsigned long long *dbg = nullptr;
 };
@@ -93,9 +91,8 @@ struct alignas(64) TcWeight {
   unsigned char map32[128], map64[128], map128[128], map256[128];
   const void *d_split = nullptr;
   int N = 0, K = 0;
-  int planes = 2; // 2: bf16 hi rows then lo rows [2N, K]; 1: one fp16 plane [N, K]
 };
-int tc_weight_init(TcWeight *w, const void *d_split, int N, int K, int planes = 2);
+int tc_weight_init(TcWeight *w, const void *d_split, int N, int K);
 // TMA map (128-byte blob, 64-byte aligned) over split activation planes: `base` points at
 // hi row 0, rows_total rows of K bf16 (hi plane then lo plane).  cin > 0 builds the 3-D
 // overlapping-row form {cin, taps, rows} for an implicit-GEMM conv (row stride cin).

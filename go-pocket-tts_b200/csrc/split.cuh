@@ -4,7 +4,6 @@
 // write the two planes directly so the GEMM can fetch both operands with TMA.
 #pragma once
 #include "kernels.cuh"
-#include <cuda_fp16.h>
 
 namespace ptts {
 
@@ -20,19 +19,8 @@ __device__ __forceinline__ void split8(const float4 &u, const float4 &v, uint4 &
   split2(v.x, v.y, hi.z, lo.z);
   split2(v.z, v.w, hi.w, lo.w);
 }
-// Single-plane mode (SplitOut::lo_off == 0): the Mimi decoder's tensor-bound GEMMs take ONE fp16 operand
-// plane (11 mantissa bits, one MMA per k-step instead of three): the decoder is feed-forward, its error
-// does not compound, and the waveform bar is 40 dB.  Same 2-byte elements, same TMA maps.
-__device__ __forceinline__ uint32_t pack_half2(float x0, float x1) {
-  const __half2 h = __floats2half2_rn(x0, x1); // x0 in the low half
-  return *reinterpret_cast<const uint32_t *>(&h);
-}
 // Four consecutive columns (col % 4 == 0) of row `row` into both planes.
 __device__ __forceinline__ void split_store4(const SplitOut &s, long row, long col, const float4 &v) {
-  if (s.lo_off == 0) {
-    *reinterpret_cast<uint2 *>(s.hi + row * s.ld + col) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
-    return;
-  }
   uint2 hi, lo;
   split2(v.x, v.y, hi.x, lo.x);
   split2(v.z, v.w, hi.y, lo.y);
@@ -40,24 +28,7 @@ __device__ __forceinline__ void split_store4(const SplitOut &s, long row, long c
   *reinterpret_cast<uint2 *>(p) = hi;
   *reinterpret_cast<uint2 *>(p + s.lo_off) = lo;
 }
-// Two consecutive columns (col % 2 == 0).
-__device__ __forceinline__ void split_store2(const SplitOut &s, long row, long col, float x0, float x1) {
-  uint16_t *p = s.hi + row * s.ld + col;
-  if (s.lo_off == 0) {
-    *reinterpret_cast<uint32_t *>(p) = pack_half2(x0, x1);
-    return;
-  }
-  uint32_t hi, lo;
-  split2(x0, x1, hi, lo);
-  *reinterpret_cast<uint32_t *>(p) = hi;
-  *reinterpret_cast<uint32_t *>(p + s.lo_off) = lo;
-}
 __device__ __forceinline__ void split_store1(const SplitOut &s, long row, long col, float v) {
-  if (s.lo_off == 0) {
-    const __half h = __float2half_rn(v);
-    s.hi[row * s.ld + col] = *reinterpret_cast<const uint16_t *>(&h);
-    return;
-  }
   uint32_t hi, lo;
   split2(v, 0.0f, hi, lo);
   uint16_t *p = s.hi + row * s.ld + col;

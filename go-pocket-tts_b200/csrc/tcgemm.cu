@@ -160,12 +160,10 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
         if (g.a_cin > 0) { // conv over overlapping rows: k = tap * cin + c
           const int tap = k0 / g.a_cin, c0 = k0 - tap * g.a_cin;
           tma_load_3d(st, &amap, &full[s], c0, tap, m0);
-          if (!g.single)
-            tma_load_3d(st + SM::A_TILE, &amap, &full[s], c0, tap, g.a_lo_row + m0);
+          tma_load_3d(st + SM::A_TILE, &amap, &full[s], c0, tap, g.a_lo_row + m0);
         } else {
           tma_load_2d(st, &amap, &full[s], k0, m0);
-          if (!g.single)
-            tma_load_2d(st + SM::A_TILE, &amap, &full[s], k0, g.a_lo_row + m0);
+          tma_load_2d(st + SM::A_TILE, &amap, &full[s], k0, g.a_lo_row + m0);
         }
       };
       auto dep_wait = [&]() {
@@ -189,7 +187,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
           uint8_t *st = smem + s * SM::STAGE;
           if (it < 32)
             TC_STAMP(96 + it);
-          mbar_arrive_expect_tx(&full[s], g.single ? SM::W_TILE + SM::A_TILE : 2 * SM::W_TILE + (ATMA ? 2 * SM::A_TILE : 0));
+          mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE + (ATMA ? 2 * SM::A_TILE : 0));
           const int k0 = (kb_begin + kb) * TC_BK;
           if (ATMA) {
             if (waited)
@@ -202,8 +200,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             }
           }
           tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], k0, n0);
-          if (!g.single)
-            tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], k0, n_rows_hi + n0);
+          tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], k0, n_rows_hi + n0);
         }
       }
       if (!waited)
@@ -212,8 +209,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = g.single ? make_idesc_f16(BN) : make_idesc(BN);
-      const bool single = g.single != 0;
+      constexpr uint32_t idesc = make_idesc(BN);
       long it = 0, li = 0;
       for (long i = blockIdx.x; i < items.total; i += gridDim.x, li++) {
         int m0, n0, kb_begin, nkb, z;
@@ -240,13 +236,9 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             const uint32_t ko = k * 32; // 16 bf16 = 32 bytes along the swizzled row
             const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
             const uint64_t dwh = make_smem_desc(w_hi + ko), dwl = make_smem_desc(w_lo + ko);
-            if (single) { // one fp16 plane per operand: one product
-              umma_bf16(tmem_d, dah, dwh, idesc, (kb | k) != 0);
-            } else {
-              umma_bf16(tmem_d, dal, dwh, idesc, (kb | k) != 0);
-              umma_bf16(tmem_d, dah, dwl, idesc, 1);
-              umma_bf16(tmem_d, dah, dwh, idesc, 1);
-            }
+            umma_bf16(tmem_d, dal, dwh, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, dah, dwl, idesc, 1);
+            umma_bf16(tmem_d, dah, dwh, idesc, 1);
           }
           umma_commit(&empty[s]); // frees the smem stage once these MMAs have read it
         }
@@ -947,11 +939,11 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
             tiles <= tc_cluster_capacity(b, s)))
         continue; // folded LayerNorm: split-K only through a cluster
       const long per_cta = (items + sms - 1) / sms; // items a CTA runs back to back
-      const double kb_bytes = (128.0 + b) * (g.single ? 128.0 : 256.0); // one fp16 plane or hi + lo
+      const double kb_bytes = (128.0 + b) * 256.0;
       double t_kb = !atma ? 1.3 : (b == 256 ? 1.3 : 0.58);
       if (kb_bytes / 95e3 > t_kb)
         t_kb = kb_bytes / 95e3;
-      const double t_mma = 128.0 * b * 64.0 * (g.single ? 2.0 : 6.0) / 9.0e6; // ~9 TFLOP/s issued per SM
+      const double t_mma = 128.0 * b * 64.0 * 6.0 / 9.0e6; // ~9 TFLOP/s issued per SM
       if (t_mma > t_kb)
         t_kb = t_mma;
       const double t_loop = t_kb * kb_per;
@@ -980,18 +972,17 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
 
 // Builds the three TMA descriptors (box 64 x {32,64,128}) over the split weight
 // matrix [2N, K] bf16.  Returns 0 on success.
-int tc_weight_init(TcWeight *w, const void *d_split, int N, int K, int planes) {
+int tc_weight_init(TcWeight *w, const void *d_split, int N, int K) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc)
     return -1;
   w->d_split = d_split;
   w->N = N;
   w->K = K;
-  w->planes = planes;
   const int boxes[4] = {32, 64, 128, 256};
   void *maps[4] = {w->map32, w->map64, w->map128, w->map256};
   for (int i = 0; i < 4; i++) {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)((cuuint64_t)planes * (cuuint64_t)N)};
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)(2 * (cuuint64_t)N)};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)boxes[i]};
     cuuint32_t estr[2] = {1, 1};
@@ -1043,11 +1034,7 @@ bool tc_gemm_supported(const GemmArgs &g) {
   return g.A != nullptr && g.lda % 4 == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
 }
 
-int tc_gemm(const TcWeight &w, const GemmArgs &g0, cudaStream_t st, const char **variant) {
-  GemmArgs g = g0;
-  g.single = w.planes == 1 ? 1 : 0; // the A planes behind amap are in the weight's format (engine invariant)
-  if (g.single && !g.amap)
-    return -1;
+int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **variant) {
   int bn, S;
   choose_tile(g, bn, S);
   static const bool no_ew8 = getenv("PTTS_TC_NO_EW8") != nullptr;
