@@ -88,13 +88,14 @@ def load_peaks():
 
 def load_ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel classes captured
-    with `ncu --set full`; profiles/ncu_traffic_r01.json records the command and the launches averaged."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    if not os.path.exists(p):
-        return {}
-    with open(p) as f:
-        d = json.load(f)
-    return {k: v for k, v in d.get("classes", {}).items()}
+    with `ncu --set full`; profiles/ncu_traffic_r0N.json record the commands and the launches averaged."""
+    out = {}
+    for name in ("ncu_traffic_r01.json", "ncu_traffic_r02.json"):  # later rounds override per class
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                out.update(json.load(f).get("classes", {}))
+    return out
 
 
 class ClockSampler:
