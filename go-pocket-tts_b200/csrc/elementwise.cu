@@ -136,38 +136,6 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// One warp per row: split planes of the raw row + (sum, sum^2) for the GEMM that has the LayerNorm folded in.
-__global__ void __launch_bounds__(128)
-    split_stats_rows_kernel(const float *x, int rows, int D, SplitOut sp, float *stats, int slots) {
-  PDL_TRIGGER();
-  PDL_WAIT();
-  const int lane = threadIdx.x & 31;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= rows)
-    return;
-  const float *xr = x + (long)row * D;
-  float s1 = 0.0f, s2 = 0.0f;
-  for (int i = lane * 4; i < D; i += 128) {
-    const float4 v = *reinterpret_cast<const float4 *>(xr + i);
-    split_store4(sp, row, i, v);
-    s1 += (v.x + v.y) + (v.z + v.w);
-    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane < slots)
-    reinterpret_cast<float2 *>(stats)[(long)row * slots + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
-}
-int split_stats_rows(const float *x, int rows, int D, SplitOut sp, float *stats, int slots, cudaStream_t st) {
-  if (rows <= 0)
-    return 0;
-  launch_k(split_stats_rows_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, x, rows, D, sp, stats, slots);
-  return 1;
-}
-
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int layernorm(const float *x, long ldx, float *out, long ldo, int rows, int D,

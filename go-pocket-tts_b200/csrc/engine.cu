@@ -638,7 +638,7 @@ struct Loader {
   }
   bool has(const std::string &k) { return get(k) != nullptr; }
   // internal/native/linear.go:19-49 (loadLinear)
-  int linear(const std::string &name, bool with_bias, DLinear *l, bool defer_tc = false) {
+  int linear(const std::string &name, bool with_bias, DLinear *l) {
     const HostTensor *w = get(name + ".weight");
     if (!w)
       PTTS_FAIL(PTTS_EINVAL, "native: tensor %s.weight not found", name.c_str());
@@ -649,9 +649,8 @@ struct Loader {
     int rc = e->upload(w->data, &l->w);
     if (rc)
       return rc;
-    if (!(defer_tc && e->tc_on)) // FlowLM in_proj / linear1: the tensor-core copy is the LayerNorm-folded one
-      if ((rc = e->make_tc(l->w, w->data, l->out, l->in)))
-        return rc;
+    if ((rc = e->make_tc(l->w, w->data, l->out, l->in)))
+      return rc;
     l->b = nullptr;
     if (with_bias) {
       const HostTensor *b = get(name + ".bias");
@@ -680,46 +679,14 @@ struct Loader {
       return rc;
     return e->upload(b->data, &ln->b);
   }
-  // The tensor-core copy of a Linear that follows a LayerNorm holds W diag(g) (g = norm.weight); its
-  // epilogue needs c1[n] = sum_k W[n,k] g[k] and c2[n] = sum_k W[n,k] beta[k] (GemmEpi::ln_stats).
-  int fold_norm(const std::string &lin, const std::string &norm, DLinear *l, float **c1, float **c2) {
-    const HostTensor *w = get(lin + ".weight"), *g = get(norm + ".weight"), *b = get(norm + ".bias");
-    const int N = l->out, K = l->in;
-    std::vector<float> wf((size_t)N * K), v1((size_t)N), v2((size_t)N);
-    for (int n = 0; n < N; n++) {
-      double a1 = 0, a2 = 0;
-      for (int k = 0; k < K; k++) {
-        const float ws = w->data[(size_t)n * K + k] * g->data[(size_t)k];
-        wf[(size_t)n * K + k] = ws;
-        a1 += (double)ws;
-        a2 += (double)w->data[(size_t)n * K + k] * (double)b->data[(size_t)k];
-      }
-      v1[(size_t)n] = (float)a1;
-      v2[(size_t)n] = (float)a2;
-    }
-    int rc = e->make_tc(l->w, wf, N, K); // replaces the plain copy made by linear() under the same key
-    if (rc)
-      return rc;
-    if ((rc = e->upload(v1, c1)))
-      return rc;
-    return e->upload(v2, c2);
-  }
   int tlayer(const std::string &p, bool mimi, DTLayer *l) {
     int rc;
     if ((rc = lnorm(p + ".norm1", 1e-5f, &l->n1))) return rc;
     if ((rc = lnorm(p + ".norm2", 1e-5f, &l->n2))) return rc;
-    const bool fold = !mimi && e->tc_on && e->ln_fold_on;
-    if ((rc = linear(p + ".self_attn.in_proj", false, &l->in_proj, fold))) return rc;
+    if ((rc = linear(p + ".self_attn.in_proj", false, &l->in_proj))) return rc;
     if ((rc = linear(p + ".self_attn.out_proj", false, &l->out_proj))) return rc;
-    if ((rc = linear(p + ".linear1", false, &l->l1, fold))) return rc;
+    if ((rc = linear(p + ".linear1", false, &l->l1))) return rc;
     if ((rc = linear(p + ".linear2", false, &l->l2))) return rc;
-    if (fold) {
-      if (l->n1.d != l->in_proj.in || l->n2.d != l->l1.in)
-        PTTS_FAIL(PTTS_EINVAL, "native-cuda: transformer layer norm / linear widths differ");
-      if ((rc = fold_norm(p + ".self_attn.in_proj", p + ".norm1", &l->in_proj, &l->in_c1, &l->in_c2))) return rc;
-      if ((rc = fold_norm(p + ".linear1", p + ".norm2", &l->l1, &l->l1_c1, &l->l1_c2))) return rc;
-      l->folded = e->tc_map.count(l->in_proj.w) && e->tc_map.count(l->l1.w);
-    }
     if (mimi) {
       if (const HostTensor *t = get(p + ".layer_scale_1.scale"))
         if ((rc = e->upload(t->data, &l->ls1))) return rc;
@@ -816,11 +783,6 @@ int Engine::finalize() {
   if (finalized)
     PTTS_FAIL(PTTS_ESTATE, "native-cuda: weights already finalized");
   CUDA_TRY(cudaSetDevice(device));
-  // LayerNorm folded into in_proj / linear1 (GemmEpi::ln_stats): opt-in (PTTS_LN_FOLD=1).  It removes 12
-  // launches per frame, but measured on B200 the per-item statistics in the consumer epilogues and the
-  // >= 128-column tiles forced on the producers cost more than the LayerNorm kernels saved
-  // (B = 256: 952 vs 909 us per frame, B = 1024: 2133 vs 1831; profiles/README_r02.md).
-  ln_fold_on = getenv("PTTS_LN_FOLD") != nullptr;
   Loader ld{this};
   int rc;
   // ---- FlowLM (flow_lm.go:51-119) ----
@@ -1142,9 +1104,6 @@ int Engine::finalize() {
   if ((rc = dmalloc((void **)&fh_x, (size_t)B * C * 4))) return rc;
   if ((rc = dmalloc((void **)&fh_h, (size_t)B * C * 4))) return rc;
   if ((rc = dmalloc((void **)&fh_h2, (size_t)B * rb[0].mlp0.out * 4))) return rc;
-  if ((rc = make_act(s_x, max_rows, D, 0))) return rc;
-  if ((rc = dmalloc((void **)&ln_stats, (size_t)max_rows * LN_SLOTS * 2 * sizeof(float)))) return rc;
-  CUDA_TRY(cudaMemset(ln_stats, 0, (size_t)max_rows * LN_SLOTS * 2 * sizeof(float)));
   if ((rc = make_act(s_nrm, max_rows, D, 0))) return rc;
   if ((rc = make_act(s_att, max_rows, D, 0))) return rc;
   if ((rc = make_act(s_ff, max_rows, F, 0))) return rc;
@@ -1582,7 +1541,7 @@ int Engine::setup_fused() {
 // FlowLM transformer over R rows already in x; row_slot/row_pos uploaded.
 // (flow_transformer.go:326-389, one pass of forwardWithState per layer)
 // ---------------------------------------------------------------------------
-int Engine::flow_forward(int R, int max_keys, bool decode, bool x_ready) {
+int Engine::flow_forward(int R, int max_keys, bool decode) {
   static const bool no_fuse = getenv("PTTS_NO_FUSED_ROPE_ATTN") != nullptr;
   decode = decode && !no_fuse;
   int64_t &nl = times.kernel_launches;
@@ -1590,26 +1549,13 @@ int Engine::flow_forward(int R, int max_keys, bool decode, bool x_ready) {
   if (prof_on)
     for (int r = 0; r < R; r++)
       prof_keys += h_row_pos[r] + 1;
-  // LayerNorm folded into in_proj / linear1 (GemmEpi::ln_stats): the GEMMs read the split planes of the
-  // RAW residual stream, the producers of x (input_linear / out_proj / linear2 epilogues, or
-  // split_stats_rows for a prompt) leave the row statistics.  x_ready: s_x + ln_stats describe x.
-  const bool fold = ln_fold_ok(R);
-  if (fold && !x_ready)
-    PK("elementwise", 0, 0, split_stats_rows(x, R, D, s_x.out(), ln_stats, LN_SLOTS, st));
   for (int l = 0; l < L; l++) {
     DTLayer &ly = fl[l];
+    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st, s_nrm.out()));
     GemmArgs g;
     g.A = nrm; g.lda = D; g.W = ly.in_proj.w; g.ldw = D; g.M = R; g.N = 3 * D; g.K = D;
     g.epi.C = qkv; g.epi.ldc = 3 * D;
-    if (fold) {
-      g.A = nullptr;
-      g.epi.bias = ly.in_c2; g.epi.ln_c1 = ly.in_c1; g.epi.ln_stats = ln_stats; g.epi.ln_eps = ly.n1.eps;
-      g.epi.ln_dim = D; g.epi.ln_slots = LN_SLOTS;
-      use_act(g, s_x);
-    } else {
-      PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st, s_nrm.out()));
-      use_act(g, s_nrm);
-    }
+    use_act(g, s_nrm);
     nl += pgemm(g);
     // decode step: RoPE + KV append + attention are one kernel; the prefill (several rows of a
     // sequence per launch) appends first, then attends
@@ -1630,31 +1576,17 @@ int Engine::flow_forward(int R, int max_keys, bool decode, bool x_ready) {
     GemmArgs o;
     o.A = att; o.lda = D; o.W = ly.out_proj.w; o.ldw = D; o.M = R; o.N = D; o.K = D;
     o.epi.residual = x; o.epi.ldr = D; o.epi.C = x; o.epi.ldc = D;
-    if (fold) {
-      o.epi.Cs = s_x.out(); o.epi.stats_out = ln_stats; o.epi.stats_slots = LN_SLOTS;
-    }
     use_act(o, s_att);
     nl += pgemm(o);
+    PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st, s_nrm.out()));
     GemmArgs f1;
     f1.A = nrm; f1.lda = D; f1.W = ly.l1.w; f1.ldw = D; f1.M = R; f1.N = F; f1.K = D;
     f1.epi.act = ACT_GELU; f1.epi.C = ff; f1.epi.ldc = F; f1.epi.Cs = s_ff.out();
-    if (fold) {
-      f1.A = nullptr;
-      f1.epi.C = nullptr; // only the split planes feed linear2
-      f1.epi.bias = ly.l1_c2; f1.epi.ln_c1 = ly.l1_c1; f1.epi.ln_stats = ln_stats; f1.epi.ln_eps = ly.n2.eps;
-      f1.epi.ln_dim = D; f1.epi.ln_slots = LN_SLOTS;
-      use_act(f1, s_x);
-    } else {
-      PK("layernorm", 0, 0, layernorm(x, D, nrm, D, R, D, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st, s_nrm.out()));
-      use_act(f1, s_nrm);
-    }
+    use_act(f1, s_nrm);
     nl += pgemm(f1);
     GemmArgs f2;
     f2.A = ff; f2.lda = F; f2.W = ly.l2.w; f2.ldw = F; f2.M = R; f2.N = D; f2.K = F;
     f2.epi.residual = x; f2.epi.ldr = D; f2.epi.C = x; f2.epi.ldc = D;
-    if (fold && l + 1 < L) { // the next layer's in_proj reads s_x + statistics again
-      f2.epi.Cs = s_x.out(); f2.epi.stats_out = ln_stats; f2.epi.stats_slots = LN_SLOTS;
-    }
     use_act(f2, s_ff);
     nl += pgemm(f2);
   }
@@ -1993,7 +1925,6 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     nl += n;
     return PTTS_OK;
   }
-  bool x_ready = false;
   if (gather_frames)
     PK("gather_scatter", 0, 0, gather_rows(d_hist, d_off_a, fh_frames, Bp, ldim, st));
   if (gather_noise)
@@ -2003,14 +1934,10 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     GemmArgs g;
     g.A = fh_in; g.lda = ldim; g.W = input_linear.w; g.ldw = ldim; g.M = Bp; g.N = D; g.K = ldim;
     g.epi.bias = input_linear.b; g.epi.C = x; g.epi.ldc = D;
-    if (ln_fold_ok(Bp) && tc_map.count(input_linear.w)) { // layer 0 reads x through its split planes + row statistics
-      g.epi.Cs = s_x.out(); g.epi.stats_out = ln_stats; g.epi.stats_slots = LN_SLOTS;
-      x_ready = true;
-    }
     use_act(g, s_in);
     nl += pgemm(g);
   }
-  int rc = flow_forward(Bp, max_keys, true, x_ready);
+  int rc = flow_forward(Bp, max_keys, true);
   if (rc)
     return rc;
   // start of the flow head: a plain record when run eagerly, an external event-record node when

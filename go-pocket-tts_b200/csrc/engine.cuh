@@ -52,10 +52,6 @@ struct DTLayer {
   DLayerNorm n1, n2;
   DLinear in_proj, out_proj, l1, l2;
   float *ls1 = nullptr, *ls2 = nullptr;
-  // LayerNorm folded into the following GEMM (FlowLM layers; GemmEpi::ln_stats): the tensor-core copy of
-  // in_proj / linear1 holds W diag(norm.weight); c1 = its row sums, c2 = W norm.bias
-  float *in_c1 = nullptr, *in_c2 = nullptr, *l1_c1 = nullptr, *l1_c2 = nullptr;
-  bool folded = false;
 };
 // Conv / ConvTranspose in GEMM form: W [N, taps*cin], A rows overlap (lda=cin).
 struct DConvG {
@@ -161,11 +157,6 @@ struct Engine {
 
   // split activation planes (A operands of the tcgen05 GEMMs)
   ActSplit s_nrm, s_att, s_ff, s_in, s_last, s_sy, s_cur, s_h, s_h2;
-  ActSplit s_x;              // split planes of the raw residual stream (A operand of the LN-folded GEMMs)
-  float *ln_stats = nullptr; // [max_rows][LN_SLOTS][2] partial (sum, sum^2) per 128-column group
-  static constexpr int LN_SLOTS = 8;
-  bool ln_fold_on = true;
-  bool ln_fold_ok(int R) const { return ln_fold_on && tc_on && R >= tc_min_m && D == 128 * LN_SLOTS && !fl.empty() && fl[0].folded; }
   ActSplit sm_latin, sm_nrm, sm_att, sm_ff, sm_x, sm_y0e, sm_ye[3], sm_he[3];
   // output of a fused residual block (its input planes are still being read as halo rows by
   // neighbouring tiles, so it cannot be written in place) + the next up-conv's map over it
@@ -379,7 +370,7 @@ struct Engine {
   int sync_pagetab(Seq *s);
 
   // passes (caller holds gpu_mu)
-  int flow_forward(int R, int max_keys, bool decode, bool x_ready = false); // decode: one new row per sequence
+  int flow_forward(int R, int max_keys, bool decode); // decode: one new row per sequence
   int prefill(const std::vector<Seq *> &seqs, const std::vector<const int64_t *> &tok,
               const std::vector<int> &ntok, const std::vector<const float *> &voice,
               const std::vector<int> &nvoice);

@@ -43,17 +43,6 @@ struct GemmEpi {
   SplitOut Cs, C2s; // split-bf16 copies of C / C2 for a following tensor-core GEMM
   const uint8_t *rowmask = nullptr; // row m is live iff rowmask[m / mask_div]
   int mask_div = 1;
-  // LayerNorm folded into the GEMM (FlowLM layers, linear.go:265-329 + :117-182).  With W' = W diag(g),
-  // c1[n] = sum_k W'[n,k], c2[n] = sum_k W[n,k] beta[k]:
-  //     LN(x) W^T = r (x W'^T - mu c1) + c2,     mu, r = rsqrt(var + eps) per row.
-  // Consumer: A = split planes of the RAW residual stream, W = W', bias = c2, ln_c1 = c1 and ln_stats =
-  // per-row partial sums [row][ln_slots][2] = (sum x, sum x^2) over 128-column groups, written by the
-  // epilogue of the GEMM that produced x (stats_out; that GEMM then runs with tiles >= 128 columns).
-  const float *ln_stats = nullptr, *ln_c1 = nullptr;
-  float ln_eps = 0.0f;
-  int ln_dim = 0, ln_slots = 0;
-  float *stats_out = nullptr;
-  int stats_slots = 0;
 };
 
 struct GemmArgs {
@@ -196,9 +185,6 @@ int copy_rows(const float *src, float *dst, int rows, int width, cudaStream_t st
               SplitOut sp = SplitOut());
 int scatter_rows(const float *src, float *dst, const int64_t *dst_off, int rows,
                  int width, cudaStream_t st);
-// Split planes of x [rows, D] plus its row statistics in the folded-LayerNorm slot format
-// (stats [rows][slots][2]: slot 0 = (sum, sum^2) of the whole row, the other slots zero).
-int split_stats_rows(const float *x, int rows, int D, SplitOut sp, float *stats, int slots, cudaStream_t st);
 
 // Depthwise ConvTranspose1d (stride s, kernel k<=2s, right trim k-s) from
 // per-frame features lat [frames, C] into the padded channels-last layout:

@@ -186,98 +186,9 @@ __device__ __forceinline__ void epi_rows_generic(const GemmEpi &e, uint32_t stg_
     }
   }
 }
-// ---- LayerNorm folded into the GEMM (GemmEpi::ln_stats / stats_out) ----
-constexpr int EPI_KIND_LN = -2, EPI_KIND_STATS = -3;
-// mean and 1/sqrt(var + eps) of row m from the partial sums the producer's epilogue left
-__device__ __forceinline__ void ln_row_stats(const GemmEpi &e, long m, float &mu, float &r) {
-  float s1 = 0.0f, s2 = 0.0f;
-  const float2 *p = reinterpret_cast<const float2 *>(e.ln_stats) + m * e.ln_slots;
-  for (int i = 0; i < e.ln_slots; i++) {
-    const float2 v = __ldcg(p + i);
-    s1 += v.x;
-    s2 += v.y;
-  }
-  mu = s1 / (float)e.ln_dim;
-  const float var = fmaxf(s2 / (float)e.ln_dim - mu * mu, 0.0f);
-  r = 1.0f / sqrtf(var + e.ln_eps);
-}
-__device__ __forceinline__ float4 ln_fix4(const float4 &a, float mu, float r, const float4 &c1) {
-  return make_float4(r * (a.x - mu * c1.x), r * (a.y - mu * c1.y), r * (a.z - mu * c1.z), r * (a.w - mu * c1.w));
-}
-// Consumer epilogue of a 32x32 chunk: v = act(r (acc - mu c1) + c2) -> C and / or its split planes.
-// ln_mu / ln_r are those of row (32 q + lane) of the tile: row rsub + 4 j is fetched by shuffle.
-__device__ __forceinline__ void epi_rows_ln(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
-                                            uint32_t rows, const float4 &bias4, const float4 &c14, float ln_mu, float ln_r,
-                                            int rsub) {
-  float mu[8], r[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    mu[j] = __shfl_sync(0xffffffffu, ln_mu, rsub + 4 * j);
-    r[j] = __shfl_sync(0xffffffffu, ln_r, rsub + 4 * j);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    if ((rows >> j) & 1) {
-      const long m = m_first + j * 4;
-      float4 o = ln_fix4(lds128(stg_addr + j * 4 * stg_ld_bytes), mu[j], r[j], c14);
-      o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
-      if (e.act != ACT_NONE) {
-        o.x = act_apply(o.x, e.act); o.y = act_apply(o.y, e.act);
-        o.z = act_apply(o.z, e.act); o.w = act_apply(o.w, e.act);
-      }
-      if (e.C)
-        *reinterpret_cast<float4 *>(e.C + m * e.ldc + n) = o;
-      if (e.Cs.hi)
-        split_store4(e.Cs, m, n, o);
-    }
-  }
-}
-// Producer epilogue of a 32x32 chunk: v = acc + bias + residual -> C (fp32 residual stream) and its
-// split planes; the lane's share of (sum v, sum v^2) per row is added to ssum / ssq.
-__device__ __forceinline__ void epi_rows_stats(const GemmEpi &e, uint32_t stg_addr, int stg_ld_bytes, long m_first, int n,
-                                               uint32_t rows, const float4 &bias4, const float4 *res, bool have_res,
-                                               float (&ssum)[8], float (&ssq)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    if ((rows >> j) & 1) {
-      const long m = m_first + j * 4;
-      float4 o = lds128(stg_addr + j * 4 * stg_ld_bytes);
-      o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
-      if (have_res) {
-        o.x += res[j].x; o.y += res[j].y; o.z += res[j].z; o.w += res[j].w;
-      }
-      *reinterpret_cast<float4 *>(e.C + m * e.ldc + n) = o;
-      if (e.Cs.hi)
-        split_store4(e.Cs, m, n, o);
-      ssum[j] += (o.x + o.y) + (o.z + o.w);
-      ssq[j] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-    }
-  }
-}
-// End of a 128-column group: the 8 lanes that share the rows add their shares, the first one
-// writes (sum, sum^2) of every row into slot `slot`, and the accumulators restart.
-__device__ __forceinline__ void epi_stats_flush(const GemmEpi &e, long m_first, uint32_t rows, int slot, int lane,
-                                                float (&ssum)[8], float (&ssq)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    float a = ssum[j], b = ssq[j];
-    a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
-    a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
-    if ((lane & 7) == 0 && ((rows >> j) & 1))
-      reinterpret_cast<float2 *>(e.stats_out)[(m_first + j * 4) * e.stats_slots + slot] = make_float2(a, b);
-    ssum[j] = 0.0f;
-    ssq[j] = 0.0f;
-  }
-}
-
 // Epilogue kinds with a compiled fast path: (activation << 4) | output mask.
 __host__ __device__ constexpr int epi_code(int act, int mask) { return (act << 4) | mask; }
 __host__ inline int epi_kind_of(const GemmEpi &e) {
-  if (e.ln_stats)
-    return EPI_KIND_LN;
-  if (e.stats_out)
-    return EPI_KIND_STATS;
   if (e.mul || e.alpha != 1.0f)
     return -1;
   const int mask = (e.C ? 1 : 0) | (e.Cs.hi ? 2 : 0) | (e.C2 ? 4 : 0) | (e.C2s.hi ? 8 : 0);

@@ -357,13 +357,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
         bool full, nok, last_chunk, have_res;
         float4 bias4, cs4;
         float4 res[8];
-        float ln_mu, ln_r; // LayerNorm-folded consumer: statistics of row 32 q + lane of the item
       };
-      float ssum[8], ssq[8]; // stats producer: this lane's share of the row sums of the current 128-column group
-#pragma unroll
-      for (int jj = 0; jj < 8; jj++)
-        ssum[jj] = ssq[jj] = 0.0f;
-      float ln_mu_item = 0.0f, ln_r_item = 1.0f;
       const int nch = (BN - c_first + C_STEP - 1) / C_STEP; // chunks of an item this warp owns
       const int my_items = ((int)items.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int nunits = c_first < BN ? my_items * nch : 0;
@@ -390,13 +384,6 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             }
           }
           full_item = __all_sync(0xffffffffu, (rows_item & 0xFFu) == 0xFFu);
-          if (e.ln_stats) {
-            const int m = im0 + q * 32 + lane;
-            ln_mu_item = 0.0f;
-            ln_r_item = 1.0f;
-            if (m < M)
-              ln_row_stats(e, m, ln_mu_item, ln_r_item);
-          }
           mbar_wait(&acc_full[c.b], (uint32_t)(li2 >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
@@ -404,8 +391,6 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
         c.n0 = in0;
         c.rows = rows_item;
         c.full = full_item;
-        c.ln_mu = ln_mu_item;
-        c.ln_r = ln_r_item;
         const int n = in0 + c.c0 + cf;
         c.nok = n < N;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c.b * BN + c.c0);
@@ -436,8 +421,6 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             c.bias4 = __ldg(reinterpret_cast<const float4 *>(e.bias + n));
           if (e.colscale)
             c.cs4 = __ldg(reinterpret_cast<const float4 *>(e.colscale + n));
-          if (e.ln_c1) // the consumer's c1 rides in the (otherwise unused) column-scale slot
-            c.cs4 = __ldg(reinterpret_cast<const float4 *>(e.ln_c1 + n));
         }
       };
       UnitCtx cur, nxt;
@@ -459,17 +442,8 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
         if (cur.nok) {
           const uint32_t rd_addr = stg_addr + (uint32_t)(rsub * SM::STG_LD + cf) * 4;
           const long m_first = cur.m0 + q * 32 + rsub;
-          if (items.epi_kind == EPI_KIND_LN) {
-            epi_rows_ln(e, rd_addr, SM::STG_LD * 4, m_first, cur.n0 + cur.c0 + cf, cur.rows, cur.bias4, cur.cs4, cur.ln_mu,
-                        cur.ln_r, rsub);
-          } else if (items.epi_kind == EPI_KIND_STATS) {
-            epi_rows_stats(e, rd_addr, SM::STG_LD * 4, m_first, cur.n0 + cur.c0 + cf, cur.rows, cur.bias4, cur.res,
-                           cur.have_res, ssum, ssq);
-            if (((cur.c0 + 32) & 127) == 0 || cur.last_chunk)
-              epi_stats_flush(e, m_first, cur.rows, (cur.n0 + cur.c0) >> 7, lane, ssum, ssq);
-          } else
-            epi_rows_dispatch(items.epi_kind, e, rd_addr, SM::STG_LD * 4, m_first, cur.n0 + cur.c0 + cf, cur.rows,
-                              cur.bias4, cur.cs4, cur.res, cur.have_res, cur.full);
+          epi_rows_dispatch(items.epi_kind, e, rd_addr, SM::STG_LD * 4, m_first, cur.n0 + cur.c0 + cf, cur.rows, cur.bias4,
+                            cur.cs4, cur.res, cur.have_res, cur.full);
         }
         __syncwarp(); // staging is rewritten by the next unit
       }
@@ -709,7 +683,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
       const uint32_t slots = smem_u32(smem);
       constexpr int C4 = BN / 4;
       const int total = rows_here * C4;
-      for (int idx = threadIdx.x - 64; idx < total; idx += EW * 32) { // total % 32 == 0: warp-uniform trip count
+      for (int idx = threadIdx.x - 64; idx < total; idx += EW * 32) {
         const int rloc = idx / C4, c4 = idx - rloc * C4;
         const int m = m0 + r_begin + rloc, n = n0 + c4 * 4;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -717,15 +691,8 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
           const float4 u = lds128(slots + (uint32_t)((((sp * rows_per + rloc) * BN) + c4 * 4) * 4));
           a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
         }
-        const bool ok = m < M && n < N;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) {
-          if (e.ln_stats) { // LayerNorm folded in: r (acc - mu c1), then bias (= c2), activation, ...
-            float mu, r;
-            ln_row_stats(e, m, mu, r);
-            a = ln_fix4(a, mu, r, __ldg(reinterpret_cast<const float4 *>(e.ln_c1 + n)));
-          }
-          o = epi_vec4(e, a, m, n);
+        if (m < M && n < N) {
+          float4 o = epi_vec4(e, a, m, n);
           if (e.rowmask && !e.rowmask[m / e.mask_div])
             o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (e.C)
@@ -739,18 +706,6 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             if (e.C2s.hi)
               split_store4(e.C2s, m, n, u2);
           }
-        }
-        if (e.stats_out) {
-          // BN >= 128 here: the 32 threads of a warp iteration hold 128 consecutive columns of ONE row,
-          // i.e. exactly one statistics slot (idx advances by a multiple of 32, C4 is a multiple of 32)
-          float s1 = (o.x + o.y) + (o.z + o.w), s2 = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-#pragma unroll
-          for (int sh = 16; sh > 0; sh >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
-          }
-          if (lane == 0 && ok)
-            reinterpret_cast<float2 *>(e.stats_out)[(long)m * e.stats_slots + (n >> 7)] = make_float2(s1, s2);
         }
       }
     }
@@ -857,12 +812,6 @@ int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
                 tiles <= tc_max_clusters<BN, STAGES, ATMA, EW>(S))
                    ? 1
                    : 0;
-  if ((g.epi.ln_stats || g.epi.stats_out) && it.S > 1 && !it.cluster) {
-    // the folded-LayerNorm epilogues exist in the single-pass and the cluster paths only
-    it.S = 1;
-    it.kb_per = it.nkb_all;
-    it.total = (int)tiles;
-  }
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
   const CUtensorMap *am = ATMA ? reinterpret_cast<const CUtensorMap *>(g.amap) : map;
   launch_kc(tc_gemm_kernel<BN, STAGES, ATMA, EW>, dim3(grid), dim3(tc_threads(EW, ATMA)), SM::BYTES, st,
@@ -924,8 +873,6 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
     const int b = cand[c];
     if (b / 2 >= g.N && b > 32)
       continue; // more than half the tile would be padding
-    if (g.epi.stats_out && b < 128)
-      continue; // row statistics are kept per 128-column group
     const long ntn = (g.N + b - 1) / b;
     const long tiles = mt * ntn;
     const int smax = tiles >= sms ? 1 : 8;
@@ -934,10 +881,6 @@ void choose_tile(const GemmArgs &g, int &bn, int &S) {
       if ((long)kb_per * (s - 1) >= nkb)
         continue;
       const long items = tiles * s;
-      if ((g.epi.ln_stats || g.epi.stats_out) && s > 1 &&
-          !(atma && items <= sms && (long)s * ((128 + s - 1) / s) * b * 4 <= (b == 32 ? 4L * 40960 : 196608L) &&
-            tiles <= tc_cluster_capacity(b, s)))
-        continue; // folded LayerNorm: split-K only through a cluster
       const long per_cta = (items + sms - 1) / sms; // items a CTA runs back to back
       const double kb_bytes = (128.0 + b) * 256.0;
       double t_kb = !atma ? 1.3 : (b == 256 ? 1.3 : 0.58);

@@ -621,46 +621,6 @@ def test_persistent_flow_head_matches_multi_kernel_head_and_oracle(pkg, small_te
         want, we, _ = st.step(np.full(32, np.nan, np.float32), pkg.make_noise(batch, 0.7, 77)[b])
         assert allclose_ref(fused[0][0][b], want, ABS, REL), (b, np.abs(fused[0][0][b] - want).max())
         assert abs(fused[0][1][b] - we) <= 5e-4 + REL * abs(we)
-
-
-def test_layernorm_folded_into_gemms_matches_oracle(pkg, small_tensors, small_oracle, monkeypatch):
-    """PTTS_LN_FOLD=1: norm1 / norm2 of the FlowLM layers live in the in_proj / linear1 GEMMs (weights scaled by
-    norm.weight, row statistics from the epilogue of the GEMM that produced the residual stream).  Same
-    tolerance as the default path, prefill and batched steps, and 12 fewer launches per frame (2 layers: 4)."""
-    monkeypatch.setenv("PTTS_LN_FOLD", "1")
-    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=48, max_seq_tokens=128, max_frames=16,
-                               mimi_group_frames=64)
-    monkeypatch.delenv("PTTS_LN_FOLD")
-    try:
-        batch = 40
-        toks = [_tokens(3 + (b * 7) % 29, 500 + b) for b in range(batch)]
-        seqs = [rt.seq_open(t, reserve_frames=4) for t in toks]
-        st = rt.stage_times(reset=True)
-        frames = np.full((batch, 32), np.nan, np.float32)
-        states = {}
-        for b in (0, 17, 39):
-            s_ = small_oracle.new_state()
-            s_.prompt(small_oracle.text_embeddings(toks[b]))
-            states[b] = s_
-            for layer in range(small_oracle.L):  # the prompt went through the folded GEMMs too
-                assert allclose_ref(seqs[b].read_kv(layer, 0), s_.read_kv(layer, 0), 5e-4, 2e-3)
-        for step in range(2):
-            noise = pkg.make_noise(batch, 0.7, 90 + step)
-            lat, eos = rt.step(seqs, noise, frames_in=frames)
-            nxt = lat.copy()
-            for b, s_ in states.items():
-                want, we, _ = s_.step(frames[b], noise[b])
-                assert allclose_ref(lat[b], want, ABS, REL), (step, b, np.abs(lat[b] - want).max())
-                assert abs(eos[b] - we) <= 5e-4 + REL * abs(we)
-                nxt[b] = want
-            frames = nxt
-        assert rt.stage_times()["kernel_launches"] / 2 <= 36  # 40 per step with the LayerNorm kernels (small model)
-        for s_ in seqs:
-            s_.close()
-    finally:
-        rt.close()
-
-
 def test_tcgen05_window_attention_matches_default_and_oracle(pkg, small_tensors, small_oracle, monkeypatch):
     """PTTS_ATTN_TC=1: the Mimi window-250 attention with S and P.V accumulated in TMEM (attention_tc.cu,
     K as K-major and V as MN-major B operands) against the oracle and the default kernel: ragged batch with
