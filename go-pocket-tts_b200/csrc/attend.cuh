@@ -122,7 +122,19 @@ __device__ __forceinline__ void attend_row(const float *q, int nkeys, KeyFn keyp
   // phase 3
   const int c4 = tid & 15, grp = tid >> 4; // 8 key groups
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = grp; j < nkeys; j += 8) {
+  // four value rows (and their page-table lookups) in flight per thread: the loop is ~nkeys/8 dependent
+  // round trips otherwise.  Same summation order as the plain loop.
+  int j = grp;
+  for (; j + 24 < nkeys; j += 32) {
+    const float4 v0 = kv_load4(valp(j) + c4 * 4), v1 = kv_load4(valp(j + 8) + c4 * 4);
+    const float4 v2 = kv_load4(valp(j + 16) + c4 * 4), v3 = kv_load4(valp(j + 24) + c4 * 4);
+    const float w0 = scores[j] * inv, w1 = scores[j + 8] * inv, w2 = scores[j + 16] * inv, w3 = scores[j + 24] * inv;
+    acc.x = fmaf(w0, v0.x, acc.x); acc.y = fmaf(w0, v0.y, acc.y); acc.z = fmaf(w0, v0.z, acc.z); acc.w = fmaf(w0, v0.w, acc.w);
+    acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y); acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+    acc.x = fmaf(w2, v2.x, acc.x); acc.y = fmaf(w2, v2.y, acc.y); acc.z = fmaf(w2, v2.z, acc.z); acc.w = fmaf(w2, v2.w, acc.w);
+    acc.x = fmaf(w3, v3.x, acc.x); acc.y = fmaf(w3, v3.y, acc.y); acc.z = fmaf(w3, v3.z, acc.z); acc.w = fmaf(w3, v3.w, acc.w);
+  }
+  for (; j < nkeys; j += 8) {
     const float w = scores[j] * inv;
     const float4 v = kv_load4(valp(j) + c4 * 4);
     acc.x = fmaf(w, v.x, acc.x);

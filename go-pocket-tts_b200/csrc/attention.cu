@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * PT * HD;
   const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * PT * HD;
   KT *pool = static_cast<KT *>(kv.pool);
+  // the sequence's page ids go to shared memory once: every key / value access below would otherwise be two
+  // dependent global loads (page id, then the row)
+  __shared__ int32_t s_pt[512];
+  for (int i = tid; i * PT < nkeys; i += ATT_THREADS)
+    s_pt[i] = pt[i];
   {
     const float *row = qkv + (long)r * ldq;
     KT *page = pool + (long)pt[pos / PT] * page_stride + (long)(pos % PT) * HD;
@@ -121,12 +126,12 @@ __global__ void __launch_bounds__(ATT_THREADS)
       kv_store(page + voff + d, row[2 * D + h * HD + d]);
     }
   }
-  __syncthreads(); // q in shared memory; this CTA's own k/v stores are visible to its loads below
+  __syncthreads(); // q and the page ids in shared memory; this CTA's own k/v stores are visible to its loads below
   auto keyp = [&](int j) {
-    return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
+    return pool + (long)s_pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
   };
   auto valp = [&](int j) {
-    return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
+    return pool + (long)s_pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
   };
   attend_row(qs, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
 }
