@@ -470,7 +470,8 @@ def main():
               "realtime_factor_including_decode": c2_audio / c2_wall,
               "definition": "host clock; first_audio = submit -> PCM of frame 0 on the host (prefill + 1 AR frame + "
                             "Mimi decode + D2H); frame_emit = interval between consecutive per-frame deliveries; every "
-                            "delivery re-runs Mimi over the frame's 33-frame receptive field (bounded work per frame)"}
+                            "delivery decodes the new frame + one context frame against the request's Mimi K/V ring "
+                            "(PTTS_NO_STREAM_STATE=1: the 33-frame receptive field instead)"}
         gv = p1.get("gemv_f32", {"ms": 0, "bytes": 0, "launches": 1})
         peaks = load_peaks()
         bytes_frame = 4.0 * info.params_ar

@@ -518,6 +518,78 @@ int kv_read_rows(float *out, int T, int slot, const KvGeom &kv, int layer,
   return 1;
 }
 
+// ---- stateful streaming decode: per-request K/V ring of the Mimi transformer ----
+__global__ void __launch_bounds__(256)
+    kv_ring_append_kernel(const float *qkv, int D, const int32_t *row_apos, const int4 *row_seg, float *ring,
+                          long state_stride, long layer_off) {
+  const int r = blockIdx.x, p = row_apos[r];
+  const int4 sg = row_seg[r];
+  if (p < 0 || sg.x < 0)
+    return;
+  const float4 *src = reinterpret_cast<const float4 *>(qkv + (long)r * 3 * D + D); // K | V of the row, 2 D floats
+  float4 *dst = reinterpret_cast<float4 *>(ring + (long)sg.x * state_stride + layer_off + (long)(p % MIMI_RING) * 2 * D);
+  for (int i = threadIdx.x; i < 2 * D / 4; i += blockDim.x)
+    dst[i] = src[i];
+}
+int kv_ring_append(const float *qkv, int rows, int D, const int32_t *row_apos, const int4 *row_seg, float *ring,
+                   long state_stride, long layer_off, cudaStream_t st) {
+  if (rows <= 0)
+    return 0;
+  kv_ring_append_kernel<<<rows, 256, 0, st>>>(qkv, D, row_apos, row_seg, ring, state_stride, layer_off);
+  return 1;
+}
+
+// Row r (absolute position p) attends the last min(ctx, p + 1) rows of its request: those at or after the
+// segment's first row come from the qkv buffer, the older ones from the request's ring
+// (mimi.go:386-441, attention.go:473-484 with the window carried across deliveries).
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_window_stream_kernel(const float *qkv, long ldq, float *out, long ldo, int D, const int32_t *row_apos,
+                                   const int4 *row_seg, const float *ring, long state_stride, long layer_off, int ctx,
+                                   SplitOut sp) {
+  extern __shared__ float smem[];
+  __shared__ float red[ATT_THREADS / 32];
+  __shared__ float4 pv[8 * 16];
+  const int r = blockIdx.x, h = blockIdx.y;
+  const int pos = row_apos[r];
+  float *o = out ? out + (long)r * ldo + h * HD : nullptr;
+  if (pos < 0) {
+    if (threadIdx.x < 16) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o)
+        *reinterpret_cast<float4 *>(o + threadIdx.x * 4) = z;
+      if (sp.hi)
+        split_store4(sp, r, h * HD + threadIdx.x * 4, z);
+    }
+    return;
+  }
+  const int4 sg = row_seg[r];
+  const int nkeys = (ctx > 0 && pos + 1 > ctx) ? ctx : pos + 1;
+  const int first = pos - (nkeys - 1); // absolute position of the oldest allowed key
+  const float *rk = ring + (long)(sg.x < 0 ? 0 : sg.x) * state_stride + layer_off + h * HD;
+  const float *bk = qkv + D + h * HD;
+  auto keyp = [&](int j) {
+    const int a = first + j;
+    return a >= sg.y ? bk + (long)(sg.z + a - sg.y) * ldq : rk + (long)(a % MIMI_RING) * 2 * D;
+  };
+  auto valp = [&](int j) {
+    const int a = first + j;
+    return a >= sg.y ? bk + D + (long)(sg.z + a - sg.y) * ldq : rk + D + (long)(a % MIMI_RING) * 2 * D;
+  };
+  attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
+}
+int attention_window_stream(const float *qkv, long ldq, float *out, long ldo, int rows, int D, int n_heads,
+                            const int32_t *row_apos, const int4 *row_seg, const float *ring, long state_stride,
+                            long layer_off, int ctx, cudaStream_t st, SplitOut sp) {
+  if (rows <= 0)
+    return 0;
+  dim3 grid(rows, n_heads);
+  const int mk = ctx > 0 ? ctx : 8192;
+  const size_t sm = sizeof(float) * (size_t)((mk + 15) / 16 * 16);
+  attention_window_stream_kernel<<<grid, ATT_THREADS, sm, st>>>(qkv, ldq, out, ldo, D, row_apos, row_seg, ring,
+                                                                state_stride, layer_off, ctx, sp);
+  return 1;
+}
+
 __global__ void __launch_bounds__(256)
     rope_inplace_kernel(float *qkv, int D, int n_heads, const int32_t *row_pos,
                         const float *cosT, const float *sinT) {

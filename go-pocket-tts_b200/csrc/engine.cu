@@ -97,6 +97,7 @@ Engine::~Engine() {
     fh(h_lat_ring[i]);
     fh(h_s16_ring[i]);
     fh(h_mrow_pos_ring[i]); fh(h_mrow_frame0_ring[i]); fh(h_mmask_ring[i]); fh(h_moff_ring[i]);
+    fh(h_mrow_apos_ring[i]); fh(h_mrow_seg_ring[i]);
     for (cudaEvent_t e2 : {ev_dec0[i], ev_pcm_ready[i], ev_copied[i], ev_copy0[i], ev_lat_ready[i]})
       if (e2)
         cudaEventDestroy(e2);
@@ -955,7 +956,7 @@ int Engine::finalize() {
   MF = ml[0].l1.out;
   {
     std::vector<float> c, s;
-    build_rope(8192, Md / MH, 10000.0, c, s);
+    build_rope(MIMI_ROPE_ROWS, Md / MH, 10000.0, c, s);
     if ((rc = upload(c, &mrope_cos))) return rc;
     if ((rc = upload(s, &mrope_sin))) return rc;
   }
@@ -1198,6 +1199,24 @@ int Engine::finalize() {
         if ((rc = make_act(sm_yf[s], r2, up[s].cout, lead))) return rc;
         if ((rc = make_conv_map(sm_yf[s], up[s + 1].cin, up[s + 1].taps, &up_alt_amap[s + 1]))) return rc;
       }
+    }
+  }
+  {
+    stream_state_on = getenv("PTTS_NO_STREAM_STATE") == nullptr;
+    n_stream_states = stream_state_on ? (max_batch < 32 ? max_batch : 32) : 0;
+    ring_layer_stride = (long)MIMI_RING * 2 * Md;
+    ring_state_stride = (long)ML * ring_layer_stride;
+    if (n_stream_states > 0) {
+      if ((rc = dmalloc((void **)&mimi_ring, (size_t)n_stream_states * ring_state_stride * sizeof(float)))) return rc;
+      CUDA_TRY(cudaMemset(mimi_ring, 0, (size_t)n_stream_states * ring_state_stride * sizeof(float)));
+    }
+    for (int i = n_stream_states - 1; i >= 0; i--)
+      free_stream_states.push_back(i);
+    if ((rc = dmalloc((void **)&d_mrow_apos, Rb * 4))) return rc;
+    if ((rc = dmalloc((void **)&d_mrow_seg, Rb * sizeof(int4)))) return rc;
+    for (int i = 0; i < NPCM; i++) {
+      CUDA_TRY(cudaMallocHost((void **)&h_mrow_apos_ring[i], Rb * 4));
+      CUDA_TRY(cudaMallocHost((void **)&h_mrow_seg_ring[i], Rb * sizeof(int4)));
     }
   }
   if ((rc = dmalloc((void **)&d_mrow_pos, Rb * 4))) return rc;
@@ -2147,18 +2166,35 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
   int64_t &nl = times.kernel_launches;
   const int P = mimi_pad;
   int Rb = 0;
+  // a pass with stateful streaming segments carries absolute row positions (RoPE, attention window across
+  // deliveries) and the per-row ring descriptors; the other segments of such a pass start at position 0
+  bool stream = false;
+  for (auto &sg : segs)
+    stream = stream || sg.ring >= 0;
+  stream = stream && job != nullptr;
+  int32_t *h_apos = stream ? h_mrow_apos_ring[job->buf] : nullptr;
+  int4 *h_seg = stream ? h_mrow_seg_ring[job->buf] : nullptr;
   for (auto &sg : segs) {
     sg.row0 = Rb;
+    const int a0 = sg.ring >= 0 ? sg.abs_frame0 * up_stride : 0;
     for (int i = 0; i < P; i++) {
       h_mrow_pos[Rb + i] = -1;
       h_mrow_frame0[Rb + i] = sg.frame0;
       h_mmask[Rb + i] = 0;
+      if (stream) {
+        h_apos[Rb + i] = -1;
+        h_seg[Rb + i] = make_int4(-1, 0, 0, 0);
+      }
     }
     int n = sg.n_frames * up_stride;
     for (int i = 0; i < n; i++) {
-      h_mrow_pos[Rb + P + i] = i;
+      h_mrow_pos[Rb + P + i] = i + sg.pre * up_stride; // (a stream pass uses it for the upsampling taps only)
       h_mrow_frame0[Rb + P + i] = sg.frame0;
       h_mmask[Rb + P + i] = 1;
+      if (stream) {
+        h_apos[Rb + P + i] = a0 + i;
+        h_seg[Rb + P + i] = make_int4(sg.ring, a0, Rb + P, 0);
+      }
     }
     Rb += P + n;
   }
@@ -2168,6 +2204,10 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
   CUDA_TRY(cudaMemcpyAsync(d_mrow_pos, h_mrow_pos, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_mrow_frame0, h_mrow_frame0, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_mmask, h_mmask, (size_t)Rb, cudaMemcpyHostToDevice, st));
+  if (stream) {
+    CUDA_TRY(cudaMemcpyAsync(d_mrow_apos, h_apos, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_mrow_seg, h_seg, (size_t)Rb * sizeof(int4), cudaMemcpyHostToDevice, st));
+  }
   // With the tensor-core path on, every GEMM / conv input is produced directly as split
   // bf16 planes (fetched by TMA) and its fp32 copy is not written.
   const bool sp_on = tc_on;
@@ -2194,8 +2234,15 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
     g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
     use_act(g, sm_nrm);
     nl += pgemm(g);
-    PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, d_mrow_pos, mrope_cos, mrope_sin, st));
-    if (prof_on) {
+    PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, stream ? d_mrow_apos : d_mrow_pos, mrope_cos, mrope_sin, st));
+    if (stream) {
+      // stateful deliveries: this layer's K (rotated) and V rows join the requests' rings, the new rows attend
+      // ring + buffer (the ring slots written here are never among the 249 older rows a row of the pass reads)
+      const long loff = (long)l * ring_layer_stride;
+      nl += kv_ring_append(m_qkv, Rb, Md, d_mrow_apos, d_mrow_seg, mimi_ring, ring_state_stride, loff, st);
+      nl += attention_window_stream(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_apos, d_mrow_seg, mimi_ring,
+                                    ring_state_stride, loff, Mctx, st, spo(sm_att));
+    } else if (prof_on) {
       // flops: every allowed (query, key) pair, 4 * head_dim per head.  bytes: what a flash-style
       // kernel must move — per block of 64 query rows the q rows, the UNIQUE K and V rows of the
       // block's windows (read once per block, not once per query) and the output rows.
@@ -2398,13 +2445,18 @@ int Engine::decode_async(const std::vector<DecodeItem> &items) {
         i++;
         continue;
       }
-      if (tf + n > mimi_frames_cap)
+      if (tf + n + it.pre > mimi_frames_cap)
         break;
       MimiSeg sg;
       sg.n_frames = n;
       sg.frame0 = tf;
       sg.row0 = 0;
       sg.host_out = nullptr;
+      sg.ring = it.ring;
+      sg.abs_frame0 = it.first;
+      sg.pre = it.pre;
+      for (int f = 0; f < it.pre; f++, tf++)
+        h_moff_ring[k][tf] = ((int64_t)r->seq->slot * (max_frames + 1) + it.first - it.pre + f + 1) * ldim;
       for (int f = 0; f < n; f++)
         h_moff_ring[k][tf + f] = ((int64_t)r->seq->slot * (max_frames + 1) + it.first + f + 1) * ldim;
       PcmJob::Seg js;

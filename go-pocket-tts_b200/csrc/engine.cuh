@@ -104,6 +104,9 @@ struct MimiSeg { // one chunk inside a batched Mimi decode
   int frame0;    // first row in the gathered latent matrix
   int row0;      // first base row (pad rows included)
   float *host_out; // destination for PCM (may be null)
+  int ring = -1;     // stateful streaming delivery: the request's Mimi K/V ring (else -1)
+  int abs_frame0 = 0; // ... and the absolute index of the segment's first ROW frame in the request
+  int pre = 0;        // latent frames gathered in front of frame0's rows for the upsampling taps only (no rows)
 };
 
 struct Engine {
@@ -236,6 +239,14 @@ struct Engine {
         *m_he[3] = {nullptr, nullptr, nullptr};
   float *m_pcm = nullptr;
   int32_t *d_mrow_pos = nullptr, *d_mrow_frame0 = nullptr;
+  // stateful streaming decode (f2): per-request K/V rings of the Mimi transformer + per-row descriptors
+  float *mimi_ring = nullptr; // [n_stream_states][ML][MIMI_RING][2 Md]
+  long ring_state_stride = 0, ring_layer_stride = 0;
+  int n_stream_states = 0;
+  std::vector<int> free_stream_states;
+  int32_t *d_mrow_apos = nullptr;
+  int4 *d_mrow_seg = nullptr;
+  bool stream_state_on = true;
   uint8_t *d_mmask = nullptr;
   int32_t *h_mrow_pos = nullptr, *h_mrow_frame0 = nullptr;
   uint8_t *h_mmask = nullptr;
@@ -263,6 +274,8 @@ struct Engine {
   int32_t *h_mrow_pos_ring[NPCM]{}, *h_mrow_frame0_ring[NPCM]{};
   uint8_t *h_mmask_ring[NPCM]{};
   int64_t *h_moff_ring[NPCM]{};
+  int32_t *h_mrow_apos_ring[NPCM]{};
+  int4 *h_mrow_seg_ring[NPCM]{};
   float *m_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   float *h_pcm_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_lat_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
   int16_t *m_s16_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr}, *h_s16_ring[NPCM] = {nullptr, nullptr, nullptr, nullptr};
@@ -298,6 +311,8 @@ struct Engine {
     std::shared_ptr<Request> r;
     int first = 0, count = 0, skip = 0;
     bool final = true;
+    int ring = -1; // stateful delivery: only `skip` (<= 1) frames of conv context are re-decoded
+    int pre = 0;   // ... with this many earlier latent frames gathered for the upsampling taps
   };
   int decode_async(const std::vector<DecodeItem> &items);
   int mimi_window_frames() const { // receptive field of one output frame, in latent frames (f2)
@@ -367,6 +382,7 @@ struct Engine {
   void voice_donate(Seq *s, VoiceEntry *v);
   int seq_alloc(int tokens_needed, Seq **out);
   void seq_free(Seq *s);
+  void release_stream_state(Request &r); // scheduler thread only
   int sync_pagetab(Seq *s);
 
   // passes (caller holds gpu_mu)
@@ -442,6 +458,7 @@ struct Request {
   int stream_seq = 0;     // deliveries issued
   int stream_applied = 0; // deliveries applied by the finishers (in order)
   int frames_ready = 0;   // PCM valid for frames [0, frames_ready)   (guarded by mu)
+  int stream_state = -1;  // Mimi K/V ring of a streaming request (-1: bounded re-decode window instead)
   std::chrono::steady_clock::time_point t_submit;
   int finished_at_iter = 0;
   // completion

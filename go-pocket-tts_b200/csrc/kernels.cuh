@@ -160,6 +160,21 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
                      int D, int n_heads, const int32_t *row_pos, int ctx,
                      cudaStream_t st, SplitOut sp = SplitOut());
 
+// Stateful streaming decode: the Mimi transformer's K (after RoPE) and V rows of a streaming
+// request live in a per-request ring [layer][MIMI_RING rows][K | V] indexed by absolute row % MIMI_RING, so a
+// delivery only runs its new rows (plus one frame of conv context) through the decoder: a row attends the
+// ring for keys older than its segment and the qkv buffer for keys inside it.
+//   row_apos[r] : absolute position of row r in its request (RoPE position), < 0 on pad rows
+//   row_seg[r]  : {ring slot of the request or -1, absolute position of the segment's first row,
+//                  buffer row of the segment's first row, unused}
+constexpr int MIMI_RING = 1024;
+constexpr int MIMI_ROPE_ROWS = 8192; // rows of the Mimi transformer's RoPE table
+int kv_ring_append(const float *qkv, int rows, int D, const int32_t *row_apos, const int4 *row_seg, float *ring,
+                   long state_stride, long layer_off, cudaStream_t st);
+int attention_window_stream(const float *qkv, long ldq, float *out, long ldo, int rows, int D, int n_heads,
+                            const int32_t *row_apos, const int4 *row_seg, const float *ring, long state_stride,
+                            long layer_off, int ctx, cudaStream_t st, SplitOut sp = SplitOut());
+
 // tcgen05 version (attention_tc.cu: flash-style, S and P.V accumulators in TMEM, split-bf16 operands,
 // head_dim 64); returns 0 without launching when the shape is not supported.
 int attention_window_tc(const float *qkv, long ldq, float *out, long ldo, int rows, int D,

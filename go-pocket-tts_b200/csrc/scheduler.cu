@@ -134,6 +134,13 @@ void Engine::finisher_loop() {
   }
 }
 
+void Engine::release_stream_state(Request &r) {
+  if (r.stream_state >= 0) {
+    free_stream_states.push_back(r.stream_state);
+    r.stream_state = -1;
+  }
+}
+
 void Engine::sched_loop() {
   cudaSetDevice(device);
   std::vector<std::shared_ptr<Request>> active, pending;
@@ -178,6 +185,7 @@ void Engine::sched_loop() {
     // ---- cancellation (ctx.Err() check per step, :156-159) ----
     for (size_t i = 0; i < active.size();) {
       if (active[i]->cancel) {
+        release_stream_state(*active[i]);
         seq_free(active[i]->seq);
         delete reinterpret_cast<ptts_seq *>(active[i]->seq);
         active[i]->seq = nullptr;
@@ -366,16 +374,40 @@ void Engine::sched_loop() {
         DecodeItem it;
         it.r = r;
         const int from = r->stream_issued, to = r->seq->frames;
-        it.first = from > wctx ? from - wctx : 0;
+        // Stateful delivery: the transformer's K/V of every earlier row sits in the request's ring, so only the
+        // new frames plus ONE frame of conv left context (16 rows >= the 8 rows the conv stack reaches back) go
+        // through the decoder.  Without a ring (none free, or a delivery too long for it): the bounded window.
+        if (r->stream_state < 0 && from == 0 && !free_stream_states.empty()) {
+          r->stream_state = free_stream_states.back();
+          free_stream_states.pop_back();
+        }
+        const int sctx = from > 0 ? 1 : 0;
+        if (r->stream_state >= 0 && (to - from + sctx) * up_stride <= MIMI_RING - Mctx && up_k <= 2 * up_stride &&
+            Mctx > 0 && to * up_stride <= MIMI_ROPE_ROWS) {
+          it.first = from - sctx;
+          it.ring = r->stream_state;
+          it.pre = it.first > 0 ? 1 : 0; // the context frame's rows take taps from the frame before it
+        } else {
+          if (r->stream_state >= 0) { // the ring has a gap from here on: give it back
+            free_stream_states.push_back(r->stream_state);
+            r->stream_state = -1;
+          }
+          it.first = from > wctx ? from - wctx : 0;
+        }
         it.skip = from - it.first;
         it.count = to - it.first;
         it.final = final;
         r->stream_issued = to;
+        if (final && r->stream_state >= 0) { // every later pass is ordered after this one on the Mimi stream
+          free_stream_states.push_back(r->stream_state);
+          r->stream_state = -1;
+        }
         deliveries.push_back(it);
       };
       for (size_t i = 0; i < active.size(); i++) {
         auto &r = active[i];
         if (failed[i]) {
+          release_stream_state(*r);
           seq_free(r->seq);
           delete reinterpret_cast<ptts_seq *>(r->seq);
           r->seq = nullptr;

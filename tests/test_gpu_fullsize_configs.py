@@ -122,6 +122,39 @@ def test_c2_long_chunk_teacher_forced_and_free_running(full_rt, full_oracle, pkg
     assert first_bad < 0, (first_bad, float(np.abs(got.latents - lat).max()))
 
 
+@pytest.mark.parametrize("stream_frames", [1, 4])
+def test_c2_streamed_per_frame_full_size(full_rt, full_oracle, pkg, stream_frames):
+    """C2 as the reference's stream handler delivers it: PCM out while the AR loop runs, the Mimi
+    transformer's K/V carried in the request's ring (window 250 rows = 15.6 frames; 160 frames = 2560 rows wrap the
+    1024-row ring).  The stream equals the oracle's whole-chunk waveform and the engine's own."""
+    toks = _tokens(50, 501)
+    n = 160
+    noise = pkg.make_noise(n, 0.7, 502)
+    kw = dict(max_steps=n, eos_threshold=1e30, force_eos_step=-1, frames_after_eos=0)
+    before = full_rt.stage_times()["mimi_frames"]
+    p = full_rt.submit(toks, pkg.RuntimeGenerateConfig(noise=noise, stream_frames=stream_frames, **kw))
+    have, pieces = 0, []
+    while True:
+        ready, done = full_rt.read(p, have)
+        if ready > have:
+            pieces.append(p.pcm[have * 1920: ready * 1920].copy())
+            have = ready
+        if done:
+            break
+    got = full_rt.wait(p, want_latents=True)
+    decoded = full_rt.stage_times()["mimi_frames"] - before
+    assert have == got.n_frames == n and len(pieces) >= n // stream_frames
+    assert decoded <= n + 2 * len(pieces) + 2, decoded  # not n * 33
+    stream = np.concatenate(pieces)
+    whole = full_rt.generate(toks, pkg.RuntimeGenerateConfig(noise=noise, **kw))
+    pcm, lat, _ = full_oracle.generate_audio(toks, noise=noise, **kw)
+    snr_self, snr = snr_db(whole.pcm, stream), snr_db(pcm, stream)
+    _report("C2_streamed", stream_frames=stream_frames, deliveries=len(pieces), mimi_frames_decoded=int(decoded),
+            snr_vs_whole_chunk_db=float(snr_self), snr_vs_oracle_db=float(snr))
+    assert allclose_ref(got.latents, lat, ABS, REL)
+    assert snr_self >= 60.0 and snr >= 40.0, (snr_self, snr)
+
+
 @pytest.mark.parametrize("batch", [64, 300])
 def test_c3_batched_step_full_size(full_rt, full_oracle, pkg, batch):
     """One batched AR step at real shapes: ragged prompts, two teacher-forced steps, the oracle

@@ -71,3 +71,81 @@ def test_stream_cancel_mid_flight(pkg, small_tensors):
         assert rt.generate_audio(_tokens(4, 4), pkg.RuntimeGenerateConfig(max_steps=2, eos_threshold=1e30)).shape == (3840,)
     finally:
         rt.close()
+
+
+def _stream_all(rt, p):
+    have, pieces = 0, []
+    while True:
+        ready, done = rt.read(p, have)
+        if ready > have:
+            pieces.append(p.pcm[have * 1920: ready * 1920].copy())
+            have = ready
+        if done:
+            return have, pieces
+
+
+@pytest.mark.parametrize("stream_frames", [1, 5])
+def test_stateful_stream_decodes_each_frame_once(pkg, small_tensors, stream_frames):
+    """Stateful deliveries (per-request K/V ring of the Mimi transformer): a delivery runs the
+    decoder over its new frames + ONE context frame (+ one latent for the upsampling taps), not over the
+    18-frame receptive field; 90 frames = 1440 rows wrap the 1024-row ring; the stream still equals the
+    whole-chunk decode."""
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=4, max_seq_tokens=256, max_frames=96,
+                               mimi_group_frames=96)
+    try:
+        toks = _tokens(9, 5)
+        n = 90
+        kw = dict(max_steps=n, eos_threshold=1e30, noise=pkg.make_noise(n, 0.7, 6))
+        whole = rt.generate(toks, pkg.RuntimeGenerateConfig(**kw))
+        before = rt.stage_times()["mimi_frames"]
+        p = rt.submit(toks, pkg.RuntimeGenerateConfig(stream_frames=stream_frames, **kw))
+        have, pieces = _stream_all(rt, p)
+        got = rt.wait(p)
+        decoded = rt.stage_times()["mimi_frames"] - before
+        assert have == got.n_frames == n
+        deliveries = -(-n // stream_frames)
+        assert decoded <= n + 2 * deliveries, (decoded, n, deliveries)  # the windowed path re-decodes ~18 per delivery
+        stream = np.concatenate(pieces)
+        assert snr_db(whole.pcm, stream) >= 60.0, snr_db(whole.pcm, stream)
+        np.testing.assert_array_equal(stream, got.pcm)
+    finally:
+        rt.close()
+
+
+def test_stateful_streams_share_passes_and_recycle_rings(pkg, small_tensors):
+    """More concurrent streams than... rings are per request and recycled: 3 waves of 4 streaming requests next to
+    whole-chunk ones; every stream equals its whole-chunk decode."""
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=8, max_seq_tokens=256, max_frames=64,
+                               mimi_group_frames=128)
+    try:
+        for wave in range(3):
+            cfgs = [dict(max_steps=20 + 3 * i, eos_threshold=1e30, seed=10 * wave + i) for i in range(4)]
+            toks = [_tokens(6 + i, 100 + 10 * wave + i) for i in range(4)]
+            ps = [rt.submit(toks[i], pkg.RuntimeGenerateConfig(stream_frames=1 + i, **cfgs[i])) for i in range(4)]
+            plain = [rt.submit(toks[i], pkg.RuntimeGenerateConfig(**cfgs[i])) for i in range(4)]
+            outs = [rt.wait(p) for p in ps]
+            refs = [rt.wait(p) for p in plain]
+            for o, r in zip(outs, refs):
+                assert o.n_frames == r.n_frames
+                assert snr_db(r.pcm, o.pcm) >= 60.0, snr_db(r.pcm, o.pcm)
+    finally:
+        rt.close()
+
+
+def test_windowed_stream_without_rings(pkg, small_tensors, monkeypatch):
+    """PTTS_NO_STREAM_STATE=1: the bounded re-decode window of round 2's first streaming path still works."""
+    monkeypatch.setenv("PTTS_NO_STREAM_STATE", "1")
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=256, max_frames=64,
+                               mimi_group_frames=64)
+    try:
+        toks = _tokens(7, 8)
+        kw = dict(max_steps=40, eos_threshold=1e30, seed=3)
+        whole = rt.generate(toks, pkg.RuntimeGenerateConfig(**kw))
+        before = rt.stage_times()["mimi_frames"]
+        p = rt.submit(toks, pkg.RuntimeGenerateConfig(stream_frames=1, **kw))
+        _stream_all(rt, p)
+        got = rt.wait(p)
+        assert rt.stage_times()["mimi_frames"] - before > 5 * 40
+        assert snr_db(whole.pcm, got.pcm) >= 60.0
+    finally:
+        rt.close()
