@@ -1546,6 +1546,21 @@ int Engine::setup_fused() {
   fused_grid = step_fused_grid(fused_smem, fused_ll);
   if (fused_grid <= 0)
     return PTTS_OK; // cannot be resident: keep the multi-kernel path
+  {
+    // the weight-ring kernel: bulk copies need 16-byte aligned rows
+    const char *v = getenv("PTTS_FUSED_RING");
+    fused_ring = v ? atoi(v) != 0 : FUSED_RING_DEFAULT;
+    auto al = [](const float *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    bool ok = al(hp.ce_w) && al(hp.ada_w) && al(hp.fin_w);
+    for (int l = 0; l < L; l++)
+      ok = ok && al(hp.layer[l].in_proj) && al(hp.layer[l].out_proj) && al(hp.layer[l].l1) && al(hp.layer[l].l2);
+    for (int b = 0; b < depth; b++)
+      ok = ok && al(hp.rb[b].mlp0w) && al(hp.rb[b].mlp2w);
+    if (fused_ring && ok)
+      ring_grid = step_ring_grid(fused_smem, &ring_slots, &ring_smem);
+    if (!ok || ring_grid <= 0)
+      fused_ring = false;
+  }
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
   if (!coop)
@@ -1935,8 +1950,12 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
     int rc = get_tvec(lsd_steps, &tv);
     if (rc)
       return rc;
-    const int n = step_fused_launch(d_fused, fused_grid, fused_smem, d_row_slot, d_row_pos, d_off_a, d_off_b, d_off_c,
-                                    gather_frames ? 1 : 0, gather_noise ? 1 : 0, tv, lsd_steps, d_fused_bar, fused_ll, st);
+    const int n =
+        fused_ring
+            ? step_ring_launch(d_fused, ring_grid, ring_smem, ring_slots, d_row_slot, d_row_pos, d_off_a, d_off_b, d_off_c,
+                               gather_frames ? 1 : 0, gather_noise ? 1 : 0, tv, lsd_steps, d_fused_bar, st)
+            : step_fused_launch(d_fused, fused_grid, fused_smem, d_row_slot, d_row_pos, d_off_a, d_off_b, d_off_c,
+                                gather_frames ? 1 : 0, gather_noise ? 1 : 0, tv, lsd_steps, d_fused_bar, fused_ll, st);
     if (n < 0) {
       cudaGetLastError();
       PTTS_FAIL(PTTS_ECUDA, "cuda: cooperative launch of the fused frame kernel failed");

@@ -15,6 +15,7 @@ struct FusedRes {
 constexpr int FUSED_MAX_LAYERS = 8;
 // default frame kernel when PTTS_FUSED_LL is unset (flag-in-data exchange vs grid barriers)
 constexpr bool FUSED_LL_DEFAULT = false;
+constexpr bool FUSED_RING_DEFAULT = false; // PTTS_FUSED_RING: the weight-ring frame kernel (step_ring.cu)
 constexpr int FUSED_L2_AHEAD_DEFAULT = 0; // PTTS_FUSED_L2_AHEAD: weight phases prefetched into L2 ahead of use
 constexpr size_t STEP_FUSED_BARRIER_BYTES = 8192; // top + per-group counters, 128 B apart (<= 63 groups)
 
@@ -60,5 +61,14 @@ int step_fused_grid(size_t smem, bool ll);
 int step_fused_launch(const FusedParams *dp, int grid, size_t smem, const int32_t *row_slot, const int32_t *row_pos,
                       const int64_t *off_a, const int64_t *off_b, const int64_t *off_c, int gather_frames,
                       int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier, bool ll, cudaStream_t st);
+
+// The weight-ring variant (step_ring.cu): one CTA per SM, the frame's weights streamed through a shared-memory
+// ring by bulk copies.  step_ring_grid returns the CTAs (0: cannot run) and the ring slots / dynamic shared
+// memory for an activation area of `act_bytes` (= step_fused_smem).
+int step_ring_grid(size_t act_bytes, int *slots, size_t *smem);
+int step_ring_launch(const FusedParams *dp, int grid, size_t smem, int slots, const int32_t *row_slot,
+                     const int32_t *row_pos, const int64_t *off_a, const int64_t *off_b, const int64_t *off_c,
+                     int gather_frames, int gather_noise, const float *tvec, int lsd_steps, unsigned *barrier,
+                     cudaStream_t st);
 
 } // namespace ptts

@@ -139,3 +139,30 @@ def test_fused_frame_kernel_variants_agree(pkg, full_tensors, monkeypatch):
         assert np.all(np.abs(a.latents - b.latents) <= 1e-5 + 1e-4 * np.abs(b.latents)), \
             (lsd, np.abs(a.latents - b.latents).max())
         assert snr_db(b.pcm, a.pcm) >= 60.0
+
+
+def test_weight_ring_frame_kernel_is_bit_identical(pkg, full_tensors, monkeypatch):
+    """PTTS_FUSED_RING=1: the frame's weights arrive through the shared-memory ring (bulk copies issued by a
+    producer thread, step_ring.cu) instead of register loads; rows belong to other warps but every dot product,
+    chunk order and reduction is the one of the grid-barrier kernel, so 24 fed-back frames are bit-identical
+    (1 and 2 LSD steps), and the oracle tolerance holds through it."""
+    toks = _tokens(22, 11)
+
+    def run(lsd):
+        rt = pkg.NativeCudaRuntime(tensors=full_tensors, max_batch=4, max_seq_tokens=256, max_frames=64,
+                                   mimi_group_frames=64)
+        try:
+            return rt.generate(toks, _cfg(pkg, 24, 20, 12, lsd_decode_steps=lsd), want_latents=True)
+        finally:
+            rt.close()
+
+    for lsd in (1, 2):
+        monkeypatch.setenv("PTTS_FUSED_LL", "0")
+        monkeypatch.setenv("PTTS_FUSED_RING", "0")
+        b = run(lsd)
+        monkeypatch.setenv("PTTS_FUSED_RING", "1")
+        a = run(lsd)
+        assert a.n_frames == b.n_frames == 23
+        np.testing.assert_array_equal(a.latents, b.latents)
+        np.testing.assert_array_equal(a.eos_logits, b.eos_logits)
+        np.testing.assert_array_equal(a.pcm, b.pcm)

@@ -653,3 +653,26 @@ def test_tcgen05_window_attention_matches_default_and_oracle(pkg, small_tensors,
         want = small_oracle.decode_latents(lat[off:off + nfr])
         assert snr_db(want, outs["tc"][off * 1920:(off + nfr) * 1920]) >= 40.0
         off += nfr
+
+
+def test_weight_ring_frame_kernel_small_model(pkg, small_tensors, monkeypatch):
+    """step_ring.cu on the small architecture (rows shorter than a ring slot, fewer rows than CTAs in most
+    phases): bit-identical to the grid-barrier frame kernel."""
+    toks = np.random.default_rng(5).integers(0, 4000, size=9).astype(np.int64)
+
+    def run():
+        rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=2, max_seq_tokens=256, max_frames=64,
+                                   mimi_group_frames=64)
+        try:
+            cfg = pkg.RuntimeGenerateConfig(max_steps=30, eos_threshold=1e30, seed=4, lsd_decode_steps=2)
+            return rt.generate(toks, cfg, want_latents=True)
+        finally:
+            rt.close()
+
+    monkeypatch.setenv("PTTS_FUSED_RING", "0")
+    b = run()
+    monkeypatch.setenv("PTTS_FUSED_RING", "1")
+    a = run()
+    assert a.n_frames == b.n_frames == 30
+    np.testing.assert_array_equal(a.latents, b.latents)
+    np.testing.assert_array_equal(a.pcm, b.pcm)
