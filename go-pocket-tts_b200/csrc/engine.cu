@@ -209,11 +209,15 @@ int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, i
   if (!tc_on || K % 8 != 0 || N % 16 != 0 || K < 32 || N < 32)
     return PTTS_OK; // stays on the CUDA-core path
   std::vector<uint16_t> sp((size_t)2 * N * K);
+  bool lo_zero = true;
   for (size_t i = 0; i < (size_t)N * K; i++) {
     uint16_t h = f32_to_bf16_rn(w[i]);
     sp[i] = h;
-    sp[(size_t)N * K + i] = f32_to_bf16_rn(w[i] - bf16_to_f32(h));
+    const uint16_t lo = f32_to_bf16_rn(w[i] - bf16_to_f32(h));
+    sp[(size_t)N * K + i] = lo;
+    lo_zero = lo_zero && (lo & 0x7fffu) == 0;
   }
+  const bool no_fast = getenv("PTTS_NO_BF16_FAST") != nullptr;
   void *d = nullptr;
   int rc = dmalloc(&d, sp.size() * 2);
   if (rc)
@@ -224,6 +228,9 @@ int Engine::make_tc(const float *d_w_fp32, const std::vector<float> &w, int N, i
   int r = tc_weight_init(t, d, N, K);
   if (r)
     PTTS_FAIL(PTTS_ECUDA, "native-cuda: cuTensorMapEncodeTiled failed (%d) for a [%d,%d] weight", r, N, K);
+  t->lo_zero = lo_zero && !no_fast;
+  if (t->lo_zero)
+    n_bf16_exact++;
   tc_map[d_w_fp32] = t;
   return PTTS_OK;
 }

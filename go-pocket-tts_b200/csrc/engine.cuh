@@ -184,6 +184,7 @@ struct Engine {
   int fused_grid = 0;
   size_t fused_smem = 0;
   bool fused_on = false, fused_ll = true;
+  int n_bf16_exact = 0; // weights whose lo plane is zero (2-product GEMMs, hi plane only)
   bool fused_ring = false; // PTTS_FUSED_RING: the frame kernel with the shared-memory weight ring (step_ring.cu)
   int ring_grid = 0, ring_slots = 0;
   size_t ring_smem = 0;

@@ -80,6 +80,9 @@ struct alignas(64) TcWeight {
   unsigned char map32[128], map64[128], map128[128], map256[128];
   const void *d_split = nullptr;
   int N = 0, K = 0;
+  // every weight is exactly a bf16 value (a checkpoint stored as BF16, store.go:339-395): the lo plane is
+  // all zero, so the TMA-fed kernels skip it — two products per k-block, half the weight stream
+  bool lo_zero = false;
 };
 int tc_weight_init(TcWeight *w, const void *d_split, int N, int K);
 // TMA map (128-byte blob, 64-byte aligned) over split activation planes: `base` points at

@@ -97,7 +97,9 @@ struct TcItems {
 // main loop of item i+1; the smem operand ring runs straight through item boundaries.
 // ATMA: A is already split into bf16 planes behind `amap`; the TMA warp fetches both
 // operands and the converter warps are not launched.
-template <int BN, int STAGES, bool ATMA, int EW>
+// WLO = false (own instantiations, TMA-fed only): the weight's lo plane is identically zero and is neither
+// fetched nor multiplied — Ahi*Wlo would add exact zeros, so the result is bit-identical to the 3-product form.
+template <int BN, int STAGES, bool ATMA, int EW, bool WLO = true>
 __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap amap, GemmArgs g,
                    int n_rows_hi, TcItems items) {
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
           uint8_t *st = smem + s * SM::STAGE;
           if (it < 32)
             TC_STAMP(96 + it);
-          mbar_arrive_expect_tx(&full[s], 2 * SM::W_TILE + (ATMA ? 2 * SM::A_TILE : 0));
+          mbar_arrive_expect_tx(&full[s], (WLO ? 2 : 1) * SM::W_TILE + (ATMA ? 2 * SM::A_TILE : 0));
           const int k0 = (kb_begin + kb) * TC_BK;
           if (ATMA) {
             if (waited)
@@ -200,7 +202,8 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             }
           }
           tma_load_2d(st + 2 * SM::A_TILE, &wmap, &full[s], k0, n0);
-          tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], k0, n_rows_hi + n0);
+          if (WLO)
+            tma_load_2d(st + 2 * SM::A_TILE + SM::W_TILE, &wmap, &full[s], k0, n_rows_hi + n0);
         }
       }
       if (!waited)
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
             const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
             const uint64_t dwh = make_smem_desc(w_hi + ko), dwl = make_smem_desc(w_lo + ko);
             umma_bf16(tmem_d, dal, dwh, idesc, (kb | k) != 0);
-            umma_bf16(tmem_d, dah, dwl, idesc, 1);
+            if (WLO)
+              umma_bf16(tmem_d, dah, dwl, idesc, 1);
             umma_bf16(tmem_d, dah, dwh, idesc, 1);
           }
           umma_commit(&empty[s]); // frees the smem stage once these MMAs have read it
@@ -778,13 +782,13 @@ int tc_cluster_capacity(int bn, int cs) {
   }
 }
 
-template <int BN, int STAGES, bool ATMA, int EW = 4>
+template <int BN, int STAGES, bool ATMA, int EW = 4, bool WLO = true>
 int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES, EW>;
   static volatile bool configured[64] = {};
   volatile bool &conf = device_flag(configured);
   if (!conf) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ATMA, EW, WLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES) != cudaSuccess)
       return -1;
     conf = true;
   }
@@ -814,12 +818,14 @@ int launch_tc_a(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
                    : 0;
   const int grid = (int)(it.total < tc_num_sms() ? it.total : tc_num_sms());
   const CUtensorMap *am = ATMA ? reinterpret_cast<const CUtensorMap *>(g.amap) : map;
-  launch_kc(tc_gemm_kernel<BN, STAGES, ATMA, EW>, dim3(grid), dim3(tc_threads(EW, ATMA)), SM::BYTES, st,
+  launch_kc(tc_gemm_kernel<BN, STAGES, ATMA, EW, WLO>, dim3(grid), dim3(tc_threads(EW, ATMA)), SM::BYTES, st,
             it.cluster ? S : 1, *map, *am, g, w.N, it);
   return 1;
 }
 template <int BN, int STAGES>
 int launch_tc(const TcWeight &w, const GemmArgs &g, int S, cudaStream_t st) {
+  if (g.amap && w.lo_zero)
+    return launch_tc_a<BN, STAGES, true, 4, false>(w, g, S, st);
   return g.amap ? launch_tc_a<BN, STAGES, true>(w, g, S, st) : launch_tc_a<BN, STAGES, false>(w, g, S, st);
 }
 // Short-K TMA-fed shapes (the SEANet tail): the epilogue is the bottleneck, so it gets
@@ -991,18 +997,19 @@ int tc_gemm(const TcWeight &w, const GemmArgs &g, cudaStream_t st, const char **
     *variant = "tcgen05_128x64_ew8";
     return launch_tc_ew8<64, 3>(w, g, S, st);
   }
+  const bool w1 = g.amap && w.lo_zero; // bf16-exact weight: hi plane only
   switch (bn) {
   case 256:
-    *variant = "tcgen05_128x256";
+    *variant = w1 ? "tcgen05_128x256_bf16w" : "tcgen05_128x256";
     return launch_tc<256, 2>(w, g, S, st);
   case 128:
-    *variant = "tcgen05_128x128";
+    *variant = w1 ? "tcgen05_128x128_bf16w" : "tcgen05_128x128";
     return launch_tc<128, 3>(w, g, S, st);
   case 64:
-    *variant = "tcgen05_128x64";
+    *variant = w1 ? "tcgen05_128x64_bf16w" : "tcgen05_128x64";
     return launch_tc<64, 4>(w, g, S, st);
   default:
-    *variant = "tcgen05_128x32";
+    *variant = w1 ? "tcgen05_128x32_bf16w" : "tcgen05_128x32";
     return launch_tc<32, 4>(w, g, S, st);
   }
 }

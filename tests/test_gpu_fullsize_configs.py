@@ -240,3 +240,70 @@ def test_f16_and_bf16_load_tensor_widening(pkg, ck, small_tensors):
         h = run(exact, dtype)
         np.testing.assert_array_equal(a.latents, h.latents)
         np.testing.assert_array_equal(a.pcm, h.pcm)
+
+
+def test_bf16_exact_checkpoint_takes_the_two_product_path(pkg, ck, orc, full_tensors, monkeypatch):
+    """A checkpoint whose weights are exactly bf16 values (stored as BF16 and widened by the loader,
+    store.go:339-395): the weights' lo planes are zero, so the TMA-fed GEMMs skip them — two products per
+    k-block, half the weight stream.  Bit-identical to the three-product kernels on the same
+    weights (Ahi * 0 adds exact zeros), inside the tolerance against the oracle on the same weights, and the
+    kernel classes of a profiled step show the `_bf16w` instantiations."""
+    tensors = ck.to_bf16_exact(full_tensors)
+    batch = 64
+    rng = np.random.default_rng(batch)
+    lens = rng.integers(5, 51, batch)
+    toks = [_tokens(int(lens[b]), 9000 + b) for b in range(batch)]
+    noise = [pkg.make_noise(batch, 0.7, 70 + step) for step in range(2)]
+
+    def run(profile):
+        rt = pkg.NativeCudaRuntime(tensors=tensors, max_batch=128, max_seq_tokens=128, max_frames=16,
+                                   mimi_group_frames=64)
+        seqs = []
+        try:
+            seqs = [rt.seq_open(t, reserve_frames=4) for t in toks]
+            frames = np.full((batch, 32), np.nan, np.float32)
+            outs = []
+            for step in range(2):
+                if profile and step == 1:
+                    rt.profile(True)
+                lat, eos = rt.step(seqs, noise[step], frames_in=frames)
+                outs.append((lat.copy(), eos.copy()))
+                frames = lat
+            rep = rt.profile_report() if profile else {}
+            pcm = seqs[3].decode(0, 2)
+            return outs, rep, pcm
+        finally:
+            for s in seqs:
+                s.close()
+            rt.close()
+
+    fast, rep, pcm_fast = run(True)
+    assert any(k.endswith("_bf16w") for k in rep), sorted(rep)
+    assert not any(k.startswith("tcgen05_128x") and not k.endswith("_bf16w") and "ew8" not in k
+                   and rep[k].get("launches", 0) > 0 and k in ("tcgen05_128x32", "tcgen05_128x64", "tcgen05_128x128")
+                   for k in rep), sorted(rep)
+    monkeypatch.setenv("PTTS_NO_BF16_FAST", "1")
+    slow, _, pcm_slow = run(False)
+    for (la, ea), (lb, eb) in zip(fast, slow):
+        np.testing.assert_array_equal(la, lb)
+        np.testing.assert_array_equal(ea, eb)
+    np.testing.assert_array_equal(pcm_fast, pcm_slow)
+    # the oracle on the same (rounded) weights, 4 sampled rows, teacher-forced
+    orc.set_workers(os.cpu_count() or 1)
+    try:
+        om = orc.OracleModel(tensors)
+        frames = np.full((batch, 32), np.nan, np.float32)
+        states = {}
+        for b in (0, 17, 40, 63):
+            st = om.new_state()
+            st.prompt(om.text_embeddings(toks[b]))
+            states[b] = st
+        for step in range(2):
+            lat, eos = fast[step]
+            for b, st in states.items():
+                wl_, we, _ = st.step(frames[b], noise[step][b])
+                assert allclose_ref(lat[b], wl_, ABS, REL), (step, b, float(np.abs(lat[b] - wl_).max()))
+                assert abs(eos[b] - we) <= 5e-4 + REL * abs(we), (step, b)
+            frames = lat  # free-running rows: the oracle follows the engine's latents
+    finally:
+        orc.set_workers(1)

@@ -9,7 +9,10 @@ ck = importlib.import_module("pockettts_b200.checkpoint")
 wl = importlib.import_module("pockettts_b200.workload")
 import numpy as np
 Bs = [int(a) for a in sys.argv[1:]] or [1, 256]
-rt = pkg.NativeCudaRuntime(tensors=ck.make_checkpoint(ck.ArchConfig.full()), max_batch=max(Bs), max_seq_tokens=512,
+tensors = ck.make_checkpoint(ck.ArchConfig.full())
+if os.environ.get("STEP_BENCH_BF16_EXACT"):  # a checkpoint stored as BF16: the two-product GEMM instantiations
+    tensors = ck.to_bf16_exact(tensors)
+rt = pkg.NativeCudaRuntime(tensors=tensors, max_batch=max(Bs), max_seq_tokens=512,
                            max_frames=256, mimi_group_frames=64)
 c2 = wl.paragraph_200_words()[0]
 rng = np.random.default_rng(1)
