@@ -10,7 +10,5 @@ $B > $O/plainB.log 2>&1 && timeout 600 ncu --set full --clock-control none --imp
 ncu -i /tmp/tc.ncu-rep --page raw --csv > $O/tcstep_r02_raw.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_paged_decode -s 60 -c 2 -f -o /tmp/at $B > $O/ncu_at.log 2>&1
 ncu -i /tmp/at.ncu-rep --page raw --csv > $O/attn_r02_raw.csv 2>/dev/null
-ncu -i /tmp/at.ncu-rep --page source --csv > /tmp/at_src.csv 2>/dev/null
-python tools/ncu_hot.py /tmp/at_src.csv 30 > $O/attn_r02_hot.txt 2>&1
-rm -f /tmp/tc.ncu-rep /tmp/at.ncu-rep /tmp/at_src.csv
+rm -f /tmp/tc.ncu-rep /tmp/at.ncu-rep
 du -sh $O
