@@ -24,7 +24,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libpockettts_cuda.so")
-CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "attention_tc.cu", "attention_mma.cu", "step_fused.cu", "step_ring.cu", "flow_head.cu", "resblock.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "pool.cu", "safetensors.cpp"]
+CSRC = ["gemm.cu", "tcgemm.cu", "attention.cu", "attention_decode.cu", "attention_tc.cu", "attention_mma.cu", "step_fused.cu", "step_ring.cu", "flow_head.cu", "resblock.cu", "elementwise.cu", "engine.cu", "scheduler.cu", "pool.cu", "safetensors.cpp"]
 
 PTTS_OK, PTTS_EINVAL, PTTS_ECUDA, PTTS_ENOMEM, PTTS_ESTATE, PTTS_ECANCELED = 0, -1, -2, -3, -4, -5
 PTTS_REQ_NO_PCM_D2H = 1

@@ -23,11 +23,11 @@
 
 namespace ptts {
 
-template <typename KT>
+template <typename KT, bool POW2>
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_kernel(const float *qkv, long ldq, float *out, long ldo,
                            const int32_t *row_slot, const int32_t *row_pos,
-                           KvGeom kv, int layer, SplitOut sp) {
+                           KvGeom kv, int layer, int pt_shift, SplitOut sp) {
   PDL_TRIGGER();
   PDL_WAIT();
   extern __shared__ float smem[];
@@ -53,10 +53,15 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * PT * HD;
   const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * PT * HD;
   const KT *pool = static_cast<const KT *>(kv.pool);
+  const int pmask = PT - 1; // POW2: PT == 1 << pt_shift (see attention_paged_decode_kernel)
   auto keyp = [&](int j) {
+    if (POW2)
+      return pool + (long)pt[j >> pt_shift] * page_stride + koff + ((j & pmask) << 6);
     return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
   };
   auto valp = [&](int j) {
+    if (POW2)
+      return pool + (long)pt[j >> pt_shift] * page_stride + voff + ((j & pmask) << 6);
     return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
   };
   attend_row(qkv + (long)r * ldq + h * HD, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
@@ -68,11 +73,13 @@ __global__ void __launch_bounds__(ATT_THREADS)
 // of its head into the sequence's page, and then attends over the cache, its own token included.
 // Only valid when no other row of the launch belongs to the same sequence (the prefill keeps the
 // separate append kernel: there a row also reads keys written by other CTAs).
-template <typename KT>
+// POW2: the page size is a power of two, 1 << pt_shift (key -> page / row by shift and mask; the integer
+// divisions by a run-time page size were a third of the instructions this issue-bound kernel executes).
+template <typename KT, bool POW2>
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_decode_kernel(const float *qkv, long ldq, float *out, long ldo,
                                   const int32_t *row_slot, const int32_t *row_pos, const float *cosT,
-                                  const float *sinT, KvGeom kv, int layer, SplitOut sp) {
+                                  const float *sinT, KvGeom kv, int layer, int pt_shift, SplitOut sp) {
   PDL_TRIGGER();
   PDL_WAIT();
   extern __shared__ float smem[];
@@ -104,9 +111,11 @@ __global__ void __launch_bounds__(ATT_THREADS)
   __shared__ int32_t s_pt[512];
   for (int i = tid; i * PT < nkeys; i += ATT_THREADS)
     s_pt[i] = pt[i];
+  const int pmask = PT - 1;
   {
     const float *row = qkv + (long)r * ldq;
-    KT *page = pool + (long)pt[pos / PT] * page_stride + (long)(pos % PT) * HD;
+    KT *page = pool + (long)pt[POW2 ? pos >> pt_shift : pos / PT] * page_stride +
+               (long)(POW2 ? pos & pmask : pos % PT) * HD;
     if (tid < HD) { // pairs (2j, 2j+1): threads 0..31 rotate q, 32..63 rotate k
       const int isk = tid >= HD / 2, j = tid & (HD / 2 - 1);
       const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
@@ -127,11 +136,16 @@ __global__ void __launch_bounds__(ATT_THREADS)
     }
   }
   __syncthreads(); // q and the page ids in shared memory; this CTA's own k/v stores are visible to its loads below
+  const KT *kbase = pool + koff, *vbase = pool + voff;
   auto keyp = [&](int j) {
-    return pool + (long)s_pt[j / PT] * page_stride + koff + (long)(j % PT) * HD;
+    if (POW2)
+      return kbase + (long)s_pt[j >> pt_shift] * page_stride + ((j & pmask) << 6);
+    return kbase + (long)s_pt[j / PT] * page_stride + (long)(j % PT) * HD;
   };
   auto valp = [&](int j) {
-    return pool + (long)s_pt[j / PT] * page_stride + voff + (long)(j % PT) * HD;
+    if (POW2)
+      return vbase + (long)s_pt[j >> pt_shift] * page_stride + ((j & pmask) << 6);
+    return vbase + (long)s_pt[j / PT] * page_stride + (long)(j % PT) * HD;
   };
   attend_row(qs, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
 }
@@ -323,6 +337,16 @@ __global__ void __launch_bounds__(ATT_THREADS)
   }
 }
 
+// log2 of a power-of-two page size, -1 otherwise
+static int page_shift(int PT) {
+  if (PT <= 0 || (PT & (PT - 1)) != 0)
+    return -1;
+  int s = 0;
+  while ((1 << s) < PT)
+    s++;
+  return s;
+}
+
 int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
                     const int32_t *row_slot, const int32_t *row_pos,
                     const KvGeom &kv, int layer, int max_keys, cudaStream_t st, SplitOut sp) {
@@ -330,12 +354,19 @@ int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
     return 0;
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
-  if (kv.half)
-    launch_k(attention_paged_kernel<__half>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv,
-             layer, sp);
+  const int pt_shift = page_shift(kv.page_tokens);
+  if (kv.half && pt_shift >= 0)
+    launch_k(attention_paged_kernel<__half, true>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos,
+             kv, layer, pt_shift, sp);
+  else if (kv.half)
+    launch_k(attention_paged_kernel<__half, false>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, kv, layer, 0, sp);
+  else if (pt_shift >= 0)
+    launch_k(attention_paged_kernel<float, true>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos,
+             kv, layer, pt_shift, sp);
   else
-    launch_k(attention_paged_kernel<float>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos, kv,
-             layer, sp);
+    launch_k(attention_paged_kernel<float, false>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot, row_pos,
+             kv, layer, 0, sp);
   return 1;
 }
 
@@ -344,14 +375,30 @@ int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int
                            int max_keys, cudaStream_t st, SplitOut sp) {
   if (rows <= 0)
     return 0;
+  // opt-in: K / V staged through shared memory by cp.async (attention_decode.cu).  Bit-identical; per launch it
+  // sits between the old and the new register kernel (64 vs 69 / 57 us at B = 512) and its 34 KB of shared
+  // memory per CTA keep the next GEMM's CTAs off the SM until the last attention CTA has left.
+  if (kv.half && getenv("PTTS_ATTN_STAGED") != nullptr) {
+    const int n = attention_paged_decode_staged(qkv, ldq, out, ldo, rows, row_slot, row_pos, cosT, sinT, kv, layer,
+                                                max_keys, st, sp);
+    if (n > 0)
+      return n;
+  }
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
-  if (kv.half)
-    launch_k(attention_paged_decode_kernel<__half>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
-             row_pos, cosT, sinT, kv, layer, sp);
+  const int pt_shift = page_shift(kv.page_tokens);
+  if (kv.half && pt_shift >= 0)
+    launch_k(attention_paged_decode_kernel<__half, true>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, cosT, sinT, kv, layer, pt_shift, sp);
+  else if (kv.half)
+    launch_k(attention_paged_decode_kernel<__half, false>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, cosT, sinT, kv, layer, 0, sp);
+  else if (pt_shift >= 0)
+    launch_k(attention_paged_decode_kernel<float, true>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, cosT, sinT, kv, layer, pt_shift, sp);
   else
-    launch_k(attention_paged_decode_kernel<float>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
-             row_pos, cosT, sinT, kv, layer, sp);
+    launch_k(attention_paged_decode_kernel<float, false>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
+             row_pos, cosT, sinT, kv, layer, 0, sp);
   return 1;
 }
 

@@ -25,7 +25,10 @@ const char *last_error() { return g_err; }
 int Engine::create(const ptts_config *c) {
   cfg = *c;
   if (cfg.max_batch <= 0) cfg.max_batch = 256;
-  if (cfg.page_tokens <= 0) cfg.page_tokens = 16;
+  if (cfg.page_tokens <= 0) {
+    const char *pt = getenv("PTTS_PAGE_TOKENS"); // experiments: K / V rows of one head are contiguous per page
+    cfg.page_tokens = pt && atoi(pt) > 0 ? atoi(pt) : 16;
+  }
   if (cfg.max_seq_tokens <= 0) cfg.max_seq_tokens = 1024;
   if (cfg.max_seq_tokens > 8192)
     PTTS_FAIL(PTTS_EINVAL, "native-cuda: max_seq_tokens %d exceeds the RoPE table (8192)",

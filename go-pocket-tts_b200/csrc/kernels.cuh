@@ -152,6 +152,10 @@ int attention_paged(const float *qkv, long ldq, float *out, long ldo, int rows,
 int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int rows, const int32_t *row_slot,
                            const int32_t *row_pos, const float *cosT, const float *sinT, const KvGeom &kv, int layer,
                            int max_keys, cudaStream_t st, SplitOut sp = SplitOut());
+// The same with the K / V rows staged through shared memory by cp.async (attention_decode.cu); 0: not applicable.
+int attention_paged_decode_staged(const float *qkv, long ldq, float *out, long ldo, int rows, const int32_t *row_slot,
+                           const int32_t *row_pos, const float *cosT, const float *sinT, const KvGeom &kv, int layer,
+                           int max_keys, cudaStream_t st, SplitOut sp = SplitOut());
 
 // RoPE in place on q and k of qkv [R, 3*D] with per-row positions (<0 = skip).
 int rope_inplace(float *qkv, int rows, int D, int n_heads, const int32_t *row_pos,

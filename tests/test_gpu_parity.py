@@ -676,3 +676,27 @@ def test_weight_ring_frame_kernel_small_model(pkg, small_tensors, monkeypatch):
     assert a.n_frames == b.n_frames == 30
     np.testing.assert_array_equal(a.latents, b.latents)
     np.testing.assert_array_equal(a.pcm, b.pcm)
+
+
+def test_staged_decode_attention_is_bit_identical(pkg, small_tensors, monkeypatch):
+    """PTTS_ATTN_STAGED=1: decode attention with the K / V rows staged through shared memory by cp.async
+    (attention_decode.cu) against the register kernel: same latents and PCM bit for bit, batch of 24 ragged
+    requests, 70 frames (kv up to ~90 keys: two 64-key tiles and the ring wrap of the value tiles)."""
+    rng = np.random.default_rng(3)
+    toks = [rng.integers(0, 4000, size=int(n)).astype(np.int64) for n in rng.integers(4, 20, 24)]
+
+    def run():
+        rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=32, max_seq_tokens=256, max_frames=80,
+                                   mimi_group_frames=256)
+        try:
+            ps = [rt.submit(t, pkg.RuntimeGenerateConfig(max_steps=70, eos_threshold=1e30, seed=i)) for i, t in enumerate(toks)]
+            return [rt.wait(p, want_latents=True) for p in ps]
+        finally:
+            rt.close()
+
+    a = run()
+    monkeypatch.setenv("PTTS_ATTN_STAGED", "1")
+    b = run()
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x.latents, y.latents)
+        np.testing.assert_array_equal(x.pcm, y.pcm)
