@@ -75,7 +75,124 @@ __global__ void __launch_bounds__(ATT_THREADS)
 // separate append kernel: there a row also reads keys written by other CTAs).
 // POW2: the page size is a power of two, 1 << pt_shift (key -> page / row by shift and mask; the integer
 // divisions by a run-time page size were a third of the instructions this issue-bound kernel executes).
-template <typename KT, bool POW2>
+// Pages of exactly 16 tokens (the default): one (row, head) of decode attention with the loops written per page —
+// a score pass is one page (one page-table lookup, no per-key guard), a value step two pages (four rows in
+// flight); the partial last page is the only guarded part.  Same thread-to-element assignment, summation order
+// and softmax as attend_row (attend.cuh): bit-identical output.  The kernel is issue-bound, so what this removes
+// (address updates, guards, page lookups per key) is time.
+template <typename KT>
+__device__ __forceinline__ void attend_row_pages16(const float *q, int nkeys, const KT *kbase, const KT *vbase,
+                                                   const int32_t *s_pt, long page_stride, float *out, float *scores,
+                                                   float *red, float4 *pv, const SplitOut &sp, long sp_row, int sp_col) {
+  const int tid = threadIdx.x;
+  const float scale = 0.125f; // 1/sqrt(64)
+  const int npg = nkeys >> 4, rem = nkeys & 15;
+  // ---- scores ----
+  const int part = tid & 7, kslot = tid >> 3;
+  const float4 q0 = *reinterpret_cast<const float4 *>(q + part * 8);
+  const float4 q1 = *reinterpret_cast<const float4 *>(q + part * 8 + 4);
+  const KT *krow = kbase + kslot * HD + part * 8;
+  auto dot8 = [&](const KT *p) {
+    float k[8];
+    kv_load8(p, k);
+    float s = q0.x * k[0];
+    s = fmaf(q0.y, k[1], s);
+    s = fmaf(q0.z, k[2], s);
+    s = fmaf(q0.w, k[3], s);
+    s = fmaf(q1.x, k[4], s);
+    s = fmaf(q1.y, k[5], s);
+    s = fmaf(q1.z, k[6], s);
+    s = fmaf(q1.w, k[7], s);
+    return s;
+  };
+  float lmax = -INFINITY;
+#pragma unroll 2
+  for (int p = 0; p < npg; p++) {
+    float s = dot8(krow + (long)s_pt[p] * page_stride);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s *= scale;
+    if (part == 0)
+      scores[p * 16 + kslot] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  if (rem) {
+    const bool ok = kslot < rem;
+    float s = ok ? dot8(krow + (long)s_pt[npg] * page_stride) : 0.0f;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok) {
+      s *= scale;
+      if (part == 0)
+        scores[npg * 16 + kslot] = s;
+      lmax = fmaxf(lmax, s);
+    }
+  }
+  const float gmax = block_reduce_max(lmax, red); // includes __syncthreads
+  // ---- exp / sum ----
+  float lsum = 0.0f;
+  for (int j = tid; j < nkeys; j += ATT_THREADS) {
+    float e = expf(scores[j] - gmax);
+    scores[j] = e;
+    lsum += e;
+  }
+  const float gsum = block_reduce_sum(lsum, red);
+  const float inv = 1.0f / gsum;
+  // ---- P.V: thread (grp, c4) owns rows grp and grp + 8 of every page, ascending ----
+  const int c4 = tid & 15, grp = tid >> 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const KT *vrow = vbase + grp * HD + c4 * 4;
+  auto fma4 = [&](float w, const float4 &v) {
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  };
+  int p = 0;
+  for (; p + 1 < npg; p += 2) {
+    const KT *a = vrow + (long)s_pt[p] * page_stride, *b = vrow + (long)s_pt[p + 1] * page_stride;
+    const float4 v0 = kv_load4(a), v1 = kv_load4(a + 8 * HD), v2 = kv_load4(b), v3 = kv_load4(b + 8 * HD);
+    const float *sc = scores + p * 16 + grp;
+    const float w0 = sc[0] * inv, w1 = sc[8] * inv, w2 = sc[16] * inv, w3 = sc[24] * inv;
+    fma4(w0, v0);
+    fma4(w1, v1);
+    fma4(w2, v2);
+    fma4(w3, v3);
+  }
+  if (p < npg) {
+    const KT *a = vrow + (long)s_pt[p] * page_stride;
+    const float4 v0 = kv_load4(a), v1 = kv_load4(a + 8 * HD);
+    const float w0 = scores[p * 16 + grp] * inv, w1 = scores[p * 16 + grp + 8] * inv;
+    fma4(w0, v0);
+    fma4(w1, v1);
+  }
+  if (rem) {
+    const KT *a = vrow + (long)s_pt[npg] * page_stride;
+    if (grp < rem)
+      fma4(scores[npg * 16 + grp] * inv, kv_load4(a));
+    if (grp + 8 < rem)
+      fma4(scores[npg * 16 + grp + 8] * inv, kv_load4(a + 8 * HD));
+  }
+  pv[grp * 16 + c4] = acc;
+  __syncthreads();
+  if (tid < 16) {
+    float4 r = pv[tid];
+#pragma unroll
+    for (int g2 = 1; g2 < 8; g2++) {
+      float4 t = pv[g2 * 16 + tid];
+      r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+    }
+    if (out)
+      *reinterpret_cast<float4 *>(out + tid * 4) = r;
+    if (sp.hi)
+      split_store4(sp, sp_row, sp_col + tid * 4, r);
+  }
+}
+
+// MODE 0: any page size (integer division); 1: power-of-two pages (shift / mask); 2: 16-token pages, page-wise loops.
+template <typename KT, int MODE>
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_decode_kernel(const float *qkv, long ldq, float *out, long ldo,
                                   const int32_t *row_slot, const int32_t *row_pos, const float *cosT,
@@ -114,8 +231,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const int pmask = PT - 1;
   {
     const float *row = qkv + (long)r * ldq;
-    KT *page = pool + (long)pt[POW2 ? pos >> pt_shift : pos / PT] * page_stride +
-               (long)(POW2 ? pos & pmask : pos % PT) * HD;
+    KT *page = pool + (long)pt[MODE ? pos >> pt_shift : pos / PT] * page_stride +
+               (long)(MODE ? pos & pmask : pos % PT) * HD;
     if (tid < HD) { // pairs (2j, 2j+1): threads 0..31 rotate q, 32..63 rotate k
       const int isk = tid >= HD / 2, j = tid & (HD / 2 - 1);
       const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
@@ -137,13 +254,17 @@ __global__ void __launch_bounds__(ATT_THREADS)
   }
   __syncthreads(); // q and the page ids in shared memory; this CTA's own k/v stores are visible to its loads below
   const KT *kbase = pool + koff, *vbase = pool + voff;
+  if (MODE == 2) {
+    attend_row_pages16(qs, nkeys, kbase, vbase, s_pt, page_stride, o, smem, red, pv, sp, r, h * HD);
+    return;
+  }
   auto keyp = [&](int j) {
-    if (POW2)
+    if (MODE)
       return kbase + (long)s_pt[j >> pt_shift] * page_stride + ((j & pmask) << 6);
     return kbase + (long)s_pt[j / PT] * page_stride + (long)(j % PT) * HD;
   };
   auto valp = [&](int j) {
-    if (POW2)
+    if (MODE)
       return vbase + (long)s_pt[j >> pt_shift] * page_stride + ((j & pmask) << 6);
     return vbase + (long)s_pt[j / PT] * page_stride + (long)(j % PT) * HD;
   };
@@ -387,18 +508,26 @@ int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int
   dim3 grid(rows, kv.n_heads);
   size_t sm = sizeof(float) * (size_t)((max_keys + 15) / 16 * 16);
   const int pt_shift = page_shift(kv.page_tokens);
-  if (kv.half && pt_shift >= 0)
-    launch_k(attention_paged_decode_kernel<__half, true>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
-             row_pos, cosT, sinT, kv, layer, pt_shift, sp);
-  else if (kv.half)
-    launch_k(attention_paged_decode_kernel<__half, false>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
-             row_pos, cosT, sinT, kv, layer, 0, sp);
-  else if (pt_shift >= 0)
-    launch_k(attention_paged_decode_kernel<float, true>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
-             row_pos, cosT, sinT, kv, layer, pt_shift, sp);
-  else
-    launch_k(attention_paged_decode_kernel<float, false>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,
-             row_pos, cosT, sinT, kv, layer, 0, sp);
+#define PTTS_DECODE_LAUNCH(KT, MODE)                                                                              \
+  launch_k(attention_paged_decode_kernel<KT, MODE>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,   \
+           row_pos, cosT, sinT, kv, layer, pt_shift < 0 ? 0 : pt_shift, sp)
+  const int mode = pt_shift == 4 && getenv("PTTS_ATTN_NO_PAGEWISE") == nullptr ? 2 : (pt_shift >= 0 ? 1 : 0);
+  if (kv.half) {
+    if (mode == 2)
+      PTTS_DECODE_LAUNCH(__half, 2);
+    else if (mode == 1)
+      PTTS_DECODE_LAUNCH(__half, 1);
+    else
+      PTTS_DECODE_LAUNCH(__half, 0);
+  } else {
+    if (mode == 2)
+      PTTS_DECODE_LAUNCH(float, 2);
+    else if (mode == 1)
+      PTTS_DECODE_LAUNCH(float, 1);
+    else
+      PTTS_DECODE_LAUNCH(float, 0);
+  }
+#undef PTTS_DECODE_LAUNCH
   return 1;
 }
 

@@ -678,25 +678,39 @@ def test_weight_ring_frame_kernel_small_model(pkg, small_tensors, monkeypatch):
     np.testing.assert_array_equal(a.pcm, b.pcm)
 
 
-def test_staged_decode_attention_is_bit_identical(pkg, small_tensors, monkeypatch):
-    """PTTS_ATTN_STAGED=1: decode attention with the K / V rows staged through shared memory by cp.async
-    (attention_decode.cu) against the register kernel: same latents and PCM bit for bit, batch of 24 ragged
-    requests, 70 frames (kv up to ~90 keys: two 64-key tiles and the ring wrap of the value tiles)."""
+def test_decode_attention_variants_are_bit_identical(pkg, small_tensors, monkeypatch):
+    """The three decode-attention kernels over the fp16 cache — page-wise loops for 16-token pages (default,
+    attend_row_pages16), the generic attend_row with shift / mask page arithmetic (PTTS_ATTN_NO_PAGEWISE=1) and the
+    cp.async-staged one (PTTS_ATTN_STAGED=1, attention_decode.cu) — share thread-to-element assignment and
+    summation order: 24 ragged sequences stepped together for 70 frames through the stage API (a fixed batch, so
+    every GEMM takes the same tiles in every run) give the same latents bit for bit; kv grows from 4..19 to
+    74..89 keys, i.e. across full / partial pages, two 64-key tiles and the staged ring's wrap."""
     rng = np.random.default_rng(3)
     toks = [rng.integers(0, 4000, size=int(n)).astype(np.int64) for n in rng.integers(4, 20, 24)]
+    noise = pkg.make_noise(70 * 24, 0.7, 11).reshape(70, 24, 32)
 
     def run():
         rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=32, max_seq_tokens=256, max_frames=80,
                                    mimi_group_frames=256)
+        seqs = []
         try:
-            ps = [rt.submit(t, pkg.RuntimeGenerateConfig(max_steps=70, eos_threshold=1e30, seed=i)) for i, t in enumerate(toks)]
-            return [rt.wait(p, want_latents=True) for p in ps]
+            seqs = [rt.seq_open(t, reserve_frames=72) for t in toks]
+            lats = []
+            for i in range(70):
+                lat, eos = rt.step(seqs, noise[i])
+                lats.append(np.concatenate([lat.ravel(), eos.ravel()]))
+            return np.stack(lats)
         finally:
+            for q in seqs:
+                q.close()
             rt.close()
 
     a = run()
+    a2 = run()
+    np.testing.assert_array_equal(a, a2)  # the comparison below is meaningful: the path is deterministic
+    monkeypatch.setenv("PTTS_ATTN_NO_PAGEWISE", "1")
+    c = run()
     monkeypatch.setenv("PTTS_ATTN_STAGED", "1")
     b = run()
-    for x, y in zip(a, b):
-        np.testing.assert_array_equal(x.latents, y.latents)
-        np.testing.assert_array_equal(x.pcm, y.pcm)
+    np.testing.assert_array_equal(a, c)
+    np.testing.assert_array_equal(a, b)
