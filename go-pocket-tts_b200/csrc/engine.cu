@@ -1944,6 +1944,12 @@ int Engine::flow_head(int B, int lsd_steps) {
 // gather / NaN->BOS / input_linear, 6 transformer layers, flow head, scatter of the
 // new latent into the per-slot history.  Only fixed device pointers are used, so
 // the sequence can be captured into a CUDA graph.
+// Largest padded batch whose AR step is launched with programmatic dependent launch (PTTS_PDL_MAX_B to experiment).
+static int pdl_max_b() {
+  static const int v = getenv("PTTS_PDL_MAX_B") ? atoi(getenv("PTTS_PDL_MAX_B")) : 1 << 30;
+  return v;
+}
+
 int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise,
                       bool timed, bool capturing) {
   // the ~79 short dependent kernels of a frame are chained with programmatic dependent
@@ -1952,7 +1958,7 @@ int Engine::step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, b
   struct PdlScope {
     PdlScope(bool on) { pdl_set(on); }
     ~PdlScope() { pdl_set(false); }
-  } pdl_scope(!no_pdl && !prof_on && Bp <= 256); // measured: -3..9 % per frame up to B=256, +2 % at 512
+  } pdl_scope(!no_pdl && !prof_on && Bp <= pdl_max_b()); // measured: -3..9 % per frame up to B = 256, -5 % at 384..768, -1..3 % at 1024
   int64_t &nl = times.kernel_launches;
   if (Bp == 1 && fused_on && !prof_on) {
     // the batch-1 latency path: the whole frame is one persistent cooperative kernel
