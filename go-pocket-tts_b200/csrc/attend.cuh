@@ -42,6 +42,17 @@ __device__ __forceinline__ float block_reduce_sum(float v, float *red) {
   return r;
 }
 
+// RoPE rotation of one interleaved pair (rope.go:81-105: x0 c - x1 s, x0 s + x1 c, every product and the sum
+// rounded separately — the reference's Go has no FMA contraction on amd64).  Intrinsics, so that every kernel that
+// rotates (prefill append, decode attention variants, the batch-1 frame kernels) produces the same bits whatever
+// the surrounding code looks like to the compiler.
+__device__ __forceinline__ float rope_even(float x0, float x1, float c, float s) {
+  return __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+}
+__device__ __forceinline__ float rope_odd(float x0, float x1, float c, float s) {
+  return __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+}
+
 // Element type of a K/V row: fp32 (Mimi: rows of the qkv GEMM output; FlowLM cache in exact mode)
 // or fp16 (the FlowLM paged cache by default: the cache stream is what bounds the batched AR step,
 // and 11 mantissa bits on K and V keep the attention output ~1e-4 relative, inside the 1e-3 latent

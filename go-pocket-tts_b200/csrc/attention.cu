@@ -197,8 +197,9 @@ __global__ void __launch_bounds__(ATT_THREADS)
     attention_paged_decode_kernel(const float *qkv, long ldq, float *out, long ldo,
                                   const int32_t *row_slot, const int32_t *row_pos, const float *cosT,
                                   const float *sinT, KvGeom kv, int layer, int pt_shift, SplitOut sp) {
+  // Everything up to PDL_WAIT reads only what no kernel of the step writes (row tables, the page table, the RoPE
+  // tables) and writes nothing global: it overlaps the tail of the in_proj GEMM this launch depends on.
   PDL_TRIGGER();
-  PDL_WAIT();
   extern __shared__ float smem[];
   __shared__ float red[ATT_THREADS / 32];
   __shared__ float4 pv[8 * 16];
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
   const int slot = row_slot[r], pos = row_pos[r];
   float *o = out ? out + (long)r * ldo + h * HD : nullptr;
   if (pos < 0) {
+    PDL_WAIT();
     if (tid < 16) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       if (o)
@@ -229,6 +231,12 @@ __global__ void __launch_bounds__(ATT_THREADS)
   for (int i = tid; i * PT < nkeys; i += ATT_THREADS)
     s_pt[i] = pt[i];
   const int pmask = PT - 1;
+  float cj = 0.0f, sj = 0.0f;
+  if (tid < HD) {
+    cj = cosT[(long)pos * (HD / 2) + (tid & (HD / 2 - 1))];
+    sj = sinT[(long)pos * (HD / 2) + (tid & (HD / 2 - 1))];
+  }
+  PDL_WAIT();
   {
     const float *row = qkv + (long)r * ldq;
     KT *page = pool + (long)pt[MODE ? pos >> pt_shift : pos / PT] * page_stride +
@@ -237,9 +245,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
       const int isk = tid >= HD / 2, j = tid & (HD / 2 - 1);
       const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
       const float a = src[0], b = src[1];
-      const float cj = cosT[(long)pos * (HD / 2) + j], sj = sinT[(long)pos * (HD / 2) + j];
-      const float o0 = a * cj - b * sj;
-      const float o1 = a * sj + b * cj;
+      const float o0 = rope_even(a, b, cj, sj);
+      const float o1 = rope_odd(a, b, cj, sj);
       if (isk) {
         kv_store(page + koff + 2 * j, o0);
         kv_store(page + koff + 2 * j + 1, o1);
@@ -614,8 +621,8 @@ __global__ void __launch_bounds__(256)
         const int isk = p >= D / 2;
         const int pp = isk ? p - D / 2 : p;
         const int h = pp / half, j = pp % half;
-        const float o0 = a[k] * cj[k] - b[k] * sj[k];
-        const float o1 = a[k] * sj[k] + b[k] * cj[k];
+        const float o0 = rope_even(a[k], b[k], cj[k], sj[k]);
+        const float o1 = rope_odd(a[k], b[k], cj[k], sj[k]);
         if (isk) {
           KT *dst = page + ((long)(layer * 2 + 0) * H + h) * PT * HD + (long)tok * HD + 2 * j;
           kv_store(dst, o0);
@@ -781,8 +788,8 @@ __global__ void __launch_bounds__(256)
     const int h = pp / half, j = pp % half;
     float *src = row + (isk ? D : 0) + h * HD + 2 * j;
     const float a = src[0], b = src[1];
-    src[0] = a * c[j] - b * s[j];
-    src[1] = a * s[j] + b * c[j];
+    src[0] = rope_even(a, b, c[j], s[j]);
+    src[1] = rope_odd(a, b, c[j], s[j]);
   }
 }
 

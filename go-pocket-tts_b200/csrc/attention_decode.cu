@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
       const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
       const float a = src[0], b = src[1];
       const float cj = cosT[(long)pos * (HD / 2) + j], sj = sinT[(long)pos * (HD / 2) + j];
-      const float o0 = a * cj - b * sj;
-      const float o1 = a * sj + b * cj;
+      const float o0 = rope_even(a, b, cj, sj);
+      const float o1 = rope_odd(a, b, cj, sj);
       if (isk) {
         kv_store(page + koff + 2 * j, o0);
         kv_store(page + koff + 2 * j + 1, o1);

@@ -77,12 +77,20 @@ __global__ void __launch_bounds__(128)
     layernorm_reg_kernel(const float *x, long ldx, float *out, long ldo, int rows, const float *w, const float *b,
                          float eps, const float *scale, const float *shift, long ldmod, SplitOut sp) {
   PDL_TRIGGER();
-  PDL_WAIT();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows)
     return;
+  // the affine weights do not depend on the previous kernel: pull this lane's lines into L1 while it drains
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    if (w)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(w + lane * 4 + 128 * j));
+    if (b)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(b + lane * 4 + 128 * j));
+  }
+  PDL_WAIT();
   const float *xr = x + (long)row * ldx;
   float4 v[NV];
 #pragma unroll

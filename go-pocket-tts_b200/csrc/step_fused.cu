@@ -446,12 +446,12 @@ __global__ void __launch_bounds__(FT, 2)
         const int j = threadIdx.x;
         const float c = __ldg(P.rope_cos + (long)pos * half + j), s = __ldg(P.rope_sin + (long)pos * half + j);
         const float qa = ldcg1(P.qkv + h * HD + 2 * j), qb = ldcg1(P.qkv + h * HD + 2 * j + 1);
-        q_s[2 * j] = qa * c - qb * s;
-        q_s[2 * j + 1] = qa * s + qb * c;
+        q_s[2 * j] = rope_even(qa, qb, c, s);
+        q_s[2 * j + 1] = rope_odd(qa, qb, c, s);
         const float ka = ldcg1(P.qkv + D + h * HD + 2 * j), kb = ldcg1(P.qkv + D + h * HD + 2 * j + 1);
         __half *dst = page + koff + (long)tok * HD + 2 * j;
-        kv_store(dst, ka * c - kb * s);
-        kv_store(dst + 1, ka * s + kb * c);
+        kv_store(dst, rope_even(ka, kb, c, s));
+        kv_store(dst + 1, rope_odd(ka, kb, c, s));
       } else if (threadIdx.x < half + HD) {
         const int d = threadIdx.x - half;
         kv_store(page + voff + (long)tok * HD + d, ldcg1(P.qkv + 2 * D + h * HD + d));
@@ -794,11 +794,11 @@ __global__ void __launch_bounds__(FT, 2)
         const float c = __ldg(P.rope_cos + (long)pos * half + j), s = __ldg(P.rope_sin + (long)pos * half + j);
         const float2 qq = ll_get2(P.ll_qkv, h * HD + 2 * j, t_qkv, pl);
         const float2 kk = ll_get2(P.ll_qkv, D + h * HD + 2 * j, t_qkv, pl);
-        q_s[2 * j] = qq.x * c - qq.y * s;
-        q_s[2 * j + 1] = qq.x * s + qq.y * c;
+        q_s[2 * j] = rope_even(qq.x, qq.y, c, s);
+        q_s[2 * j + 1] = rope_odd(qq.x, qq.y, c, s);
         __half *dst = page + koff + (long)tok * HD + 2 * j;
-        kv_store(dst, kk.x * c - kk.y * s);
-        kv_store(dst + 1, kk.x * s + kk.y * c);
+        kv_store(dst, rope_even(kk.x, kk.y, c, s));
+        kv_store(dst + 1, rope_odd(kk.x, kk.y, c, s));
       } else if (threadIdx.x < half + HD) {
         const int d = threadIdx.x - half;
         kv_store(page + voff + (long)tok * HD + d, ll_get1(P.ll_qkv, 2 * D + h * HD + d, t_qkv, pl));
