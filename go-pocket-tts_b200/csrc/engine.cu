@@ -88,6 +88,9 @@ Engine::~Engine() {
   for (auto &kv : step_graphs)
     if (kv.second.exec)
       cudaGraphExecDestroy(kv.second.exec);
+  for (auto &kv : mimi_graphs)
+    if (kv.second.exec)
+      cudaGraphExecDestroy(kv.second.exec);
   auto fh = [](void *p) {
     if (p)
       cudaFreeHost(p);
@@ -1166,6 +1169,7 @@ int Engine::finalize() {
     cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
     CUDA_TRY(cudaStreamCreateWithPriority(&st_mimi, cudaStreamNonBlocking, lo_prio));
     overlap_on = getenv("PTTS_NO_MIMI_OVERLAP") == nullptr;
+    mimi_graphs_on = getenv("PTTS_NO_MIMI_GRAPHS") == nullptr;
   }
   for (int i = 0; i < NPCM; i++) {
     if ((rc = slack_alloc(&m_pcm_ring[i], rows, 1))) return rc;
@@ -2243,167 +2247,208 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
     CUDA_TRY(cudaMemcpyAsync(d_mrow_apos, h_apos, (size_t)Rb * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_mrow_seg, h_seg, (size_t)Rb * sizeof(int4), cudaMemcpyHostToDevice, st));
   }
-  // With the tensor-core path on, every GEMM / conv input is produced directly as split
-  // bf16 planes (fetched by TMA) and its fp32 copy is not written.
-  const bool sp_on = tc_on;
-  auto f32 = [&](float *p) { return sp_on ? nullptr : p; };
-  auto spo = [&](const ActSplit &a) { return sp_on ? a.out() : SplitOut(); };
-  // latent -> mimi projection (folded denorm + 1x1 conv); m_latin is filled by the
-  // caller (gather from the frame history, or host latents), split here
-  if (sp_on && total_frames >= tc_min_m)
-    PK("elementwise", 0, 0, copy_rows(m_latin, m_latin, total_frames, ldim, st, sm_latin.out()));
-  {
-    GemmArgs g;
-    g.A = m_latin; g.lda = ldim; g.W = proj.w; g.ldw = ldim; g.M = total_frames; g.N = Md; g.K = ldim;
-    g.epi.bias = proj.b; g.epi.C = m_lat; g.epi.ldc = Md;
-    use_act(g, sm_latin);
-    nl += pgemm(g);
-  }
-  PK("upsample_depthwise", 0, 0, upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st));
-  // decoder transformer (mimi.go:245-441)
-  for (int l = 0; l < ML; l++) {
-    DTLayer &ly = ml[l];
-    PK("layernorm", 0, 0, layernorm(m_x, Md, f32(m_nrm), Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st, spo(sm_nrm)));
-    GemmArgs g;
-    g.A = f32(m_nrm); g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
-    g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
-    use_act(g, sm_nrm);
-    nl += pgemm(g);
-    PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, stream ? d_mrow_apos : d_mrow_pos, mrope_cos, mrope_sin, st));
-    if (stream) {
-      // stateful deliveries: this layer's K (rotated) and V rows join the requests' rings, the new rows attend
-      // ring + buffer (the ring slots written here are never among the 249 older rows a row of the pass reads)
-      const long loff = (long)l * ring_layer_stride;
-      nl += kv_ring_append(m_qkv, Rb, Md, d_mrow_apos, d_mrow_seg, mimi_ring, ring_state_stride, loff, st);
-      nl += attention_window_stream(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_apos, d_mrow_seg, mimi_ring,
-                                    ring_state_stride, loff, Mctx, st, spo(sm_att));
-    } else if (prof_on) {
-      // flops: every allowed (query, key) pair, 4 * head_dim per head.  bytes: what a flash-style
-      // kernel must move — per block of 64 query rows the q rows, the UNIQUE K and V rows of the
-      // block's windows (read once per block, not once per query) and the output rows.
-      double keys = 0, rows_moved = 0;
-      for (int r0 = 0; r0 < Rb; r0 += 64) {
-        int lo = Rb, hi = -1;
-        for (int r = r0; r < r0 + 64 && r < Rb; r++) {
-          const int pos = h_mrow_pos[r];
-          if (pos < 0)
-            continue;
-          const int n = pos + 1 < Mctx ? pos + 1 : Mctx;
-          keys += n;
-          if (r - n + 1 < lo)
-            lo = r - n + 1;
-          hi = r;
+  // ---- the kernels of the pass (captured once and replayed for small asynchronous passes) ----
+  int rows_out = Rb;
+  for (int s3 = 0; s3 < 3; s3++)
+    rows_out *= up[s3].stride;
+  const int spb = rows_out / Rb; // samples per base row
+  auto run_kernels = [&]() -> int {
+    // With the tensor-core path on, every GEMM / conv input is produced directly as split
+    // bf16 planes (fetched by TMA) and its fp32 copy is not written.
+    const bool sp_on = tc_on;
+    auto f32 = [&](float *p) { return sp_on ? nullptr : p; };
+    auto spo = [&](const ActSplit &a) { return sp_on ? a.out() : SplitOut(); };
+    // latent -> mimi projection (folded denorm + 1x1 conv); m_latin is filled by the
+    // caller (gather from the frame history, or host latents), split here
+    if (sp_on && total_frames >= tc_min_m)
+      PK("elementwise", 0, 0, copy_rows(m_latin, m_latin, total_frames, ldim, st, sm_latin.out()));
+    {
+      GemmArgs g;
+      g.A = m_latin; g.lda = ldim; g.W = proj.w; g.ldw = ldim; g.M = total_frames; g.N = Md; g.K = ldim;
+      g.epi.bias = proj.b; g.epi.C = m_lat; g.epi.ldc = Md;
+      use_act(g, sm_latin);
+      nl += pgemm(g);
+    }
+    PK("upsample_depthwise", 0, 0, upsample_depthwise(m_lat, up_w, m_x, Rb, Md, up_stride, up_k, d_mrow_pos, d_mrow_frame0, st));
+    // decoder transformer (mimi.go:245-441)
+    for (int l = 0; l < ML; l++) {
+      DTLayer &ly = ml[l];
+      PK("layernorm", 0, 0, layernorm(m_x, Md, f32(m_nrm), Md, Rb, Md, ly.n1.w, ly.n1.b, ly.n1.eps, nullptr, nullptr, 0, st, spo(sm_nrm)));
+      GemmArgs g;
+      g.A = f32(m_nrm); g.lda = Md; g.W = ly.in_proj.w; g.ldw = Md; g.M = Rb; g.N = 3 * Md; g.K = Md;
+      g.epi.C = m_qkv; g.epi.ldc = 3 * Md;
+      use_act(g, sm_nrm);
+      nl += pgemm(g);
+      PK("rope_inplace", 0, 0, rope_inplace(m_qkv, Rb, Md, MH, stream ? d_mrow_apos : d_mrow_pos, mrope_cos, mrope_sin, st));
+      if (stream) {
+        // stateful deliveries: this layer's K (rotated) and V rows join the requests' rings, the new rows attend
+        // ring + buffer (the ring slots written here are never among the 249 older rows a row of the pass reads)
+        const long loff = (long)l * ring_layer_stride;
+        nl += kv_ring_append(m_qkv, Rb, Md, d_mrow_apos, d_mrow_seg, mimi_ring, ring_state_stride, loff, st);
+        nl += attention_window_stream(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_apos, d_mrow_seg, mimi_ring,
+                                      ring_state_stride, loff, Mctx, st, spo(sm_att));
+      } else if (prof_on) {
+        // flops: every allowed (query, key) pair, 4 * head_dim per head.  bytes: what a flash-style
+        // kernel must move — per block of 64 query rows the q rows, the UNIQUE K and V rows of the
+        // block's windows (read once per block, not once per query) and the output rows.
+        double keys = 0, rows_moved = 0;
+        for (int r0 = 0; r0 < Rb; r0 += 64) {
+          int lo = Rb, hi = -1;
+          for (int r = r0; r < r0 + 64 && r < Rb; r++) {
+            const int pos = h_mrow_pos[r];
+            if (pos < 0)
+              continue;
+            const int n = pos + 1 < Mctx ? pos + 1 : Mctx;
+            keys += n;
+            if (r - n + 1 < lo)
+              lo = r - n + 1;
+            hi = r;
+          }
+          if (hi >= 0)
+            rows_moved += 2.0 * (hi - lo + 1) + 2.0 * 64; // K + V window rows, q rows in, out rows
         }
-        if (hi >= 0)
-          rows_moved += 2.0 * (hi - lo + 1) + 2.0 * 64; // K + V window rows, q rows in, out rows
-      }
-      cudaEvent_t a, b;
-      prof_begin(&a, &b);
-      nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
-      prof_end(a, b, "attention_window", 4.0 * keys * Md, 4.0 * rows_moved * Md);
-    } else
-      nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
-    GemmArgs o;
-    o.A = f32(m_att); o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
-    o.epi.colscale = ly.ls1; o.epi.residual = m_x; o.epi.ldr = Md; o.epi.C = m_x; o.epi.ldc = Md;
-    use_act(o, sm_att);
-    nl += pgemm(o);
-    PK("layernorm", 0, 0, layernorm(m_x, Md, f32(m_nrm), Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st, spo(sm_nrm)));
-    GemmArgs f1;
-    f1.A = f32(m_nrm); f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
-    f1.epi.act = ACT_GELU; f1.epi.C = f32(m_ff); f1.epi.ldc = MF; f1.epi.Cs = spo(sm_ff);
-    use_act(f1, sm_nrm);
-    nl += pgemm(f1);
-    GemmArgs f2;
-    f2.A = f32(m_ff); f2.lda = MF; f2.W = ly.l2.w; f2.ldw = MF; f2.M = Rb; f2.N = Md; f2.K = MF;
-    f2.epi.colscale = ly.ls2; f2.epi.residual = m_x; f2.epi.ldr = Md; f2.epi.C = m_x; f2.epi.ldc = Md;
-    if (l == ML - 1) { // pad rows must be zero again: they are the conv left context
-      f2.epi.rowmask = d_mmask;
-      f2.epi.mask_div = 1;
-      f2.epi.Cs = spo(sm_x); // the SEANet input
-    }
-    use_act(f2, sm_ff);
-    nl += pgemm(f2);
-  }
-  debug_bufs["mimi_transformer"] = {m_x, (size_t)Rb * Md};
-  // SEANet (mimi.go:745-787): convs as GEMMs over overlapping channels-last rows
-  auto conv_gemm = [&](const DConvG &c, const float *in, const ActSplit &ins, int rows, int div, float *raw,
-                       float *elu, const ActSplit *elus, const float *residual) {
-    GemmArgs g;
-    g.A = sp_on ? nullptr : in - (size_t)(c.taps - 1) * c.cin; g.lda = c.cin; g.W = c.w; g.ldw = c.K;
-    g.M = rows; g.N = c.N; g.K = c.K;
-    g.epi.bias = c.b; g.epi.C = raw; g.epi.ldc = c.N;
-    g.epi.C2 = elu; g.epi.ldc2 = c.N;
-    if (elus && sp_on) {
-      // a stride-s transposed conv writes s output rows per input row: the split planes of
-      // its output have c.N / s channels per row, the same memory seen as [rows, c.N]
-      g.epi.C2s = elus->out();
-      g.epi.C2s.ld = c.N;
-    }
-    g.epi.residual = residual; g.epi.ldr = c.N;
-    g.epi.rowmask = d_mmask; g.epi.mask_div = div;
-    if (sp_on) {
-      if (c.taps > 1) {
-        g.amap = c.amap;
-        g.a_lo_row = (int)ins.plane_rows;
-        g.a_cin = c.cin;
+        cudaEvent_t a, b;
+        prof_begin(&a, &b);
+        nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
+        prof_end(a, b, "attention_window", 4.0 * keys * Md, 4.0 * rows_moved * Md);
       } else
-        use_act(g, ins);
-    }
-    nl += pgemm(g);
-  };
-  conv_gemm(init_conv, m_x, sm_x, Rb, 1, nullptr, f32(m_y0e), &sm_y0e, nullptr);
-  const float *cur = m_y0e;
-  const ActSplit *curs = &sm_y0e;
-  bool cur_alt = false; // the previous stage's fused block wrote sm_yf instead of sm_ye
-  int rows = Rb, div = 1;
-  for (int s = 0; s < 3; s++) {
-    if (cur_alt) {
-      DConvG u = up[s];
-      u.amap = up_alt_amap[s];
-      conv_gemm(u, cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr);
-    } else
-      conv_gemm(up[s], cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr); // rows*stride outputs
-    cur_alt = false;
-    rows *= up[s].stride;
-    div *= up[s].stride;
-    // elu(x + conv2(elu(conv1(elu(x))))); the last stage feeds the fp32 final conv
-    const bool last = s == 2;
-    bool fused = false;
-    static const bool no_rb = getenv("PTTS_NO_FUSED_RESBLOCK") != nullptr;
-    if (sp_on && !no_rb && res1[s].amap && res2[s].taps == 1 && (last || (sm_yf[s].p && up_alt_amap[s + 1]))) {
-      auto w1 = tc_map.find(res1[s].w), w2 = tc_map.find(res2[s].w);
-      if (w1 != tc_map.end() && w2 != tc_map.end()) {
-        cudaEvent_t pa, pb;
-        if (prof_on)
-          prof_begin(&pa, &pb);
-        const int n = resblock_fused(*w1->second, *w2->second, res1[s].amap, (int)sm_ye[s].plane_rows, rows, res1[s].cin,
-                                     res1[s].cout, res1[s].taps, res1[s].b, res2[s].b, m_y[s], d_mmask, div,
-                                     last ? m_ye[s] : nullptr, last ? SplitOut() : sm_yf[s].out(), st);
-        if (prof_on) {
-          const double c = res1[s].cin, h = res1[s].cout;
-          prof_end(pa, pb, n ? "resblock_fused" : "none", 2.0 * rows * (3 * c * h + h * c), 4.0 * rows * 3 * c,
-                   s == 2 ? "shape/resblock3" : "shape/resblock2");
-        }
-        nl += n;
-        fused = n > 0;
+        nl += attention_window(m_qkv, 3 * Md, f32(m_att), Md, Rb, Md, MH, d_mrow_pos, Mctx, st, spo(sm_att));
+      GemmArgs o;
+      o.A = f32(m_att); o.lda = Md; o.W = ly.out_proj.w; o.ldw = Md; o.M = Rb; o.N = Md; o.K = Md;
+      o.epi.colscale = ly.ls1; o.epi.residual = m_x; o.epi.ldr = Md; o.epi.C = m_x; o.epi.ldc = Md;
+      use_act(o, sm_att);
+      nl += pgemm(o);
+      PK("layernorm", 0, 0, layernorm(m_x, Md, f32(m_nrm), Md, Rb, Md, ly.n2.w, ly.n2.b, ly.n2.eps, nullptr, nullptr, 0, st, spo(sm_nrm)));
+      GemmArgs f1;
+      f1.A = f32(m_nrm); f1.lda = Md; f1.W = ly.l1.w; f1.ldw = Md; f1.M = Rb; f1.N = MF; f1.K = Md;
+      f1.epi.act = ACT_GELU; f1.epi.C = f32(m_ff); f1.epi.ldc = MF; f1.epi.Cs = spo(sm_ff);
+      use_act(f1, sm_nrm);
+      nl += pgemm(f1);
+      GemmArgs f2;
+      f2.A = f32(m_ff); f2.lda = MF; f2.W = ly.l2.w; f2.ldw = MF; f2.M = Rb; f2.N = Md; f2.K = MF;
+      f2.epi.colscale = ly.ls2; f2.epi.residual = m_x; f2.epi.ldr = Md; f2.epi.C = m_x; f2.epi.ldc = Md;
+      if (l == ML - 1) { // pad rows must be zero again: they are the conv left context
+        f2.epi.rowmask = d_mmask;
+        f2.epi.mask_div = 1;
+        f2.epi.Cs = spo(sm_x); // the SEANet input
       }
+      use_act(f2, sm_ff);
+      nl += pgemm(f2);
     }
-    const ActSplit *next_src = &sm_ye[s];
-    if (fused && !last) {
-      next_src = &sm_yf[s];
-      cur_alt = true;
+    debug_bufs["mimi_transformer"] = {m_x, (size_t)Rb * Md};
+    // SEANet (mimi.go:745-787): convs as GEMMs over overlapping channels-last rows
+    auto conv_gemm = [&](const DConvG &c, const float *in, const ActSplit &ins, int rows, int div, float *raw,
+                         float *elu, const ActSplit *elus, const float *residual) {
+      GemmArgs g;
+      g.A = sp_on ? nullptr : in - (size_t)(c.taps - 1) * c.cin; g.lda = c.cin; g.W = c.w; g.ldw = c.K;
+      g.M = rows; g.N = c.N; g.K = c.K;
+      g.epi.bias = c.b; g.epi.C = raw; g.epi.ldc = c.N;
+      g.epi.C2 = elu; g.epi.ldc2 = c.N;
+      if (elus && sp_on) {
+        // a stride-s transposed conv writes s output rows per input row: the split planes of
+        // its output have c.N / s channels per row, the same memory seen as [rows, c.N]
+        g.epi.C2s = elus->out();
+        g.epi.C2s.ld = c.N;
+      }
+      g.epi.residual = residual; g.epi.ldr = c.N;
+      g.epi.rowmask = d_mmask; g.epi.mask_div = div;
+      if (sp_on) {
+        if (c.taps > 1) {
+          g.amap = c.amap;
+          g.a_lo_row = (int)ins.plane_rows;
+          g.a_cin = c.cin;
+        } else
+          use_act(g, ins);
+      }
+      nl += pgemm(g);
+    };
+    conv_gemm(init_conv, m_x, sm_x, Rb, 1, nullptr, f32(m_y0e), &sm_y0e, nullptr);
+    const float *cur = m_y0e;
+    const ActSplit *curs = &sm_y0e;
+    bool cur_alt = false; // the previous stage's fused block wrote sm_yf instead of sm_ye
+    int rows = Rb, div = 1;
+    for (int s = 0; s < 3; s++) {
+      if (cur_alt) {
+        DConvG u = up[s];
+        u.amap = up_alt_amap[s];
+        conv_gemm(u, cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr);
+      } else
+        conv_gemm(up[s], cur, *curs, rows, div, m_y[s], f32(m_ye[s]), &sm_ye[s], nullptr); // rows*stride outputs
+      cur_alt = false;
+      rows *= up[s].stride;
+      div *= up[s].stride;
+      // elu(x + conv2(elu(conv1(elu(x))))); the last stage feeds the fp32 final conv
+      const bool last = s == 2;
+      bool fused = false;
+      static const bool no_rb = getenv("PTTS_NO_FUSED_RESBLOCK") != nullptr;
+      if (sp_on && !no_rb && res1[s].amap && res2[s].taps == 1 && (last || (sm_yf[s].p && up_alt_amap[s + 1]))) {
+        auto w1 = tc_map.find(res1[s].w), w2 = tc_map.find(res2[s].w);
+        if (w1 != tc_map.end() && w2 != tc_map.end()) {
+          cudaEvent_t pa, pb;
+          if (prof_on)
+            prof_begin(&pa, &pb);
+          const int n = resblock_fused(*w1->second, *w2->second, res1[s].amap, (int)sm_ye[s].plane_rows, rows, res1[s].cin,
+                                       res1[s].cout, res1[s].taps, res1[s].b, res2[s].b, m_y[s], d_mmask, div,
+                                       last ? m_ye[s] : nullptr, last ? SplitOut() : sm_yf[s].out(), st);
+          if (prof_on) {
+            const double c = res1[s].cin, h = res1[s].cout;
+            prof_end(pa, pb, n ? "resblock_fused" : "none", 2.0 * rows * (3 * c * h + h * c), 4.0 * rows * 3 * c,
+                     s == 2 ? "shape/resblock3" : "shape/resblock2");
+          }
+          nl += n;
+          fused = n > 0;
+        }
+      }
+      const ActSplit *next_src = &sm_ye[s];
+      if (fused && !last) {
+        next_src = &sm_yf[s];
+        cur_alt = true;
+      }
+      if (!fused) {
+        conv_gemm(res1[s], m_ye[s], sm_ye[s], rows, div, nullptr, f32(m_he[s]), &sm_he[s], nullptr);
+        conv_gemm(res2[s], m_he[s], sm_he[s], rows, div, nullptr, (last || !sp_on) ? m_ye[s] : nullptr,
+                  last ? nullptr : &sm_ye[s], m_y[s]);
+      }
+      cur = m_ye[s];
+      curs = next_src;
     }
-    if (!fused) {
-      conv_gemm(res1[s], m_ye[s], sm_ye[s], rows, div, nullptr, f32(m_he[s]), &sm_he[s], nullptr);
-      conv_gemm(res2[s], m_he[s], sm_he[s], rows, div, nullptr, (last || !sp_on) ? m_ye[s] : nullptr,
-                last ? nullptr : &sm_ye[s], m_y[s]);
-    }
-    cur = m_ye[s];
-    curs = next_src;
+    PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, pcm, st));
+    return PTTS_OK;
+  };
+  StepGraph *mg = nullptr;
+  if (side && mimi_graphs_on && graphs_on && total_frames <= 16 && job) {
+    const uint64_t key = ((uint64_t)Rb << 40) | ((uint64_t)total_frames << 24) | ((uint64_t)segs.size() << 8) |
+                         ((uint64_t)job->buf << 1) | (stream ? 1u : 0u);
+    mg = &mimi_graphs[key];
+    mg->uses++;
   }
-  PK("final_conv", 0, 0, final_conv(cur, rows, final_cin, final_k, final_w, final_b, d_mmask, div, pcm, st));
-  const int spb = div; // samples per base row
+  if (mg && mg->exec) {
+    CUDA_TRY(cudaGraphLaunch(mg->exec, st));
+    nl += mg->launches;
+  } else if (mg && mg->uses >= 2) {
+    const int64_t before = nl;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_kernels();
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc)
+      return rc;
+    if (ce != cudaSuccess)
+      PTTS_FAIL(PTTS_ECUDA, "cuda: graph capture of a Mimi pass failed: %s", cudaGetErrorString(ce));
+    mg->launches = nl - before;
+    ce = cudaGraphInstantiate(&mg->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      mg->exec = nullptr;
+      PTTS_FAIL(PTTS_ECUDA, "cuda: graph instantiate of a Mimi pass failed: %s", cudaGetErrorString(ce));
+    }
+    CUDA_TRY(cudaGraphLaunch(mg->exec, st));
+  } else {
+    const int rc = run_kernels();
+    if (rc)
+      return rc;
+  }
+  const int rows = rows_out;
   debug_bufs["mimi_pcm"] = {pcm, (size_t)rows};
   times.mimi_frames += total_frames;
   if (job) {

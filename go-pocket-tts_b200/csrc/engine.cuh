@@ -405,6 +405,10 @@ struct Engine {
   };
   bool graphs_on = true;
   std::map<uint64_t, StepGraph> step_graphs;
+  // Small asynchronous Mimi passes (streaming deliveries: a few frames, ~30 launch-bound kernels) replay a
+  // captured graph per (rows, frames, segments, ring slot, stateful) instead of launching kernel by kernel.
+  std::map<uint64_t, StepGraph> mimi_graphs;
+  bool mimi_graphs_on = true; // PTTS_NO_MIMI_GRAPHS
   int step_body(int Bp, int max_keys, int lsd_steps, bool gather_frames, bool gather_noise, bool timed,
                 bool capturing = false);
   int step(const std::vector<Seq *> &seqs, const float *frames_in_host,
