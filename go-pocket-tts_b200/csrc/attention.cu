@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
   KT *pool = static_cast<KT *>(kv.pool);
   // the sequence's page ids go to shared memory once: every key / value access below would otherwise be two
   // dependent global loads (page id, then the row)
-  __shared__ int32_t s_pt[512];
+  __shared__ int32_t s_pt[KV_MAX_SEQ_PAGES];
   for (int i = tid; i * PT < nkeys; i += ATT_THREADS)
     s_pt[i] = pt[i];
   const int pmask = PT - 1;

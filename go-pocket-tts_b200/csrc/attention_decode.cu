@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
   __shared__ float red[ATT_THREADS / 32];
   __shared__ float4 pv[8 * 16];
   __shared__ __align__(16) float qs[HD];
-  __shared__ int32_t s_pt[512];
+  __shared__ int32_t s_pt[KV_MAX_SEQ_PAGES];
   const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int slot = row_slot[r], pos = row_pos[r];
   float *o = out ? out + (long)r * ldo + h * HD : nullptr;
@@ -217,7 +217,7 @@ int attention_paged_decode_staged(const float *qkv, long ldq, float *out, long l
                                   const int32_t *row_pos, const float *cosT, const float *sinT, const KvGeom &kv,
                                   int layer, int max_keys, cudaStream_t st, SplitOut sp) {
   const int PT = kv.page_tokens;
-  if (rows <= 0 || !kv.half || PT <= 0 || (PT & (PT - 1)) != 0 || (max_keys + PT - 1) / PT > 512)
+  if (rows <= 0 || !kv.half || PT <= 0 || (PT & (PT - 1)) != 0 || (max_keys + PT - 1) / PT > KV_MAX_SEQ_PAGES)
     return 0;
   int pt_shift = 0;
   while ((1 << pt_shift) < PT)

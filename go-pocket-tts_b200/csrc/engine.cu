@@ -1050,6 +1050,9 @@ int Engine::finalize() {
   max_frames = cfg.max_frames;
   page_tokens = cfg.page_tokens;
   max_pages = (cfg.max_seq_tokens + page_tokens - 1) / page_tokens;
+  if (max_pages > KV_MAX_SEQ_PAGES)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda: max_seq_tokens %d / page_tokens %d = %d pages per sequence (max %d)",
+              cfg.max_seq_tokens, page_tokens, max_pages, KV_MAX_SEQ_PAGES);
   n_pages = cfg.kv_pages > 0 ? cfg.kv_pages : max_batch * max_pages;
   // The cache holds K (rotated) and V as fp16 by default: its stream is what bounds the batched AR
   // step (48 KB per token and sequence as fp32), and 11 mantissa bits keep the attention output
@@ -2419,8 +2422,13 @@ int Engine::mimi_decode(std::vector<MimiSeg> &segs, int total_frames, bool d2h, 
   if (side && mimi_graphs_on && graphs_on && total_frames <= 16 && job) {
     const uint64_t key = ((uint64_t)Rb << 40) | ((uint64_t)total_frames << 24) | ((uint64_t)segs.size() << 8) |
                          ((uint64_t)job->buf << 1) | (stream ? 1u : 0u);
-    mg = &mimi_graphs[key];
-    mg->uses++;
+    auto it = mimi_graphs.find(key);
+    if (it != mimi_graphs.end())
+      mg = &it->second;
+    else if (mimi_graphs.size() < 256) // shapes beyond that run kernel by kernel
+      mg = &mimi_graphs[key];
+    if (mg)
+      mg->uses++;
   }
   if (mg && mg->exec) {
     CUDA_TRY(cudaGraphLaunch(mg->exec, st));

@@ -174,6 +174,7 @@ int attention_window(const float *qkv, long ldq, float *out, long ldo, int rows,
 //   row_apos[r] : absolute position of row r in its request (RoPE position), < 0 on pad rows
 //   row_seg[r]  : {ring slot of the request or -1, absolute position of the segment's first row,
 //                  buffer row of the segment's first row, unused}
+constexpr int KV_MAX_SEQ_PAGES = 512; // page ids of one sequence staged in shared memory by the decode attention
 constexpr int MIMI_RING = 1024;
 constexpr int MIMI_ROPE_ROWS = 8192; // rows of the Mimi transformer's RoPE table
 int kv_ring_append(const float *qkv, int rows, int D, const int32_t *row_apos, const int4 *row_seg, float *ring,
