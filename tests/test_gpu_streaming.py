@@ -149,3 +149,32 @@ def test_windowed_stream_without_rings(pkg, small_tensors, monkeypatch):
         assert snr_db(whole.pcm, got.pcm) >= 60.0
     finally:
         rt.close()
+
+
+def test_more_streams_than_rings(pkg, small_tensors):
+    """40 concurrent streaming requests on an engine with 32 Mimi K/V rings: the first 32 decode statefully, the
+    others through the bounded re-decode window; a cancelled stream returns its ring; every stream equals the
+    whole-chunk decode of the same request."""
+    rt = pkg.NativeCudaRuntime(tensors=small_tensors, max_batch=48, max_seq_tokens=256, max_frames=48,
+                               mimi_group_frames=256)
+    try:
+        toks = [_tokens(5 + i % 9, 300 + i) for i in range(40)]
+        cfgs = [dict(max_steps=18 + i % 7, eos_threshold=1e30, seed=500 + i) for i in range(40)]
+        ps = [rt.submit(toks[i], pkg.RuntimeGenerateConfig(stream_frames=1 + i % 3, **cfgs[i])) for i in range(40)]
+        victim = rt.submit(_tokens(6, 999), pkg.RuntimeGenerateConfig(max_steps=40, eos_threshold=1e30, stream_frames=1))
+        rt.read(victim, 0)
+        rt.cancel(victim)
+        outs = [rt.wait(p) for p in ps]
+        with pytest.raises(pkg.NativeCudaError):
+            rt.wait(victim)
+        refs = [rt.generate(toks[i], pkg.RuntimeGenerateConfig(**cfgs[i])) for i in range(40)]
+        for o, r in zip(outs, refs):
+            assert o.n_frames == r.n_frames
+            assert snr_db(r.pcm, o.pcm) >= 60.0, snr_db(r.pcm, o.pcm)
+        # the rings all came back: 32 more streams decode statefully again (3 latent frames per 1-frame delivery at most)
+        before = rt.stage_times()["mimi_frames"]
+        ps = [rt.submit(toks[i], pkg.RuntimeGenerateConfig(stream_frames=1, **cfgs[i])) for i in range(32)]
+        n = sum(rt.wait(p).n_frames for p in ps)
+        assert rt.stage_times()["mimi_frames"] - before <= 3 * n
+    finally:
+        rt.close()
