@@ -278,6 +278,217 @@ __global__ void __launch_bounds__(ATT_THREADS)
   attend_row(qs, nkeys, keyp, valp, o, smem, red, pv, sp, r, h * HD);
 }
 
+// Two heads of one row per CTA, 64 threads per head (16-token pages; opt-in, see attention_paged_decode).  The
+// kernel above is issue-bound and more than half of what it issues at kv ~ 100 is per-CTA overhead that every
+// warp repeats (row / page-table setup, block reductions, barriers): here four warps carry two heads, so that
+// overhead is paid once per two heads.  Measured: no faster.
+// Each thread plays two threads of the 128-thread layout — keys kslot and kslot + 8 of a page in the score pass,
+// the partial sums of threads t and t + 64 in the softmax denominator, value groups grp and grp + 4 — and every
+// sum is formed in the same order, so the output is bit-identical to attend_row / attend_row_pages16.
+template <typename KT>
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_paged_decode2_kernel(const float *qkv, long ldq, float *out, long ldo, const int32_t *row_slot,
+                                   const int32_t *row_pos, const float *cosT, const float *sinT, KvGeom kv, int layer,
+                                   int score_floats, SplitOut sp) {
+  PDL_TRIGGER();
+  extern __shared__ float smem[]; // scores of the two heads
+  __shared__ float red[2][4];
+  __shared__ float4 pv[2][8 * 16];
+  __shared__ __align__(16) float qs2[2][HD];
+  __shared__ int32_t s_pt[KV_MAX_SEQ_PAGES];
+  const int r = blockIdx.x, tid = threadIdx.x, sub = tid >> 6, t = tid & 63, lane = tid & 31, w = t >> 5;
+  const int h = blockIdx.y * 2 + sub;
+  const int slot = row_slot[r], pos = row_pos[r];
+  float *o = out ? out + (long)r * ldo + h * HD : nullptr;
+  if (pos < 0) {
+    PDL_WAIT();
+    if (t < 16) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o)
+        *reinterpret_cast<float4 *>(o + t * 4) = z;
+      if (sp.hi)
+        split_store4(sp, r, h * HD + t * 4, z);
+    }
+    return;
+  }
+  const int nkeys = pos + 1, npg = nkeys >> 4, rem = nkeys & 15;
+  const int32_t *pt = kv.pagetab + (long)slot * kv.max_pages;
+  const int D = kv.n_heads * HD;
+  const long page_stride = (long)kv.n_layers * 2 * kv.n_heads * 16 * HD;
+  const long koff = ((long)(layer * 2 + 0) * kv.n_heads + h) * 16 * HD;
+  const long voff = ((long)(layer * 2 + 1) * kv.n_heads + h) * 16 * HD;
+  KT *pool = static_cast<KT *>(kv.pool);
+  for (int i = tid; (i << 4) < nkeys; i += ATT_THREADS)
+    s_pt[i] = pt[i];
+  float cj = 0.0f, sj = 0.0f;
+  {
+    const int j = t & (HD / 2 - 1);
+    cj = cosT[(long)pos * (HD / 2) + j];
+    sj = sinT[(long)pos * (HD / 2) + j];
+  }
+  float *qs = qs2[sub];
+  float *scores = smem + sub * score_floats;
+  PDL_WAIT();
+  {
+    const float *row = qkv + (long)r * ldq;
+    KT *page = pool + (long)pt[pos >> 4] * page_stride + (long)(pos & 15) * HD;
+    const int isk = t >= HD / 2, j = t & (HD / 2 - 1); // threads 0..31 of the head rotate q, 32..63 rotate k
+    const float *src = row + (isk ? D : 0) + h * HD + 2 * j;
+    const float a = src[0], b = src[1];
+    const float o0 = rope_even(a, b, cj, sj);
+    const float o1 = rope_odd(a, b, cj, sj);
+    if (isk) {
+      kv_store(page + koff + 2 * j, o0);
+      kv_store(page + koff + 2 * j + 1, o1);
+    } else {
+      qs[2 * j] = o0;
+      qs[2 * j + 1] = o1;
+    }
+    kv_store(page + voff + t, row[2 * D + h * HD + t]); // and every thread one element of the head's v
+  }
+  __syncthreads(); // q and the page ids in shared memory; this CTA's own k/v stores are visible to its loads below
+  const KT *kbase = pool + koff, *vbase = pool + voff;
+  const float scale = 0.125f; // 1/sqrt(64)
+  // ---- scores: rows kslot and kslot + 8 of every page ----
+  const int part = t & 7, kslot = t >> 3; // 0..7
+  const float4 q0 = *reinterpret_cast<const float4 *>(qs + part * 8);
+  const float4 q1 = *reinterpret_cast<const float4 *>(qs + part * 8 + 4);
+  const KT *krow = kbase + kslot * HD + part * 8;
+  auto dot8 = [&](const KT *p) {
+    float k[8];
+    kv_load8(p, k);
+    float s = q0.x * k[0];
+    s = fmaf(q0.y, k[1], s);
+    s = fmaf(q0.z, k[2], s);
+    s = fmaf(q0.w, k[3], s);
+    s = fmaf(q1.x, k[4], s);
+    s = fmaf(q1.y, k[5], s);
+    s = fmaf(q1.z, k[6], s);
+    s = fmaf(q1.w, k[7], s);
+    return s;
+  };
+  auto red8 = [&](float s) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+  };
+  float lmax = -INFINITY;
+  for (int p = 0; p < npg; p++) {
+    const KT *kp = krow + (long)s_pt[p] * page_stride;
+    float s0 = dot8(kp), s1 = dot8(kp + 8 * HD);
+    s0 = red8(s0) * scale;
+    s1 = red8(s1) * scale;
+    if (part == 0) {
+      scores[p * 16 + kslot] = s0;
+      scores[p * 16 + kslot + 8] = s1;
+    }
+    lmax = fmaxf(lmax, fmaxf(s0, s1));
+  }
+  if (rem) {
+    const KT *kp = krow + (long)s_pt[npg] * page_stride;
+    const bool ok0 = kslot < rem, ok1 = kslot + 8 < rem;
+    float s0 = ok0 ? dot8(kp) : 0.0f, s1 = ok1 ? dot8(kp + 8 * HD) : 0.0f;
+    s0 = red8(s0);
+    s1 = red8(s1);
+    if (ok0) {
+      s0 *= scale;
+      if (part == 0)
+        scores[npg * 16 + kslot] = s0;
+      lmax = fmaxf(lmax, s0);
+    }
+    if (ok1) {
+      s1 *= scale;
+      if (part == 0)
+        scores[npg * 16 + kslot + 8] = s1;
+      lmax = fmaxf(lmax, s1);
+    }
+  }
+  // max over the head's 64 threads
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1)
+    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, of));
+  if (lane == 0)
+    red[sub][w] = lmax;
+  __syncthreads();
+  const float gmax = fmaxf(red[sub][0], red[sub][1]);
+  __syncthreads();
+  // ---- exp / sum: the partial sums of threads t and t + 64 of the 128-thread layout, reduced per (virtual) warp ----
+  float la = 0.0f, lb = 0.0f;
+  for (int j = t; j < nkeys; j += ATT_THREADS) {
+    const float e = expf(scores[j] - gmax);
+    scores[j] = e;
+    la += e;
+    if (j + 64 < nkeys) {
+      const float e2 = expf(scores[j + 64] - gmax);
+      scores[j + 64] = e2;
+      lb += e2;
+    }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) {
+    la += __shfl_xor_sync(0xffffffffu, la, of);
+    lb += __shfl_xor_sync(0xffffffffu, lb, of);
+  }
+  if (lane == 0) { // virtual warps w (threads t) and w + 2 (threads t + 64)
+    red[sub][w] = la;
+    red[sub][w + 2] = lb;
+  }
+  __syncthreads();
+  float gsum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    gsum += red[sub][i];
+  const float inv = 1.0f / gsum;
+  // ---- P.V: value groups grp and grp + 4 (rows grp, grp + 8 and grp + 4, grp + 12 of every page), ascending ----
+  const int c4 = t & 15, grp = t >> 4; // 0..3
+  float4 acA = make_float4(0.f, 0.f, 0.f, 0.f), acB = acA;
+  const KT *vrow = vbase + grp * HD + c4 * 4;
+  auto fma4 = [](float4 &acc, float wv, const float4 &v) {
+    acc.x = fmaf(wv, v.x, acc.x);
+    acc.y = fmaf(wv, v.y, acc.y);
+    acc.z = fmaf(wv, v.z, acc.z);
+    acc.w = fmaf(wv, v.w, acc.w);
+  };
+  for (int p = 0; p < npg; p++) {
+    const KT *a = vrow + (long)s_pt[p] * page_stride;
+    const float4 v0 = kv_load4(a), v1 = kv_load4(a + 4 * HD), v2 = kv_load4(a + 8 * HD), v3 = kv_load4(a + 12 * HD);
+    const float *sc = scores + p * 16 + grp;
+    const float w0 = sc[0] * inv, w1 = sc[4] * inv, w2 = sc[8] * inv, w3 = sc[12] * inv;
+    fma4(acA, w0, v0);
+    fma4(acB, w1, v1);
+    fma4(acA, w2, v2);
+    fma4(acB, w3, v3);
+  }
+  if (rem) {
+    const KT *a = vrow + (long)s_pt[npg] * page_stride;
+    const float *sc = scores + npg * 16 + grp;
+    if (grp < rem)
+      fma4(acA, sc[0] * inv, kv_load4(a));
+    if (grp + 4 < rem)
+      fma4(acB, sc[4] * inv, kv_load4(a + 4 * HD));
+    if (grp + 8 < rem)
+      fma4(acA, sc[8] * inv, kv_load4(a + 8 * HD));
+    if (grp + 12 < rem)
+      fma4(acB, sc[12] * inv, kv_load4(a + 12 * HD));
+  }
+  pv[sub][grp * 16 + c4] = acA;
+  pv[sub][(grp + 4) * 16 + c4] = acB;
+  __syncthreads();
+  if (t < 16) {
+    float4 rr = pv[sub][t];
+#pragma unroll
+    for (int g2 = 1; g2 < 8; g2++) {
+      const float4 t4 = pv[sub][g2 * 16 + t];
+      rr.x += t4.x; rr.y += t4.y; rr.z += t4.z; rr.w += t4.w;
+    }
+    if (o)
+      *reinterpret_cast<float4 *>(o + t * 4) = rr;
+    if (sp.hi)
+      split_store4(sp, r, h * HD + t * 4, rr);
+  }
+}
+
 __global__ void __launch_bounds__(ATT_THREADS)
     attention_window_kernel(const float *qkv, long ldq, float *out, long ldo,
                             int D, const int32_t *row_pos, int ctx, SplitOut sp) {
@@ -519,6 +730,21 @@ int attention_paged_decode(const float *qkv, long ldq, float *out, long ldo, int
   launch_k(attention_paged_decode_kernel<KT, MODE>, grid, dim3(ATT_THREADS), sm, st, qkv, ldq, out, ldo, row_slot,   \
            row_pos, cosT, sinT, kv, layer, pt_shift < 0 ? 0 : pt_shift, sp)
   const int mode = pt_shift == 4 && getenv("PTTS_ATTN_NO_PAGEWISE") == nullptr ? 2 : (pt_shift >= 0 ? 1 : 0);
+  // opt-in (PTTS_ATTN_PAIRS=1): two heads per CTA.  Bit-identical; measured no faster than one head per CTA
+  // (54.6 vs 53.2 us per launch at B = 512, 92.8 vs 93.5 at 1024, 35.1 vs 31.3 at 256): what the shared
+  // prologue saves, the doubled dependent work per thread gives back.
+  if (mode == 2 && (kv.n_heads & 1) == 0 && getenv("PTTS_ATTN_PAIRS") != nullptr) {
+    const int score_floats = (max_keys + 15) / 16 * 16;
+    dim3 grid2(rows, kv.n_heads / 2);
+    const size_t sm2 = sizeof(float) * 2 * (size_t)score_floats;
+    if (kv.half)
+      launch_k(attention_paged_decode2_kernel<__half>, grid2, dim3(ATT_THREADS), sm2, st, qkv, ldq, out, ldo, row_slot,
+               row_pos, cosT, sinT, kv, layer, score_floats, sp);
+    else
+      launch_k(attention_paged_decode2_kernel<float>, grid2, dim3(ATT_THREADS), sm2, st, qkv, ldq, out, ldo, row_slot,
+               row_pos, cosT, sinT, kv, layer, score_floats, sp);
+    return 1;
+  }
   if (kv.half) {
     if (mode == 2)
       PTTS_DECODE_LAUNCH(__half, 2);

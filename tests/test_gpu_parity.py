@@ -679,8 +679,8 @@ def test_weight_ring_frame_kernel_small_model(pkg, small_tensors, monkeypatch):
 
 
 def test_decode_attention_variants_are_bit_identical(pkg, small_tensors, monkeypatch):
-    """The three decode-attention kernels over the fp16 cache — page-wise loops for 16-token pages (default,
-    attend_row_pages16), the generic attend_row with shift / mask page arithmetic (PTTS_ATTN_NO_PAGEWISE=1) and the
+    """The decode-attention kernels over the fp16 cache — page-wise loops for 16-token pages (default,
+    attend_row_pages16), two heads per CTA (PTTS_ATTN_PAIRS=1), the generic attend_row with shift / mask page arithmetic (PTTS_ATTN_NO_PAGEWISE=1) and the
     cp.async-staged one (PTTS_ATTN_STAGED=1, attention_decode.cu) — share thread-to-element assignment and
     summation order: 24 ragged sequences stepped together for 70 frames through the stage API (a fixed batch, so
     every GEMM takes the same tiles in every run) give the same latents bit for bit; kv grows from 4..19 to
@@ -705,12 +705,16 @@ def test_decode_attention_variants_are_bit_identical(pkg, small_tensors, monkeyp
                 q.close()
             rt.close()
 
-    a = run()
+    a = run()  # default: one head per CTA, page-wise loops (attend_row_pages16)
     a2 = run()
     np.testing.assert_array_equal(a, a2)  # the comparison below is meaningful: the path is deterministic
+    monkeypatch.setenv("PTTS_ATTN_PAIRS", "1")
+    d = run()  # two heads per CTA, 64 threads per head (attention_paged_decode2_kernel)
+    monkeypatch.delenv("PTTS_ATTN_PAIRS")
     monkeypatch.setenv("PTTS_ATTN_NO_PAGEWISE", "1")
     c = run()
     monkeypatch.setenv("PTTS_ATTN_STAGED", "1")
     b = run()
+    np.testing.assert_array_equal(a, d)
     np.testing.assert_array_equal(a, c)
     np.testing.assert_array_equal(a, b)
