@@ -273,6 +273,9 @@ class RuntimeGenerateConfig:
     no_pcm_d2h: bool = False
     pcm16: bool = False  # PCM16 samples quantised on the device (wav_stream.go:44-54); GenerateResult.pcm is int16
     stream_frames: int = 0  # > 0: frame-level streaming (PTTS_REQ_STREAM), PCM delivered every this many frames
+    # Caller-owned output buffer (>= max steps * 1920 samples, float32 or int16 with pcm16), e.g. one a server
+    # reuses across requests: the C ABI writes PCM into whatever `pcm_out` it is given (ptts_submit).
+    pcm_out: Optional[np.ndarray] = None
 
 
 def estimate_max_frames(n_tokens: int, frame_rate: float = 12.5) -> int:
@@ -429,8 +432,16 @@ class NativeCudaRuntime:
                        estimated_max_steps=cfg.estimated_max_steps, lsd_decode_steps=cfg.lsd_decode_steps,
                        frames_after_eos=cfg.frames_after_eos, force_eos_step=cfg.force_eos_step, flags=flags,
                        stream_frames=max(getattr(cfg, "stream_frames", 0), 0))
-        pcm = None if cfg.no_pcm_d2h else np.empty(ms * SAMPLES_PER_FRAME,
-                                                    dtype=np.int16 if getattr(cfg, "pcm16", False) else np.float32)
+        want = np.int16 if getattr(cfg, "pcm16", False) else np.float32
+        pcm = None
+        if not cfg.no_pcm_d2h:
+            pcm = getattr(cfg, "pcm_out", None)
+            if pcm is None:
+                pcm = np.empty(ms * SAMPLES_PER_FRAME, dtype=want)
+            elif (pcm.dtype != want or pcm.ndim != 1 or pcm.size < ms * SAMPLES_PER_FRAME or
+                  not pcm.flags["C_CONTIGUOUS"] or not pcm.flags["WRITEABLE"]):
+                raise NativeCudaError(PTTS_EINVAL, "generate: pcm_out must be a writable contiguous 1-D %s array of "
+                                                   ">= %d samples" % (np.dtype(want).name, ms * SAMPLES_PER_FRAME))
         ticket = C.c_int64()
         _check(self._submit(toks.ctypes.data_as(C.POINTER(C.c_int64)), toks.size, vemb, vframes,
                             vkv, C.byref(g), _fptr(noise), noise.shape[0],

@@ -718,3 +718,20 @@ def test_decode_attention_variants_are_bit_identical(pkg, small_tensors, monkeyp
     np.testing.assert_array_equal(a, d)
     np.testing.assert_array_equal(a, c)
     np.testing.assert_array_equal(a, b)
+
+
+def test_caller_owned_pcm_buffer(small_rt, pkg):
+    """RuntimeGenerateConfig.pcm_out: the PCM lands in the caller's (reused) buffer; a buffer of the wrong type or
+    size is refused before anything is submitted."""
+    toks = np.random.default_rng(8).integers(0, 4000, size=7).astype(np.int64)
+    kw = dict(max_steps=6, eos_threshold=1e30, seed=2)
+    ref = small_rt.generate(toks, pkg.RuntimeGenerateConfig(**kw))
+    buf = np.full(8 * 1920, 7.0, np.float32)
+    for _ in range(2):
+        got = small_rt.generate(toks, pkg.RuntimeGenerateConfig(pcm_out=buf, **kw))
+        assert got.pcm.base is buf or np.shares_memory(got.pcm, buf)
+        np.testing.assert_array_equal(got.pcm, ref.pcm)
+        assert np.all(buf[6 * 1920:] == 7.0)
+    for bad in (np.zeros(5 * 1920, np.float32), np.zeros(8 * 1920, np.float64), np.zeros((8, 1920), np.float32)):
+        with pytest.raises(pkg.NativeCudaError):
+            small_rt.generate(toks, pkg.RuntimeGenerateConfig(pcm_out=bad, **kw))
