@@ -131,7 +131,7 @@ EXPORTS = [
     "ptts_load_safetensors", "ptts_finalize_weights", "ptts_model_info_get", "ptts_generate_audio",
     "ptts_submit", "ptts_wait", "ptts_cancel", "ptts_ticket_latents", "ptts_ticket_error", "ptts_ticket_read",
     "ptts_ticket_release", "ptts_seq_open",
-    "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
+    "ptts_step", "ptts_decode", "ptts_decode_latents", "ptts_mimi_encode_to_latent", "ptts_seq_frames", "ptts_seq_kv_len", "ptts_seq_read_kv",
     "ptts_seq_close", "ptts_stage_times_get", "ptts_debug_fetch", "ptts_profile_enable", "ptts_profile_report",
     "ptts_voice_cache_stats", "ptts_debug_gemm", "ptts_debug_gemm_bench", "ptts_debug_tc_force", "ptts_debug_gemm_tma",
     "ptts_pool_create", "ptts_pool_destroy", "ptts_pool_size", "ptts_pool_engine", "ptts_pool_load_tensor",
@@ -569,6 +569,14 @@ class NativeCudaRuntime:
         _check(self._lib.ptts_decode_latents(self._h, _fptr(lat), fps.ctypes.data_as(C.POINTER(C.c_int32)),
                                              fps.size, _fptr(pcm)))
         return pcm
+
+    def encode_to_latent(self, pcm: np.ndarray) -> np.ndarray:
+        """MimiModel.EncodeToLatent (mimi.go:791-794): not implemented in the reference's native backend either;
+        raises with ErrMimiEncoderNotImplemented's text."""
+        a = np.ascontiguousarray(pcm, dtype=np.float32).ravel()
+        out = np.empty((max(a.size // SAMPLES_PER_FRAME, 1), LATENT_DIM), np.float32)
+        _check(self._lib.ptts_mimi_encode_to_latent(self._h, _fptr(a), C.c_int64(a.size), _fptr(out), out.shape[0]))
+        return out
 
     def stage_times(self, reset: bool = False) -> dict:
         t = PttsStageTimes()

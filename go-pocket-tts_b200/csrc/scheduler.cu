@@ -842,6 +842,13 @@ int ptts_decode(ptts_engine *e, ptts_seq *seq, int32_t first_frame, int32_t n_fr
   return PTTS_OK;
 }
 
+// mimi.go:14,791-794: the reference's native Mimi encoder is a hook that returns this error.
+int ptts_mimi_encode_to_latent(ptts_engine *e, const float *, int64_t, float *, int32_t) {
+  if (!e)
+    PTTS_FAIL(PTTS_EINVAL, "native-cuda runtime unavailable");
+  PTTS_FAIL(PTTS_ESTATE, "native mimi encoder is not implemented");
+}
+
 int ptts_decode_latents(ptts_engine *e, const float *latents, const int32_t *frames_per_seq,
                         int32_t n_seqs, float *pcm_out) {
   if (!e || !e->impl.finalized)

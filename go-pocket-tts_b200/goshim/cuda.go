@@ -262,6 +262,19 @@ func (e *Engine) Wait(t *Ticket) ([]float32, int, error) {
 // Cancel evicts the request at the next step boundary.
 func (e *Engine) Cancel(t *Ticket) { C.ptts_cancel(e.h, t.id) }
 
+// EncodeToLatent mirrors native.MimiModel.EncodeToLatent (internal/native/mimi.go:791-794): the native backend
+// has no Mimi encoder; the error text is ErrMimiEncoderNotImplemented's.
+func (e *Engine) EncodeToLatent(pcm []float32) ([]float32, error) {
+	var p *C.float
+	if len(pcm) > 0 {
+		p = (*C.float)(unsafe.Pointer(&pcm[0]))
+	}
+	err := locked(func() C.int {
+		return C.ptts_mimi_encode_to_latent(e.h, p, C.int64_t(len(pcm)), nil, 0)
+	})
+	return nil, err
+}
+
 // Read blocks until more than have frames of PCM are valid (or the request is done) and returns the
 // new frame count; samples [have*1920, ready*1920) of the returned slice are the freshly decoded
 // audio.  This is what lets Service.SynthesizeStream (internal/tts/service.go:161-200) emit a

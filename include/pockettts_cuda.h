@@ -273,6 +273,12 @@ int ptts_decode(ptts_engine *e, ptts_seq *seq, int32_t first_frame,
 int ptts_decode_latents(ptts_engine *e, const float *latents,
                         const int32_t *frames_per_seq, int32_t n_seqs,
                         float *pcm_out);
+/* MimiModel.EncodeToLatent (internal/native/mimi.go:791-794): the reference's native backend leaves the Mimi
+ * encoder as a hook and returns ErrMimiEncoderNotImplemented ("native mimi encoder is not implemented",
+ * mimi.go:14); voices come in as embeddings or model states (a9).  Mirrored with the same behaviour: always
+ * PTTS_ESTATE and that message, nothing is written to latents_out. */
+int ptts_mimi_encode_to_latent(ptts_engine *e, const float *pcm, int64_t n_samples, float *latents_out,
+                               int32_t cap_frames);
 int ptts_seq_frames(ptts_seq *s);
 int ptts_seq_kv_len(ptts_seq *s);
 /* Parity tap: valid K or V rows of one layer as [H, kv_len, Dh]. */

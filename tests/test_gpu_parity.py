@@ -735,3 +735,11 @@ def test_caller_owned_pcm_buffer(small_rt, pkg):
     for bad in (np.zeros(5 * 1920, np.float32), np.zeros(8 * 1920, np.float64), np.zeros((8, 1920), np.float32)):
         with pytest.raises(pkg.NativeCudaError):
             small_rt.generate(toks, pkg.RuntimeGenerateConfig(pcm_out=bad, **kw))
+
+
+def test_mimi_encoder_is_the_reference_hook(small_rt, pkg):
+    """mimi.go:14,791-794: EncodeToLatent returns ErrMimiEncoderNotImplemented in the reference's native backend."""
+    with pytest.raises(pkg.NativeCudaError) as ei:
+        small_rt.encode_to_latent(np.zeros(1920, np.float32))
+    assert ei.value.status == pkg.PTTS_ESTATE
+    assert "native mimi encoder is not implemented" in str(ei.value)
