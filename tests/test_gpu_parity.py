@@ -679,8 +679,8 @@ def test_weight_ring_frame_kernel_small_model(pkg, small_tensors, monkeypatch):
 
 
 def test_decode_attention_variants_are_bit_identical(pkg, small_tensors, monkeypatch):
-    """The decode-attention kernels over the fp16 cache — page-wise loops for 16-token pages (default,
-    attend_row_pages16), two heads per CTA (PTTS_ATTN_PAIRS=1), the generic attend_row with shift / mask page arithmetic (PTTS_ATTN_NO_PAGEWISE=1) and the
+    """The decode-attention kernels over the fp16 cache — page-wise loops for 16-token pages (attend_row_pages16),
+    two heads per CTA (PTTS_ATTN_PAIRS=1), the generic attend_row with shift / mask page arithmetic (PTTS_ATTN_NO_PAGEWISE=1) and the
     cp.async-staged one (PTTS_ATTN_STAGED=1, attention_decode.cu) — share thread-to-element assignment and
     summation order: 24 ragged sequences stepped together for 70 frames through the stage API (a fixed batch, so
     every GEMM takes the same tiles in every run) give the same latents bit for bit; kv grows from 4..19 to
@@ -705,7 +705,10 @@ def test_decode_attention_variants_are_bit_identical(pkg, small_tensors, monkeyp
                 q.close()
             rt.close()
 
-    a = run()  # default: one head per CTA, page-wise loops (attend_row_pages16)
+    f = run()  # default at this batch size (24 rows): one-pass flash decoding, another summation order
+    monkeypatch.setenv("PTTS_ATTN_FLASH_MAX_ROWS", "0")
+    a = run()  # one head per CTA, page-wise loops (attend_row_pages16): the default above 96 rows
+    assert np.abs(f - a).max() <= 2e-4, float(np.abs(f - a).max())  # 70 fed-back frames apart by rounding only
     a2 = run()
     np.testing.assert_array_equal(a, a2)  # the comparison below is meaningful: the path is deterministic
     monkeypatch.setenv("PTTS_ATTN_PAIRS", "1")
