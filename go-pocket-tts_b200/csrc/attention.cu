@@ -191,146 +191,6 @@ __device__ __forceinline__ void attend_row_pages16(const float *q, int nkeys, co
   }
 }
 
-// One (row, head) of decode attention in ONE pass over 16-token pages (flash-decoding inside the CTA): the 16
-// groups of 8 lanes are 16 independent softmax streams — warp w takes pages w, w + 4, ..., group g of the warp
-// rows g, g + 4, g + 8, g + 12 of the page — each with its own running max, denominator and 64-wide accumulator
-// (8 elements per lane); K and V rows of a page are requested together, and the streams are combined once at the
-// end.  One block barrier instead of six and half the dependent memory round trips per CTA: this is what bounds
-// the kernel when there are too few (row, head) pairs to hide a CTA's latency chain (small batches).  The
-// summation order differs from attend_row's (not bit-identical to it; same tolerance against the oracle).
-// 8 consecutive K / V elements as loaded (registers: 4 for fp16, 8 for fp32), unpacked to fp32 where they are used
-template <typename KT>
-struct KvRaw8;
-template <>
-struct KvRaw8<__half> {
-  uint4 u;
-  __device__ __forceinline__ void load(const __half *p) { u = *reinterpret_cast<const uint4 *>(p); }
-  __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&u.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&u.w));
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-  }
-};
-template <>
-struct KvRaw8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float *p) {
-    a = *reinterpret_cast<const float4 *>(p);
-    b = *reinterpret_cast<const float4 *>(p + 4);
-  }
-  __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-};
-
-template <typename KT>
-__device__ __forceinline__ void attend_row_flash16(const float *q, int nkeys, const KT *kbase, const KT *vbase,
-                                                   const int32_t *s_pt, long page_stride, float *out, float *comb,
-                                                   const SplitOut &sp, long sp_row, int sp_col) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int part = lane & 7, g = lane >> 3;
-  const float scale = 0.125f; // 1/sqrt(64)
-  const int npages = (nkeys + 15) >> 4;
-  float qv[8];
-  {
-    const float4 a = *reinterpret_cast<const float4 *>(q + part * 8), b = *reinterpret_cast<const float4 *>(q + part * 8 + 4);
-    qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
-  }
-  float m = -INFINITY, l = 0.0f, acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; e++)
-    acc[e] = 0.0f;
-  const long roff = (long)g * HD + part * 8;
-  for (int p = warp; p < npages; p += 4) {
-    const long base = (long)s_pt[p] * page_stride + roff;
-    const int left = nkeys - p * 16 - g; // rows g + 4 i of this page are valid while 4 i < left
-    KvRaw8<KT> kr[4], vr[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (4 * i < left) {
-        kr[i].load(kbase + base + (long)(4 * i) * HD);
-        vr[i].load(vbase + base + (long)(4 * i) * HD);
-      }
-    float sc[4], pm = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      float s = 0.0f;
-      if (4 * i < left) {
-        float kf[8];
-        kr[i].unpack(kf);
-#pragma unroll
-        for (int e = 0; e < 8; e++)
-          s = fmaf(qv[e], kf[e], s);
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      sc[i] = 4 * i < left ? s * scale : -INFINITY;
-      pm = fmaxf(pm, sc[i]);
-    }
-    if (left > 0) { // (a stream's page always has its first row unless the page ends before row g)
-      const float mn = fmaxf(m, pm);
-      const float rescale = expf(m - mn); // 0 on the stream's first page (m = -inf)
-      l *= rescale;
-#pragma unroll
-      for (int e = 0; e < 8; e++)
-        acc[e] *= rescale;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (4 * i < left) {
-          const float pe = expf(sc[i] - mn);
-          l += pe;
-          float vf[8];
-          vr[i].unpack(vf);
-#pragma unroll
-          for (int e = 0; e < 8; e++)
-            acc[e] = fmaf(pe, vf[e], acc[e]);
-        }
-      m = mn;
-    }
-  }
-  // ---- combine the 16 streams: comb = [16][64] accumulators | [16] max | [16] denominators ----
-  const int stream = warp * 4 + g;
-  float *cm = comb + 16 * HD, *cl = cm + 16;
-#pragma unroll
-  for (int e = 0; e < 8; e += 4)
-    *reinterpret_cast<float4 *>(comb + stream * HD + part * 8 + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
-  if (part == 0) {
-    cm[stream] = m;
-    cl[stream] = l;
-  }
-  __syncthreads();
-  if (tid < 16) {
-    float M = -INFINITY;
-#pragma unroll
-    for (int s2 = 0; s2 < 16; s2++)
-      M = fmaxf(M, cm[s2]);
-    float den = 0.0f;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int s2 = 0; s2 < 16; s2++) {
-      const float ms = cm[s2];
-      if (ms == -INFINITY)
-        continue; // a stream that saw no key
-      const float wgt = expf(ms - M);
-      den = fmaf(wgt, cl[s2], den);
-      const float4 a = *reinterpret_cast<const float4 *>(comb + s2 * HD + tid * 4);
-      r.x = fmaf(wgt, a.x, r.x);
-      r.y = fmaf(wgt, a.y, r.y);
-      r.z = fmaf(wgt, a.z, r.z);
-      r.w = fmaf(wgt, a.w, r.w);
-    }
-    const float inv = 1.0f / den;
-    r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
-    if (out)
-      *reinterpret_cast<float4 *>(out + tid * 4) = r;
-    if (sp.hi)
-      split_store4(sp, sp_row, sp_col + tid * 4, r);
-  }
-}
-
 // MODE 0: any page size (integer division); 1: power-of-two pages (shift / mask); 2: 16-token pages, page-wise loops;
 // 3: 16-token pages, one-pass flash decoding (attend_row_flash16).
 template <typename KT, int MODE>

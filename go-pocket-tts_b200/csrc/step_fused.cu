@@ -460,7 +460,10 @@ __global__ void __launch_bounds__(FT, 2)
       const __half *pool = static_cast<const __half *>(kv.pool);
       auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
       auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
-      attend_row(q_s, pos + 1, keyp, valp, P.att + h * HD, dsm, red, pv, SplitOut(), 0, 0);
+      if (PT == 16) // one pass, one block barrier (attend.cuh): this phase is a latency chain on 16 CTAs
+        attend_row_flash16(q_s, pos + 1, pool + koff, pool + voff, pt, page_stride, P.att + h * HD, dsm, SplitOut(), 0, 0);
+      else
+        attend_row(q_s, pos + 1, keyp, valp, P.att + h * HD, dsm, red, pv, SplitOut(), 0, 0);
     }
     // ---- x += out_proj(att) ----
     grid_arrive(bar);
@@ -808,7 +811,11 @@ __global__ void __launch_bounds__(FT, 2)
       const __half *pool = static_cast<const __half *>(kv.pool);
       auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
       auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
-      attend_row(q_s, pos + 1, keyp, valp, nullptr, dsm, red, pv, SplitOut(), 0, 0, P.ll_att + h * HD, T);
+      if (PT == 16)
+        attend_row_flash16(q_s, pos + 1, pool + koff, pool + voff, pt, page_stride, (float *)nullptr, dsm, SplitOut(), 0,
+                           0, P.ll_att + h * HD, T);
+      else
+        attend_row(q_s, pos + 1, keyp, valp, nullptr, dsm, red, pv, SplitOut(), 0, 0, P.ll_att + h * HD, T);
       __syncthreads(); // scores (dsm) are restaged as the activation vector below
     }
     const unsigned t_att = T;

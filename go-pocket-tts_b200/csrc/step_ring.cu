@@ -500,7 +500,10 @@ __global__ void __launch_bounds__(RING_BLOCK, 1)
       const __half *pool = static_cast<const __half *>(kv.pool);
       auto keyp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + koff + (long)(j % PT) * HD; };
       auto valp = [&](int j) { return pool + (long)pt[j / PT] * page_stride + voff + (long)(j % PT) * HD; };
-      attend_row(q_s, pos + 1, keyp, valp, P.att + h * HD, sA, red, pv, SplitOut(), 0, 0);
+      if (PT == 16)
+        attend_row_flash16(q_s, pos + 1, pool + koff, pool + voff, pt, page_stride, P.att + h * HD, sA, SplitOut(), 0, 0);
+      else
+        attend_row(q_s, pos + 1, keyp, valp, P.att + h * HD, sA, red, pv, SplitOut(), 0, 0);
     }
     // ---- x += out_proj(att) ----
     PHASE_BEGIN();
