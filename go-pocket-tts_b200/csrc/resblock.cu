@@ -263,13 +263,26 @@ __global__ void __launch_bounds__(rb_threads(C), 1)
       const int b = k & 1;
       const int m0 = ((int)blockIdx.x + k * (int)gridDim.x) * TC_BM;
       uint32_t rows = 0;
+      // one integer division per tile and thread instead of eight (the epilogue is what bounds this kernel):
+      // the eight rows are 4 apart, so quotient and remainder by mask_div are carried along
+      int mq = 0, mr = 0;
+      if (g.rowmask) {
+        const int mb = m0 + q * 32 + rsub;
+        mq = mb / g.mask_div;
+        mr = mb - mq * g.mask_div;
+      }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int m = m0 + q * 32 + j * 4 + rsub;
         if (m < M) {
           rows |= 1u << j;
-          if (!g.rowmask || g.rowmask[m / g.mask_div])
+          if (!g.rowmask || g.rowmask[mq])
             rows |= 0x100u << j;
+        }
+        mr += 4;
+        while (mr >= g.mask_div) {
+          mr -= g.mask_div;
+          mq++;
         }
       }
       const bool fullrows = __all_sync(0xffffffffu, (rows & 0xFFu) == 0xFFu);

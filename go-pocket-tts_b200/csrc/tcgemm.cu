@@ -378,13 +378,28 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
           int kb_begin, nkb, z, tile;
           items.decode((int)blockIdx.x + li2 * (int)gridDim.x, im0, in0, kb_begin, nkb, z, tile, BN);
           rows_item = 0;
+          // masked (Mimi conv) launches: one integer division per item and thread, quotient / remainder carried
+          // along the eight rows (4 apart); unmasked launches (the AR step) skip all of it
+          int mq = 0, mr = 0;
+          if (e.rowmask) {
+            const int mb = im0 + q * 32 + rsub;
+            mq = mb / e.mask_div;
+            mr = mb - mq * e.mask_div;
+          }
 #pragma unroll
           for (int jj = 0; jj < 8; jj++) {
             const int m = im0 + q * 32 + jj * 4 + rsub;
             if (m < M) {
               rows_item |= 1u << jj;
-              if (!e.rowmask || e.rowmask[m / e.mask_div])
+              if (!e.rowmask || e.rowmask[mq])
                 rows_item |= 0x100u << jj;
+            }
+            if (e.rowmask) {
+              mr += 4;
+              while (mr >= e.mask_div) {
+                mr -= e.mask_div;
+                mq++;
+              }
             }
           }
           full_item = __all_sync(0xffffffffu, (rows_item & 0xFFu) == 0xFFu);
@@ -466,13 +481,26 @@ __global__ void __launch_bounds__(tc_threads(EW, ATMA), 1)
       const int b = (int)(li & 1);
       // row state of the 8 rows this lane touches: bit j = in range, bit 8+j = live (not masked)
       uint32_t rows = 0;
+      int mq = 0, mr = 0; // see the epilogue above
+      if (e.rowmask) {
+        const int mb = m0 + q * 32 + rsub;
+        mq = mb / e.mask_div;
+        mr = mb - mq * e.mask_div;
+      }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int m = m0 + q * 32 + j * 4 + rsub;
         if (m < M) {
           rows |= 1u << j;
-          if (!e.rowmask || e.rowmask[m / e.mask_div])
+          if (!e.rowmask || e.rowmask[mq])
             rows |= 0x100u << j;
+        }
+        if (e.rowmask) {
+          mr += 4;
+          while (mr >= e.mask_div) {
+            mr -= e.mask_div;
+            mq++;
+          }
         }
       }
       const bool full = __all_sync(0xffffffffu, (rows & 0xFFu) == 0xFFu);
