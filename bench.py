@@ -404,7 +404,10 @@ def main():
                                    for k in ("prefill_ms", "step_ms", "flow_head_ms", "mimi_ms", "d2h_ms")},
             "stage_note": "device time per stage over the K timed steps (CUDA events; flow_head_ms is the part of "
                           "step_ms after the transformer, d2h_ms the PCM copies on the copy stream, which overlap "
-                          "compute); the value leg leaves PCM on the device, so its d2h_ms is 0 by construction",
+                          "compute); the value leg leaves PCM on the device, so its d2h_ms is 0 by construction; "
+                          "mimi_ms runs on its own stream beside step_ms, so the stages do not add up to the wall "
+                          "time, and with programmatic dependent launch the in-graph event that splits off "
+                          "flow_head_ms sits at a full (non-programmatic) dependency, so the split is approximate",
             "mean_batch_occupancy": st["step_rows"] / max(st["steps"], 1),
             "steps_per_s_rank0": st["steps"] / (ms / 1e3),
             "realtime_factor_per_gpu": value / n_gpus_job,
