@@ -106,10 +106,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // The hot configurations are compiled as straight-line code (activation ACT, output set
 // MASK: 1 = C, 2 = Cs, 4 = C2, 8 = C2s, FULL = all 8 rows in range); anything else (adaLN
 // gate `mul`, `alpha`, unusual output sets) takes the generic path with runtime checks.
-// ELU with the hardware exponential (ex2.approx): abs error ~1e-7 on values in (-1, 0],
-// far inside the waveform tolerance; the full-precision expf was most of the epilogue's
-// instructions on the HBM-bound SEANet layers.
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.0f ? v : __expf(v) - 1.0f; }
+// ELU with the hardware exponential: abs error ~1e-7 on values in (-1, 0], far inside the waveform tolerance;
+// the full-precision expf was most of the epilogue's instructions on the HBM-bound SEANet layers.
+// exp is ex2.approx.ftz(v * log2 e): __expf is the same product and the same MUFU, but its non-ftz
+// ex2 wraps the MUFU in denormal scaling (two more FMUL and an FSETP per element — a fifth of the instructions of
+// the conv epilogues, which are what bounds the SEANet kernels).  For v <= 0 the results differ only where
+// exp(v) or v itself is denormal: exp(v) - 1 is -1 either way, and an input below 1e-38 gives 0 instead of v.
+__device__ __forceinline__ float elu_fast(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(v, 1.4426950216293335f)));
+  return v > 0.0f ? v : e - 1.0f;
+}
 __device__ __forceinline__ float4 elu4(const float4 &o) {
   return make_float4(elu_fast(o.x), elu_fast(o.y), elu_fast(o.z), elu_fast(o.w));
 }
